@@ -1,0 +1,68 @@
+#!/usr/bin/env bash
+# oracle/build_ref.sh — TEST INFRASTRUCTURE, not product code.
+#
+# Compiles the reference's own matcher (Xapiand's vendored Xapian 1.5.0,
+# /root/reference/src/xapian) from the sources WHERE THEY LIE into oracle/_ref/:
+#   oracle/_ref/libxapian_ref.so   the reference Xapian library (api, matcher, weight, backends …)
+#   oracle/_ref/gen/               generated headers (error.h via the reference's own perl generator)
+# Nothing from /root/reference is copied into the repository; oracle/_ref/ is git-ignored but
+# travels to the GPU box with gpurun.  Recipe = SURVEY.md Appendix A (the reference's own CMake
+# build is NOT run: it needs libuuid headers, tclsh and GTest which this image lacks).
+# Flags follow the reference release flags (CMakeLists.txt:99-104: -std=c++17 -O3 -DNDEBUG).
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF="${XGM_REFERENCE:-/root/reference}"
+R="$REF/src"
+O="$HERE/_ref"
+JOBS="${JOBS:-$(nproc)}"
+
+if [ ! -d "$R/xapian" ]; then
+  echo "build_ref: $R/xapian not present (GPU box?) — keeping prebuilt $O" >&2
+  exit 0
+fi
+if [ -f "$O/libxapian_ref.so" ] && [ "${FORCE:-0}" != "1" ]; then
+  echo "build_ref: $O/libxapian_ref.so already built (FORCE=1 to rebuild)"
+  exit 0
+fi
+
+mkdir -p "$O/gen/xapian/unicode" "$O/gen/xapian/languages" "$O/obj"
+cp "$HERE/ref_config.h" "$O/gen/config.h"
+# generated headers, by the reference's own generators (CMakeLists.txt:402-412, 472-479)
+(cd "$O/gen" && perl -w -I "$R/xapian" "$R/xapian/generate-exceptions")
+perl "$R/xapian/unicode/gen_c_istab" "$O/gen/xapian/unicode/c_istab.h"
+printf '#define LANGSTRING "none"\n' > "$O/gen/xapian/languages/sbl-dispatch.h"
+
+# link-only stubs for symbols that live in parts of Xapian needing tclsh/lemon/snowball outputs
+# (queryparser, languages, unicode-data); never reached by matching.
+cat > "$O/gen/ref_stubs.cc" <<'STUB'
+#include "config.h"
+#include <cstdlib>
+#include <string>
+#include "xapian.h"
+#include "xapian/api/msetinternal.h"
+namespace Xapian {
+RangeProcessor::~RangeProcessor() {}
+Stem::Stem(const Stem& o) : internal(o.internal) {}
+Stem::~Stem() {}
+std::string Stem::operator()(const std::string& w) const { return w; }
+std::string Stopper::get_description() const { return "Stopper"; }
+std::string MSet::Internal::snippet(const std::string&, size_t, const Stem&, unsigned,
+                                    const std::string&, const std::string&, const std::string&) const { abort(); }
+}
+STUB
+
+DIRS="api matcher weight common backends backends/glass backends/inmemory backends/multi backends/honey backends/remote net expand geospatial diversify cluster"
+FILES=""
+for d in $DIRS; do FILES="$FILES $(ls "$R"/xapian/$d/*.cc)"; done
+FILES="$FILES $R/xapian/unicode/description_append.cc $R/xapian/unicode/utf8itor.cc $O/gen/ref_stubs.cc"
+
+CXXFLAGS="-std=c++17 -O3 -DNDEBUG -fPIC -w -include limits -include cstdint -I$O/gen -I$R"
+: > "$O/obj/.list"
+for f in $FILES; do
+  o="$O/obj/$(echo "${f#$R/}" | tr '/' '_' | sed 's/\.cc$/.o/')"
+  echo "$f $o" >> "$O/obj/.list"
+done
+# compile in parallel
+xargs -P "$JOBS" -L 1 bash -c 'if [ ! -f "$1" ] || [ "$0" -nt "$1" ]; then g++ '"$CXXFLAGS"' -c "$0" -o "$1" || exit 255; fi' < "$O/obj/.list"
+g++ -shared -o "$O/libxapian_ref.so" $(awk '{print $2}' "$O/obj/.list") -lz -lpthread
+echo "build_ref: built $O/libxapian_ref.so ($(wc -l < "$O/obj/.list") objects)"
