@@ -1,0 +1,220 @@
+/* xgm.h — C-ABI of the B200-native inverted-index matcher (libxgm.so).
+ *
+ * This is the drop-in boundary for ONE path of Kronuz/Xapiand: everything from
+ * Matcher::get_local_mset (src/xapian/matcher/matcher.cc:346-542) downward — PostList tree
+ * construction, GlassPostList iteration, MultiAndPostList / OrPostList advance,
+ * BM25Weight::get_sumpart, ProtoMSet top-k — for the query shapes listed below.  The reference's
+ * Xapian::Enquire / MSet surface and Xapiand's DatabaseHandler::get_mset
+ * (src/database/handler.cc:1414-1553) stay above it unchanged; INTEGRATION.md shows the shim a
+ * maintainer adds inside Matcher::get_local_mset.
+ *
+ * Conventions: plain C types, no C++ exceptions cross the boundary, every entry point returns an
+ * xgm_status (0 = ok).  Handles are opaque.  An xgm_index is immutable after xgm_builder_finish /
+ * xgm_index_load and may be shared by any number of host threads; an xgm_searcher (stream +
+ * staging buffers) must be used by one thread at a time — the same rule as one Xapian::Enquire per
+ * thread (src/database/lock.h:59-75 serialises a shard checkout).
+ *
+ * The CUDA path is the only path: there is no CPU fallback.  Query shapes the kernels do not cover
+ * return XGM_E_UNIMPLEMENTED so the shim can throw Xapian::UnimplementedError and leave the query
+ * to the reference's own matcher.
+ */
+#ifndef XGM_H
+#define XGM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XGM_ABI_VERSION 1
+#define XGM_MAX_TERMS 16u      /* leaves per query handled on the device */
+#define XGM_MAX_TOPK 4096u     /* first + maxitems */
+
+typedef enum xgm_status {
+    XGM_OK = 0,
+    XGM_E_INVALID = 1,        /* bad argument */
+    XGM_E_UNIMPLEMENTED = 2,  /* query shape not covered → reference matcher should run it */
+    XGM_E_CUDA = 3,           /* CUDA runtime failure (→ Xapian::DatabaseError) */
+    XGM_E_NOMEM = 4,
+    XGM_E_IO = 5,
+    XGM_E_STALE = 6,          /* revision mismatch (→ Xapian::DatabaseModifiedError) */
+    XGM_E_NODEVICE = 7        /* no CUDA device: this library has no CPU path */
+} xgm_status;
+
+typedef struct xgm_builder xgm_builder;
+typedef struct xgm_index xgm_index;
+typedef struct xgm_searcher xgm_searcher;
+
+/* ---- error text ------------------------------------------------------------------------- */
+/* Thread-local description of the last failure on the calling thread (never NULL). */
+const char* xgm_last_error(void);
+uint32_t xgm_abi_version(void);
+
+/* ---- index construction ------------------------------------------------------------------
+ * Replaces the read side of GlassPostList (src/xapian/backends/glass/glass_postlist.cc:722-991):
+ * the shim walks the glass DB once through Database::allterms_begin / postlist_begin /
+ * get_doclength / valuestream_begin and hands the flat postings over; docids/wdfs are what
+ * PostingIterator::operator* / get_wdf return. */
+xgm_status xgm_builder_new(xgm_builder** out);
+/* doclen[docid] for docid in [0, lastdocid]; entry 0 unused; 0 for unused docids.
+ * Database::get_doccount/get_lastdocid/get_total_length/get_doclength_{lower,upper}_bound. */
+xgm_status xgm_builder_set_docs(xgm_builder*, uint32_t doccount, uint32_t lastdocid,
+                                uint64_t total_length, uint32_t doclen_lower_bound,
+                                uint32_t doclen_upper_bound, const uint32_t* doclen);
+/* One term's posting list, docids strictly ascending.  wdf_upper_bound = the reference's
+ * Database::get_wdf_upper_bound(term) (glass_database.cc:822-829); pass 0 to have it derived the
+ * same way from (termfreq, collfreq, first wdf, max wdf over the index). */
+xgm_status xgm_builder_add_term(xgm_builder*, const char* term, uint32_t term_len,
+                                const uint32_t* docids, const uint32_t* wdfs, uint32_t n,
+                                uint64_t collfreq, uint32_t wdf_upper_bound, uint32_t* term_id);
+/* Numeric value slot: for every docid up to `nvals[docid]` (0..255) order-preserving u64 keys,
+ * ascending, laid out CSR-style: keys of docid d are vals[voff[d] .. voff[d+1]).  This is the
+ * decoded form of Xapiand's StringList of sortable_serialise()d numbers
+ * (src/serialise_list.h:301-356, src/sortable_serialise.cc). */
+xgm_status xgm_builder_add_value_slot(xgm_builder*, uint32_t slot, const uint64_t* voff /*[lastdocid+2]*/,
+                                      const uint64_t* vals);
+/* Compress into the HBM block format and upload to `device`. Consumes the builder. */
+xgm_status xgm_builder_finish(xgm_builder*, int device, xgm_index** out);
+void xgm_builder_free(xgm_builder*);
+
+/* Synthetic Zipfian corpus of BASELINE.md §3 (xgm_corpus.h), shard `shard` of `nshards`
+ * (interleaved docids, src/xapian/backends/multi.h:37-70), built directly into an index. */
+xgm_status xgm_index_build_synthetic(uint32_t ndocs, uint32_t vocab, uint64_t seed, uint32_t nshards,
+                                     uint32_t shard, int with_values, int device, int host_threads,
+                                     xgm_index** out);
+/* XGMFLAT1 file (oracle/ref_runner `export`: a glass DB dumped through the public iterators). */
+xgm_status xgm_index_load_flat(const char* path, int device, xgm_index** out);
+void xgm_index_close(xgm_index*);
+
+typedef struct xgm_index_info {
+    uint32_t doccount, lastdocid;
+    uint64_t total_length;
+    uint32_t doclen_lower_bound, doclen_upper_bound;
+    uint32_t nterms;
+    uint64_t npostings;
+    uint64_t nblocks;
+    uint64_t bytes_docids, bytes_wdfs, bytes_headers, bytes_doclen; /* HBM footprint by column */
+    int device;
+    uint64_t revision;
+} xgm_index_info;
+xgm_status xgm_index_info_get(const xgm_index*, xgm_index_info* out);
+
+typedef struct xgm_term_stats {
+    uint32_t term_id;
+    uint32_t termfreq;       /* GlassPostListTable::get_freqs glass_postlist.cc:150-192 */
+    uint64_t collfreq;
+    uint32_t wdf_upper_bound;
+    uint64_t bytes;          /* compressed HBM bytes of this term (docids + wdfs + headers) */
+} xgm_term_stats;
+/* Returns XGM_OK with termfreq == 0 for an unknown term (like Database::get_termfreq). */
+xgm_status xgm_term_stats_get(const xgm_index*, const char* term, uint32_t term_len, xgm_term_stats* out);
+/* Round-trip check: decode a term's posting list on the device back into flat arrays (capacity n). */
+xgm_status xgm_index_decode_term(const xgm_index*, uint32_t term_id, uint32_t* docids, uint32_t* wdfs,
+                                 uint32_t capacity, uint32_t* n);
+
+/* ---- queries ------------------------------------------------------------------------------ */
+enum { XGM_OP_AND = 0, XGM_OP_OR = 1 };                      /* Query::OP_AND / OP_OR of LEAF_TERMs */
+enum { XGM_SORT_REL = 0, XGM_SORT_VAL_REL = 1, XGM_SORT_VAL = 2, XGM_SORT_REL_VAL = 3 };
+                                                              /* Enquire::Internal::sort_setting */
+enum { XGM_FILTER_NONE = 0,
+       XGM_FILTER_VALUE_RANGE = 1,  /* OP_FILTER(q, OP_VALUE_RANGE(slot, lo, hi)): first value in range,
+                                       src/xapian/matcher/valuerangepostlist.cc */
+       XGM_FILTER_MULTI_RANGE = 2   /* OP_FILTER(q, MultipleValueRange): src/multivalue/range.cc:351-368 */ };
+
+/* Collection statistics for Weight::init_ (src/xapian/weight/weight.cc:59-83).  NULL means "this
+ * index alone".  In Xapiand's two-phase scheme (src/database/handler.cc:1532-1551) the caller sums
+ * them over shards (Weight::Internal::operator+=, weightinternal.cc:54-72) and passes the totals. */
+typedef struct xgm_stats {
+    uint32_t collection_size;
+    uint64_t total_length;
+    const uint32_t* termfreq;   /* one per query term, in query order */
+} xgm_stats;
+
+typedef struct xgm_query {
+    uint32_t op;                 /* XGM_OP_* over the terms below */
+    uint32_t nterms;             /* 1..XGM_MAX_TERMS */
+    const char* const* terms;    /* term bytes; may be NULL if term_ids is given */
+    const uint32_t* term_lens;   /* NULL → NUL-terminated */
+    const uint32_t* term_ids;    /* optional pre-resolved ids (xgm_term_stats.term_id); UINT32_MAX = absent */
+    const uint32_t* wqf;         /* NULL → 1 each */
+    uint32_t first, maxitems, check_at_least;   /* Enquire::get_mset arguments */
+    const xgm_stats* stats;      /* NULL → local statistics */
+    double k1, k3, b, min_normlen; /* BM25Weight parameters; all 0 → defaults 1,1,0.5,0.5 (weight.h:665-667) */
+    uint32_t filter, filter_slot;
+    uint64_t range_lo, range_hi;
+    uint32_t sort_by, sort_slot, sort_reverse, sort_use_max; /* sort_use_max: key = largest value of the slot */
+} xgm_query;
+
+/* One query's result: the fields of MSet::Internal (src/xapian/api/msetinternal.h:58-99). */
+typedef struct xgm_mset_info {
+    uint32_t n;                    /* items written (after dropping `first`) */
+    uint32_t first;
+    uint32_t matches_lower_bound, matches_estimated, matches_upper_bound;
+    uint32_t uncollapsed_lower_bound, uncollapsed_estimated, uncollapsed_upper_bound;
+    uint32_t exact_matches;        /* documents matching the boolean structure */
+    uint32_t status;               /* xgm_status for this query */
+    double max_possible, max_attained, percent_scale_factor;
+} xgm_mset_info;
+
+/* ---- searching ---------------------------------------------------------------------------- */
+/* A searcher owns a CUDA stream and pinned/device staging for batches of up to max_batch queries
+ * with first+maxitems <= max_topk each. */
+xgm_status xgm_searcher_new(const xgm_index*, uint32_t max_batch, uint32_t max_topk, xgm_searcher** out);
+void xgm_searcher_free(xgm_searcher*);
+
+/* Asynchronous batch: plan on the host, copy the plan to the device, launch the kernels, start the
+ * device→host copy of the results.  Returns as soon as the work is enqueued. */
+xgm_status xgm_search_submit(xgm_searcher*, const xgm_query* queries, uint32_t nq);
+/* Wait for the submitted batch and scatter results: docids/weights hold `stride` entries per query
+ * (query i at [i*stride, i*stride + info[i].n)); sort_keys may be NULL. */
+xgm_status xgm_search_wait(xgm_searcher*, uint32_t* docids, double* weights, uint64_t* sort_keys,
+                           uint32_t stride, xgm_mset_info* info);
+/* Convenience: submit + wait. */
+xgm_status xgm_search_batch(xgm_searcher*, const xgm_query* queries, uint32_t nq, uint32_t* docids,
+                            double* weights, uint64_t* sort_keys, uint32_t stride, xgm_mset_info* info);
+/* Single query, like Enquire::get_mset(first, maxitems, check_at_least). */
+xgm_status xgm_search(xgm_searcher*, const xgm_query* query, uint32_t* docids, double* weights,
+                      uint64_t* sort_keys, uint32_t capacity, xgm_mset_info* info);
+
+/* Device-resident variant used for throughput measurement and multi-GPU merging: the plan built by
+ * the last xgm_search_submit stays resident; xgm_search_replay relaunches the kernels on it without
+ * host work or copies, leaving results in device memory. */
+xgm_status xgm_search_replay(xgm_searcher*);
+/* Device pointers of the last batch's top-k records (first+maxitems stride = xgm_searcher max_topk):
+ * weights f64[nq*max_topk], docids u32[nq*max_topk], counts u32[nq] */
+xgm_status xgm_search_device_results(xgm_searcher*, void** weights, void** docids, void** counts,
+                                     uint32_t* stride);
+/* CUDA stream of the searcher (cudaStream_t as void*) and timing/roofline counters of the last batch. */
+void* xgm_searcher_stream(xgm_searcher*);
+typedef struct xgm_batch_stats {
+    uint64_t algorithmic_bytes;   /* sum over query terms of column bytes + 16*blocks, + 4*candidates + 16*k */
+    uint64_t postings;            /* sum of termfreqs over the batch */
+    uint32_t work_items;
+    uint32_t kernel_launches;
+    float match_kernel_ms;        /* CUDA-event time of the decode+intersect+score kernel(s) */
+    float topk_kernel_ms;
+} xgm_batch_stats;
+xgm_status xgm_search_last_stats(xgm_searcher*, xgm_batch_stats* out);
+
+/* ---- multi-shard merge (Matcher::merge_mset, src/xapian/matcher/matcher.cc:653-782) --------
+ * parts: nparts per-shard results for the same query, docids already unsharded
+ * (Xapian's unshard(), src/xapian/backends/multi.h:66-70, is applied by xgm_unshard). */
+void xgm_unshard(uint32_t* docids, uint32_t n, uint32_t shard, uint32_t nshards);
+xgm_status xgm_merge_msets(const uint32_t* const* docids, const double* const* weights,
+                           const uint64_t* const* sort_keys, const xgm_mset_info* infos, uint32_t nparts,
+                           uint32_t first, uint32_t maxitems, uint32_t sort_by, uint32_t sort_reverse,
+                           uint32_t* out_docids, double* out_weights, uint64_t* out_sort_keys,
+                           xgm_mset_info* out_info);
+/* Device-side merge after an all-gather of per-GPU top-k records: gathered weights/docids hold
+ * nparts*nq*stride records laid out [part][query][rank]; local docids are unsharded on the fly. */
+xgm_status xgm_merge_topk_device(const void* gathered_weights, const void* gathered_docids,
+                                 const void* gathered_counts, uint32_t nparts, uint32_t nq, uint32_t stride,
+                                 uint32_t k, void* out_weights, void* out_docids, void* out_counts,
+                                 void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XGM_H */

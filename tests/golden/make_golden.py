@@ -1,0 +1,107 @@
+"""Generate the golden fixtures in tests/golden/ by running the COMPILED REFERENCE (oracle/_ref:
+the reference's own Xapian built from /root/reference/src/xapian by oracle/build_ref.sh) on seeded
+synthetic corpora.  Only runs where oracle/_ref exists (this container); the fixtures it writes are
+committed so the oracle and the CUDA path can be checked against the reference anywhere.
+
+    python tests/golden/make_golden.py
+"""
+import json
+import os
+import random
+import shutil
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def name(r):
+    return f"T{r:06d}"
+
+
+def run_set(tag, ndocs, vocab, queries, nshards=1, twophase=False, values=False, seed=12345):
+    tmp = tempfile.mkdtemp(prefix="xgm_golden_")
+    try:
+        dbs = []
+        for s in range(nshards):
+            d = os.path.join(tmp, f"s{s}")
+            O.ref_build(d, ndocs, vocab, seed=seed, nshards=nshards, shard=s, values=values)
+            dbs.append(d)
+        lines = []
+        for q in queries:
+            lines.append(O.query_line("TERM" if len(q["terms"]) == 1 else q["op"], [name(t) for t in q["terms"]],
+                                      q["first"], q["maxitems"], q["check_at_least"], vr=q.get("vr"), sort=q.get("sort")))
+        info, res = O.ref_query(dbs, lines, os.path.join(tmp, "w"), twophase=twophase)
+        fixture = dict(tag=tag, ndocs=ndocs, vocab=vocab, seed=seed, nshards=nshards, twophase=twophase, values=values,
+                       queries=[])
+        for q, r in zip(queries, res):
+            e = dict(q)
+            e["docids"] = r.docids
+            e["weights"] = [float(w).hex() for w in r.weights]
+            if r.sort_keys:
+                e["sort_keys"] = r.sort_keys
+            e.update(lb=r.lb, est=r.est, ub=r.ub, max_possible=float(r.max_possible).hex(),
+                     max_attained=float(r.max_attained).hex())
+            fixture["queries"].append(e)
+        with open(os.path.join(OUT, f"{tag}.json"), "w") as f:
+            json.dump(fixture, f, separators=(",", ":"))
+        print(tag, len(queries), "queries", os.path.getsize(os.path.join(OUT, f"{tag}.json")), "bytes")
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def mixed(rng, n, topranks, ndocs, big_or_items):
+    qs = []
+    for i in range(n):
+        kind = i % 5
+        if kind == 0:
+            q = dict(op="AND", terms=rng.sample(range(topranks), 3), first=0, maxitems=100, check_at_least=0)
+        elif kind == 1:
+            q = dict(op="OR", terms=rng.sample(range(topranks), 5), first=0, maxitems=big_or_items, check_at_least=0)
+        elif kind == 2:
+            q = dict(op="AND", terms=rng.sample(range(topranks), 1), first=0, maxitems=10, check_at_least=0)
+        elif kind == 3:
+            q = dict(op=rng.choice(["AND", "OR"]), terms=rng.sample(range(topranks), rng.choice([2, 3, 4])),
+                     first=rng.choice([0, 3]), maxitems=rng.choice([1, 5, 20, 100]), check_at_least=ndocs)
+        else:
+            q = dict(op="AND", terms=rng.sample(range(topranks), 2), first=rng.choice([0, 0, 7]),
+                     maxitems=rng.choice([10, 30]), check_at_least=0)
+        qs.append(q)
+    return qs
+
+
+def main():
+    if not O.have_reference():
+        raise SystemExit("oracle/_ref not built: run oracle/build_ref.sh (needs /root/reference)")
+    rng = random.Random(20260923)
+    # C1: BASELINE config 1 — 1k docs / 100 terms, every single term top-10, plus mixed shapes
+    c1 = [dict(op="AND", terms=[t], first=0, maxitems=10, check_at_least=0) for t in range(100)]
+    c1 += mixed(rng, 60, 100, 1000, 50)
+    run_set("c1_1k_100", 1000, 100, c1)
+    run_set("mid_20k", 20000, 5000, mixed(rng, 120, 400, 20000, 200))
+    # Xapiand two-phase scheme over 4 interleaved shards (handler.cc:1485-1551)
+    sh = []
+    for i in range(60):
+        op = "AND" if i % 2 == 0 else "OR"
+        k = 3 if op == "AND" else 4
+        sh.append(dict(op=op, terms=rng.sample(range(300), k), first=rng.choice([0, 0, 5]), maxitems=rng.choice([10, 100]),
+                       check_at_least=rng.choice([0, 20000])))
+    run_set("shard4_20k", 20000, 5000, sh, nshards=4, twophase=True)
+    # value range filter + sort by value then relevance (stock OP_VALUE_RANGE / set_sort_by_value_then_relevance)
+    vq = []
+    for i in range(60):
+        lo = rng.randrange(0, 900000)
+        q = dict(op="AND", terms=rng.sample(range(60), 2), first=0, maxitems=rng.choice([10, 100]),
+                 check_at_least=rng.choice([0, 5000]), vr=[0, lo, lo + rng.choice([10000, 100000, 400000])])
+        if i % 3 != 2:
+            q["sort"] = [1, rng.choice([0, 1])]
+        vq.append(q)
+    run_set("values_5k", 5000, 2000, vq, values=True)
+
+
+if __name__ == "__main__":
+    main()

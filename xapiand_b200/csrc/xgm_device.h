@@ -1,0 +1,61 @@
+/* xgm_device.h — kernel parameter block and launcher prototypes (host <-> kernels, internal). */
+#ifndef XGM_DEVICE_H
+#define XGM_DEVICE_H
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "xgm_format.h"
+
+#define XGM_MAX_SLOTS 8
+
+struct XgmDevSlot {
+    const uint32_t* voff; /* [lastdocid+2] CSR offsets, NULL = slot absent */
+    const uint64_t* vals; /* order-preserving numeric keys, ascending per doc */
+};
+
+struct XgmDevResult {
+    uint32_t n;      /* entries written to out_* (<= topk) */
+    uint32_t exact;  /* documents matching the boolean structure */
+    uint32_t known;  /* ProtoMSet::known_matching_docs */
+    uint32_t flags;  /* bit0: match buffer overflowed (query must be re-run on the dense kernel) */
+    double max_w;    /* dense kernel: best weight seen */
+    uint32_t max_subqs;
+    uint32_t pad;
+};
+
+struct XgmKernelParams {
+    /* index */
+    const XgmBlockHdr* hdr;
+    const uint4* docs;
+    const uint4* tfs;
+    const uint32_t* doclen;
+    uint32_t lastdocid;
+    XgmDevSlot slots[XGM_MAX_SLOTS];
+    /* batch */
+    const XgmDevQuery* queries;
+    const XgmWorkItem* items;
+    uint32_t nitems;
+    uint32_t nq;
+    uint32_t* work_counter;
+    /* per-query match buffers (sparse AND kernel) */
+    uint32_t match_cap;
+    uint32_t* match_count;
+    double* match_w;
+    uint32_t* match_d;
+    uint64_t* match_k;
+    /* results */
+    uint32_t out_stride;
+    double* out_w;
+    uint32_t* out_d;
+    uint64_t* out_k;
+    XgmDevResult* out_info;
+};
+
+cudaError_t xgm_launch_and(const XgmKernelParams& p, int grid, cudaStream_t s);
+cudaError_t xgm_launch_topk(const XgmKernelParams& p, uint32_t nq, cudaStream_t s);
+cudaError_t xgm_launch_decode(const XgmKernelParams& p, uint32_t blk_begin, uint32_t nblocks, uint32_t* out_d,
+                              uint32_t* out_w, cudaStream_t s);
+size_t xgm_topk_smem_bytes(uint32_t match_cap);
+int xgm_and_occupancy_blocks_per_sm();
+
+#endif

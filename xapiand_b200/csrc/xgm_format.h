@@ -1,0 +1,68 @@
+/* xgm_format.h — HBM index layout and device-side query descriptors (shared by host and kernels).
+ *
+ * Posting lists (the reference's GlassPostList chunks, glass_postlist.cc:677-695: ~2000-byte chunks
+ * of vbyte (docid delta-1, wdf) pairs behind a B-tree) are re-laid-out for the GPU as three columns:
+ *
+ *   hdr[]   one 16-byte XgmBlockHdr per block of up to 128 postings, all terms back to back, each
+ *           term followed by one sentinel header (first = 0xFFFFFFFF) so "first docid of the next
+ *           block" is always readable — that is the skip table the warp-galloping search walks.
+ *   docs[]  per block 128 x doc_bits bits: delta-1 between consecutive docids (slot 0 = 0, the first
+ *           docid lives in the header), little-endian bit-packed, value i at bit i*doc_bits.  A block
+ *           is 16*doc_bits bytes, so every block starts 16-byte aligned (cp.async.bulk granularity).
+ *   tfs[]   per block 128 x tf_bits bits of wdf, same packing, separate column: the intersection
+ *           only touches it for documents that survive.
+ *   doclen[] dense u32 per docid (the reference keeps a second vbyte stream under key "\0\xe0",
+ *           glass_postlist.cc:194-205,994-1021).
+ */
+#ifndef XGM_FORMAT_H
+#define XGM_FORMAT_H
+#include <stdint.h>
+
+#define XGM_BLOCK 128u
+#define XGM_SENTINEL 0xFFFFFFFFu
+#define XGM_DEV_MAX_TERMS 16u
+
+struct XgmBlockHdr {
+    uint32_t first;    /* docid of the block's first posting */
+    uint32_t doc_off;  /* offset of the packed docid deltas, in 16-byte units into docs[] */
+    uint32_t tf_off;   /* offset of the packed wdfs, in 16-byte units into tfs[] */
+    uint32_t meta;     /* doc_bits | tf_bits << 8 | (count-1) << 16 */
+};
+
+#define XGM_HDR_DOC_BITS(m) ((m) & 0xffu)
+#define XGM_HDR_TF_BITS(m) (((m) >> 8) & 0xffu)
+#define XGM_HDR_COUNT(m) ((((m) >> 16) & 0xffu) + 1u)
+
+struct XgmDevTerm {
+    uint32_t blk_begin;   /* index of the term's first header in hdr[] */
+    uint32_t nblocks;     /* real blocks (the sentinel sits at blk_begin + nblocks) */
+    double termweight;    /* BM25Weight::init result, bm25weight.cc:46-130 (computed on the host) */
+};
+
+struct XgmDevQuery {
+    uint32_t op, nterms, topk, check_at_least;
+    double len_factor, k1, b, one_minus_b, min_normlen;
+    uint32_t filter, filter_slot;
+    uint64_t range_lo, range_hi;
+    uint32_t sort_by, sort_slot, sort_reverse, sort_use_max;
+    uint32_t prog_len;
+    int8_t prog[2 * XGM_DEV_MAX_TERMS]; /* OR: postfix program over leaves (>=0) and '+' (-1) */
+    uint32_t route;                     /* 0 = sparse AND kernel, 1 = dense tile kernel */
+    uint32_t pad;
+    XgmDevTerm terms[XGM_DEV_MAX_TERMS]; /* AND: ascending termfreq (MultiAndPostList order) */
+};
+
+struct XgmWorkItem {
+    uint32_t query;
+    uint32_t b0, b1;   /* sparse kernel: driver-block range; dense kernel: docid tile range */
+    uint32_t pad;
+};
+
+/* per-query match record */
+struct XgmMatch {
+    double w;
+    uint32_t did;
+    uint32_t aux;
+};
+
+#endif

@@ -1,0 +1,1179 @@
+/* xgm_host.cu — host side of libxgm.so: index builder (HBM block format), term dictionary, query
+ * planner (the host half of the reference's LocalSubMatch/Weight::init_ work) and the C-ABI of
+ * include/xgm.h.  There is no CPU matching path in this file: every search goes through the kernels
+ * in xgm_kernels.cu, and the library refuses to create an index without a CUDA device. */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/xgm.h"
+#include "xgm_corpus.h"
+#include "xgm_device.h"
+
+/* ------------------------------------------------------------------ errors */
+
+static thread_local char g_err[512] = "";
+
+static xgm_status fail(xgm_status st, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return st;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(XGM_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* xgm_last_error(void) { return g_err; }
+extern "C" uint32_t xgm_abi_version(void) { return XGM_ABI_VERSION; }
+
+/* ------------------------------------------------------------------ small helpers */
+
+template <class F>
+static void parallel_for(size_t n, int threads, F f) {
+    if (threads <= 1 || n < 2) {
+        for (size_t i = 0; i < n; ++i) f(i, 0);
+        return;
+    }
+    if ((size_t)threads > n) threads = (int)n;
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; ++t)
+        th.emplace_back([&, t]() {
+            for (;;) {
+                size_t i = next.fetch_add(1);
+                if (i >= n) break;
+                f(i, t);
+            }
+        });
+    for (auto& x : th) x.join();
+}
+
+static int default_threads() {
+    unsigned hc = std::thread::hardware_concurrency();
+    if (hc == 0) hc = 4;
+    if (hc > 64) hc = 64;
+    return (int)hc;
+}
+
+static inline uint32_t bits_for(uint32_t v) { return v ? 32u - (uint32_t)__builtin_clz(v) : 0u; }
+
+/* ------------------------------------------------------------------ index */
+
+struct TermInfo {
+    uint32_t blk_begin = 0;
+    uint32_t nblocks = 0;
+    uint32_t termfreq = 0;
+    uint32_t wdf_ub = 0;
+    uint64_t collfreq = 0;
+    uint64_t bytes = 0; /* docs + tfs + headers */
+};
+
+struct HostSlot {
+    bool present = false;
+    std::vector<uint32_t> voff;
+    std::vector<uint64_t> vals;
+};
+
+struct xgm_index {
+    int device = 0;
+    uint32_t doccount = 0, lastdocid = 0;
+    uint64_t total_length = 0;
+    uint32_t doclen_lb = 0, doclen_ub = 0;
+    uint64_t npostings = 0, nblocks = 0;
+    uint64_t bytes_docs = 0, bytes_tfs = 0, bytes_hdr = 0, bytes_doclen = 0;
+    uint64_t revision = 1;
+    std::vector<TermInfo> terms;
+    std::unordered_map<std::string, uint32_t> dict;
+    bool synthetic_names = false; /* "T%06u" names resolved arithmetically, no dictionary */
+    /* device */
+    XgmBlockHdr* d_hdr = nullptr;
+    uint4* d_docs = nullptr;
+    uint4* d_tfs = nullptr;
+    uint32_t* d_doclen = nullptr;
+    uint32_t* d_voff[XGM_MAX_SLOTS] = {};
+    uint64_t* d_vals[XGM_MAX_SLOTS] = {};
+    int sm_count = 148;
+};
+
+/* Compressed form of a contiguous range of terms, produced by one builder thread. */
+struct Chunk {
+    std::vector<XgmBlockHdr> hdr;
+    std::vector<uint32_t> docs; /* packed words, 4*bits words per block */
+    std::vector<uint32_t> tfs;
+};
+
+static inline void pack_bits(std::vector<uint32_t>& out, const uint32_t* v, uint32_t n, uint32_t bits) {
+    /* 128 slots x bits, little-endian bit order; slots >= n are zero */
+    if (bits == 0) return;
+    size_t base = out.size();
+    out.resize(base + 4 * (size_t)bits, 0u);
+    uint32_t* w = out.data() + base;
+    for (uint32_t i = 0; i < n; ++i) {
+        uint64_t o = (uint64_t)i * bits;
+        uint32_t wi = (uint32_t)(o >> 5), sh = (uint32_t)(o & 31);
+        uint64_t val = (uint64_t)v[i] << sh;
+        w[wi] |= (uint32_t)val;
+        if (sh + bits > 32) w[wi + 1] |= (uint32_t)(val >> 32);
+    }
+}
+
+/* Append one term's postings to a chunk in the block format of xgm_format.h. */
+static void compress_term(Chunk& c, const uint32_t* docids, const uint32_t* wdfs, uint32_t n, TermInfo& ti) {
+    ti.blk_begin = (uint32_t)c.hdr.size(); /* chunk-relative, fixed up later */
+    ti.nblocks = (n + XGM_BLOCK - 1) / XGM_BLOCK;
+    ti.termfreq = n;
+    uint32_t delta[XGM_BLOCK];
+    size_t d0 = c.docs.size(), t0 = c.tfs.size();
+    for (uint32_t b = 0; b < ti.nblocks; ++b) {
+        uint32_t off = b * XGM_BLOCK;
+        uint32_t cnt = std::min<uint32_t>(XGM_BLOCK, n - off);
+        uint32_t maxd = 0, maxw = 0;
+        delta[0] = 0;
+        for (uint32_t i = 1; i < cnt; ++i) {
+            delta[i] = docids[off + i] - docids[off + i - 1] - 1;
+            maxd = std::max(maxd, delta[i]);
+        }
+        for (uint32_t i = 0; i < cnt; ++i) maxw = std::max(maxw, wdfs[off + i]);
+        uint32_t db = bits_for(maxd), tb = bits_for(maxw);
+        XgmBlockHdr h;
+        h.first = docids[off];
+        h.doc_off = (uint32_t)(c.docs.size() / 4);
+        h.tf_off = (uint32_t)(c.tfs.size() / 4);
+        h.meta = db | (tb << 8) | ((cnt - 1) << 16);
+        c.hdr.push_back(h);
+        pack_bits(c.docs, delta, cnt, db);
+        pack_bits(c.tfs, wdfs + off, cnt, tb);
+    }
+    XgmBlockHdr s;
+    s.first = XGM_SENTINEL;
+    s.doc_off = (uint32_t)(c.docs.size() / 4);
+    s.tf_off = (uint32_t)(c.tfs.size() / 4);
+    s.meta = 0;
+    c.hdr.push_back(s);
+    ti.bytes = (c.docs.size() - d0) * 4 + (c.tfs.size() - t0) * 4 + (uint64_t)ti.nblocks * sizeof(XgmBlockHdr);
+}
+
+/* reference wdf upper bound: glass_postlist.cc:175-190 + glass_database.cc:822-829 */
+static uint32_t derive_wdf_ub(uint32_t tf, uint64_t cf, uint32_t first_wdf, uint32_t db_wdf_ub) {
+    uint64_t ub;
+    if (cf == 0 || tf == 1) ub = cf;
+    else ub = (cf - first_wdf > first_wdf) ? cf - first_wdf : first_wdf;
+    if (ub > db_wdf_ub) ub = db_wdf_ub;
+    return (uint32_t)ub;
+}
+
+struct xgm_builder {
+    uint32_t doccount = 0, lastdocid = 0;
+    uint64_t total_length = 0;
+    uint32_t doclen_lb = 0, doclen_ub = 0;
+    std::vector<uint32_t> doclen;
+    std::vector<std::string> names;
+    std::vector<TermInfo> terms;
+    std::vector<uint32_t> first_wdf;
+    std::vector<bool> ub_given;
+    uint32_t db_wdf_ub = 0;
+    Chunk chunk; /* sequential builder: one chunk */
+    HostSlot slots[XGM_MAX_SLOTS];
+    bool have_docs = false;
+};
+
+static xgm_status upload_index(xgm_index* ix, std::vector<Chunk>& chunks, const std::vector<size_t>& chunk_first_term,
+                               const std::vector<uint32_t>& doclen, HostSlot* slots, int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(XGM_E_NODEVICE, "no CUDA device visible: libxgm has no CPU path");
+    if (device < 0 || device >= ndev) return fail(XGM_E_INVALID, "device %d out of range (%d visible)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    ix->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    ix->sm_count = prop.multiProcessorCount;
+    /* global bases per chunk */
+    size_t nh = 0, nd = 0, nt = 0;
+    std::vector<size_t> hb(chunks.size()), dbase(chunks.size()), tb(chunks.size());
+    for (size_t i = 0; i < chunks.size(); ++i) {
+        hb[i] = nh; dbase[i] = nd; tb[i] = nt;
+        nh += chunks[i].hdr.size(); nd += chunks[i].docs.size(); nt += chunks[i].tfs.size();
+    }
+    if (nh >= 0xffffffffull || nd / 4 >= 0xffffffffull || nt / 4 >= 0xffffffffull)
+        return fail(XGM_E_INVALID, "index too large for 32-bit block offsets");
+    /* fix up offsets */
+    parallel_for(chunks.size(), default_threads(), [&](size_t i, int) {
+        uint32_t dadd = (uint32_t)(dbase[i] / 4), tadd = (uint32_t)(tb[i] / 4);
+        for (auto& h : chunks[i].hdr) { h.doc_off += dadd; h.tf_off += tadd; }
+        size_t t_begin = chunk_first_term[i], t_end = chunk_first_term[i + 1];
+        for (size_t t = t_begin; t < t_end; ++t) ix->terms[t].blk_begin += (uint32_t)hb[i];
+    });
+    /* +16 bytes slack at the end of each column: the unpackers may read one word past a block */
+    CUDA_TRY(cudaMalloc(&ix->d_hdr, (nh + 1) * sizeof(XgmBlockHdr)));
+    CUDA_TRY(cudaMalloc(&ix->d_docs, nd * 4 + 64));
+    CUDA_TRY(cudaMalloc(&ix->d_tfs, nt * 4 + 64));
+    CUDA_TRY(cudaMemset(reinterpret_cast<char*>(ix->d_docs) + nd * 4, 0, 64));
+    CUDA_TRY(cudaMemset(reinterpret_cast<char*>(ix->d_tfs) + nt * 4, 0, 64));
+    for (size_t i = 0; i < chunks.size(); ++i) {
+        if (!chunks[i].hdr.empty())
+            CUDA_TRY(cudaMemcpy(ix->d_hdr + hb[i], chunks[i].hdr.data(), chunks[i].hdr.size() * sizeof(XgmBlockHdr), cudaMemcpyHostToDevice));
+        if (!chunks[i].docs.empty())
+            CUDA_TRY(cudaMemcpy(reinterpret_cast<uint32_t*>(ix->d_docs) + dbase[i], chunks[i].docs.data(), chunks[i].docs.size() * 4, cudaMemcpyHostToDevice));
+        if (!chunks[i].tfs.empty())
+            CUDA_TRY(cudaMemcpy(reinterpret_cast<uint32_t*>(ix->d_tfs) + tb[i], chunks[i].tfs.data(), chunks[i].tfs.size() * 4, cudaMemcpyHostToDevice));
+        std::vector<XgmBlockHdr>().swap(chunks[i].hdr);
+        std::vector<uint32_t>().swap(chunks[i].docs);
+        std::vector<uint32_t>().swap(chunks[i].tfs);
+    }
+    XgmBlockHdr tail;
+    tail.first = XGM_SENTINEL; tail.doc_off = 0; tail.tf_off = 0; tail.meta = 0;
+    CUDA_TRY(cudaMemcpy(ix->d_hdr + nh, &tail, sizeof(tail), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&ix->d_doclen, doclen.size() * 4));
+    CUDA_TRY(cudaMemcpy(ix->d_doclen, doclen.data(), doclen.size() * 4, cudaMemcpyHostToDevice));
+    for (int s = 0; s < XGM_MAX_SLOTS; ++s) {
+        if (!slots || !slots[s].present) continue;
+        CUDA_TRY(cudaMalloc(&ix->d_voff[s], slots[s].voff.size() * 4));
+        CUDA_TRY(cudaMemcpy(ix->d_voff[s], slots[s].voff.data(), slots[s].voff.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&ix->d_vals[s], std::max<size_t>(1, slots[s].vals.size()) * 8));
+        if (!slots[s].vals.empty())
+            CUDA_TRY(cudaMemcpy(ix->d_vals[s], slots[s].vals.data(), slots[s].vals.size() * 8, cudaMemcpyHostToDevice));
+    }
+    ix->nblocks = 0;
+    ix->npostings = 0;
+    for (auto& t : ix->terms) { ix->nblocks += t.nblocks; ix->npostings += t.termfreq; }
+    ix->bytes_docs = nd * 4;
+    ix->bytes_tfs = nt * 4;
+    ix->bytes_hdr = nh * sizeof(XgmBlockHdr);
+    ix->bytes_doclen = doclen.size() * 4;
+    return XGM_OK;
+}
+
+extern "C" xgm_status xgm_builder_new(xgm_builder** out) {
+    if (!out) return fail(XGM_E_INVALID, "null out");
+    *out = new (std::nothrow) xgm_builder();
+    return *out ? XGM_OK : fail(XGM_E_NOMEM, "out of memory");
+}
+
+extern "C" void xgm_builder_free(xgm_builder* b) { delete b; }
+
+extern "C" xgm_status xgm_builder_set_docs(xgm_builder* b, uint32_t doccount, uint32_t lastdocid, uint64_t total_length,
+                                           uint32_t doclen_lb, uint32_t doclen_ub, const uint32_t* doclen) {
+    if (!b || !doclen) return fail(XGM_E_INVALID, "null argument");
+    b->doccount = doccount; b->lastdocid = lastdocid; b->total_length = total_length;
+    b->doclen_lb = doclen_lb; b->doclen_ub = doclen_ub;
+    b->doclen.assign(doclen, doclen + (size_t)lastdocid + 1);
+    b->doclen.push_back(0);
+    b->have_docs = true;
+    return XGM_OK;
+}
+
+extern "C" xgm_status xgm_builder_add_term(xgm_builder* b, const char* term, uint32_t term_len, const uint32_t* docids,
+                                           const uint32_t* wdfs, uint32_t n, uint64_t collfreq, uint32_t wdf_ub,
+                                           uint32_t* term_id) {
+    if (!b || !term || (n && (!docids || !wdfs))) return fail(XGM_E_INVALID, "null argument");
+    for (uint32_t i = 0; i < n; ++i) {
+        if (docids[i] == 0 || docids[i] == XGM_SENTINEL || (i && docids[i] <= docids[i - 1]))
+            return fail(XGM_E_INVALID, "docids of term must be strictly ascending and in [1, 2^32-2]");
+        b->db_wdf_ub = std::max(b->db_wdf_ub, wdfs[i]);
+    }
+    TermInfo ti;
+    compress_term(b->chunk, docids, wdfs, n, ti);
+    ti.collfreq = collfreq;
+    ti.wdf_ub = wdf_ub;
+    if (term_id) *term_id = (uint32_t)b->terms.size();
+    b->terms.push_back(ti);
+    b->names.emplace_back(term, term_len);
+    b->first_wdf.push_back(n ? wdfs[0] : 0);
+    b->ub_given.push_back(wdf_ub != 0);
+    return XGM_OK;
+}
+
+extern "C" xgm_status xgm_builder_add_value_slot(xgm_builder* b, uint32_t slot, const uint64_t* voff, const uint64_t* vals) {
+    if (!b || !voff || slot >= XGM_MAX_SLOTS) return fail(XGM_E_INVALID, "bad slot");
+    if (!b->have_docs) return fail(XGM_E_INVALID, "call xgm_builder_set_docs first");
+    HostSlot& s = b->slots[slot];
+    size_t n = (size_t)b->lastdocid + 2;
+    if (voff[n - 1] >= 0xffffffffull) return fail(XGM_E_INVALID, "too many values");
+    s.voff.resize(n);
+    for (size_t i = 0; i < n; ++i) s.voff[i] = (uint32_t)voff[i];
+    s.vals.assign(vals, vals + voff[n - 1]);
+    s.present = true;
+    return XGM_OK;
+}
+
+extern "C" xgm_status xgm_builder_finish(xgm_builder* b, int device, xgm_index** out) {
+    if (!b || !out) return fail(XGM_E_INVALID, "null argument");
+    if (!b->have_docs) { delete b; return fail(XGM_E_INVALID, "xgm_builder_set_docs was not called"); }
+    std::unique_ptr<xgm_index> ix(new xgm_index());
+    ix->doccount = b->doccount; ix->lastdocid = b->lastdocid; ix->total_length = b->total_length;
+    ix->doclen_lb = b->doclen_lb; ix->doclen_ub = b->doclen_ub;
+    ix->terms = b->terms;
+    for (size_t t = 0; t < ix->terms.size(); ++t) {
+        if (!b->ub_given[t])
+            ix->terms[t].wdf_ub = derive_wdf_ub(ix->terms[t].termfreq, ix->terms[t].collfreq, b->first_wdf[t], b->db_wdf_ub);
+        ix->dict.emplace(b->names[t], (uint32_t)t);
+    }
+    std::vector<Chunk> chunks;
+    chunks.emplace_back(std::move(b->chunk));
+    std::vector<size_t> first = {0, ix->terms.size()};
+    xgm_status st = upload_index(ix.get(), chunks, first, b->doclen, b->slots, device);
+    delete b;
+    if (st != XGM_OK) return st;
+    *out = ix.release();
+    return XGM_OK;
+}
+
+extern "C" void xgm_index_close(xgm_index* ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    cudaFree(ix->d_hdr); cudaFree(ix->d_docs); cudaFree(ix->d_tfs); cudaFree(ix->d_doclen);
+    for (int s = 0; s < XGM_MAX_SLOTS; ++s) { cudaFree(ix->d_voff[s]); cudaFree(ix->d_vals[s]); }
+    delete ix;
+}
+
+/* ---- synthetic corpus straight into the block format (bench / tests) ---------------------- */
+
+extern "C" xgm_status xgm_index_build_synthetic(uint32_t ndocs, uint32_t vocab, uint64_t seed, uint32_t nshards,
+                                                uint32_t shard, int with_values, int device, int host_threads,
+                                                xgm_index** out) {
+    if (!out || nshards == 0 || shard >= nshards || vocab == 0) return fail(XGM_E_INVALID, "bad arguments");
+    int T = host_threads > 0 ? host_threads : default_threads();
+    xgm_zipf z;
+    if (xgm_zipf_init(&z, vocab)) return fail(XGM_E_NOMEM, "zipf table");
+    uint32_t nlocal = shard < ndocs ? (ndocs - shard - 1) / nshards + 1 : 0;
+    std::unique_ptr<xgm_index> ix(new xgm_index());
+    ix->doccount = ix->lastdocid = nlocal;
+    ix->synthetic_names = true;
+    std::vector<uint32_t> doclen((size_t)nlocal + 2, 0);
+    /* pass 1: per-thread, per-term posting counts over contiguous local-docid ranges */
+    size_t per = ((size_t)nlocal + T - 1) / T;
+    if (per == 0) per = 1;
+    int nparts = (int)(((size_t)nlocal + per - 1) / per);
+    if (nparts < 1) nparts = 1;
+    std::vector<std::vector<uint32_t>> cnt(nparts);
+    std::vector<uint64_t> part_len(nparts, 0);
+    std::vector<uint32_t> part_lb(nparts, 0xffffffffu), part_ub(nparts, 0), part_wub(nparts, 0);
+    parallel_for((size_t)nparts, T, [&](size_t pi, int) {
+        cnt[pi].assign(vocab, 0);
+        uint32_t ranks[XGM_CORPUS_MAX_LEN], wdf[XGM_CORPUS_MAX_LEN];
+        size_t a = pi * per + 1, b = std::min<size_t>((size_t)nlocal, (pi + 1) * per);
+        for (size_t l = a; l <= b; ++l) {
+            uint32_t gd = (uint32_t)((l - 1) * nshards + shard + 1);
+            uint32_t len = xgm_corpus_doc(&z, seed, gd, ranks);
+            uint32_t n = xgm_corpus_collapse(ranks, len, wdf);
+            for (uint32_t i = 0; i < n; ++i) { cnt[pi][ranks[i]]++; part_wub[pi] = std::max(part_wub[pi], wdf[i]); }
+            doclen[l] = len;
+            part_len[pi] += len;
+            part_lb[pi] = std::min(part_lb[pi], len);
+            part_ub[pi] = std::max(part_ub[pi], len);
+        }
+    });
+    uint32_t db_wdf_ub = 0;
+    ix->doclen_lb = nlocal ? 0xffffffffu : 0;
+    for (int pi = 0; pi < nparts; ++pi) {
+        ix->total_length += part_len[pi];
+        ix->doclen_lb = std::min(ix->doclen_lb, part_lb[pi]);
+        ix->doclen_ub = std::max(ix->doclen_ub, part_ub[pi]);
+        db_wdf_ub = std::max(db_wdf_ub, part_wub[pi]);
+    }
+    /* term offsets, then per-part write cursors */
+    std::vector<uint64_t> off((size_t)vocab + 1, 0);
+    for (uint32_t t = 0; t < vocab; ++t) {
+        uint64_t s = 0;
+        for (int pi = 0; pi < nparts; ++pi) s += cnt[pi][t];
+        off[t + 1] = off[t] + s;
+    }
+    uint64_t total = off[vocab];
+    std::vector<uint32_t> docids(total), wdfs(total);
+    /* convert counts into start cursors (part-major within a term keeps docids ascending) */
+    parallel_for((size_t)T, T, [&](size_t ti, int) {
+        size_t a = (size_t)vocab * ti / T, b = (size_t)vocab * (ti + 1) / T;
+        for (size_t t = a; t < b; ++t) {
+            uint64_t cur = off[t];
+            for (int pi = 0; pi < nparts; ++pi) { uint32_t c = cnt[pi][t]; cnt[pi][t] = (uint32_t)(cur - off[t]); cur += c; }
+        }
+    });
+    parallel_for((size_t)nparts, T, [&](size_t pi, int) {
+        uint32_t ranks[XGM_CORPUS_MAX_LEN], wdf[XGM_CORPUS_MAX_LEN];
+        size_t a = pi * per + 1, b = std::min<size_t>((size_t)nlocal, (pi + 1) * per);
+        std::vector<uint32_t>& cur = cnt[pi];
+        for (size_t l = a; l <= b; ++l) {
+            uint32_t gd = (uint32_t)((l - 1) * nshards + shard + 1);
+            uint32_t len = xgm_corpus_doc(&z, seed, gd, ranks);
+            uint32_t n = xgm_corpus_collapse(ranks, len, wdf);
+            for (uint32_t i = 0; i < n; ++i) {
+                uint64_t p = off[ranks[i]] + cur[ranks[i]]++;
+                docids[p] = (uint32_t)l;
+                wdfs[p] = wdf[i];
+            }
+        }
+    });
+    cnt.clear();
+    cnt.shrink_to_fit();
+    /* compress: contiguous term ranges balanced by posting count */
+    int nchunks = std::max(1, T * 4);
+    std::vector<size_t> first(nchunks + 1, 0);
+    {
+        size_t t = 0;
+        for (int c = 1; c < nchunks; ++c) {
+            uint64_t target = total / nchunks * c;
+            while (t < vocab && off[t] < target) ++t;
+            first[c] = t;
+        }
+        first[nchunks] = vocab;
+        for (int c = 1; c <= nchunks; ++c) first[c] = std::max(first[c], first[c - 1]);
+    }
+    ix->terms.resize(vocab);
+    std::vector<Chunk> chunks(nchunks);
+    parallel_for((size_t)nchunks, T, [&](size_t c, int) {
+        for (size_t t = first[c]; t < first[c + 1]; ++t) {
+            uint32_t n = (uint32_t)(off[t + 1] - off[t]);
+            TermInfo& ti = ix->terms[t];
+            compress_term(chunks[c], docids.data() + off[t], wdfs.data() + off[t], n, ti);
+            uint64_t cf = 0;
+            for (uint64_t p = off[t]; p < off[t + 1]; ++p) cf += wdfs[p];
+            ti.collfreq = cf;
+            ti.wdf_ub = n ? derive_wdf_ub(n, cf, wdfs[off[t]], db_wdf_ub) : 0;
+        }
+    });
+    std::vector<uint32_t>().swap(docids);
+    std::vector<uint32_t>().swap(wdfs);
+    HostSlot slots[XGM_MAX_SLOTS];
+    if (with_values) {
+        slots[0].present = slots[1].present = true;
+        slots[0].voff.assign((size_t)nlocal + 2, 0);
+        slots[1].voff.assign((size_t)nlocal + 2, 0);
+        slots[1].vals.assign((size_t)nlocal, 0);
+        std::vector<uint8_t> n0((size_t)nlocal + 1, 0);
+        std::vector<uint64_t> v0(3 * ((size_t)nlocal + 1), 0);
+        parallel_for((size_t)nparts, T, [&](size_t pi, int) {
+            size_t a = pi * per + 1, b = std::min<size_t>((size_t)nlocal, (pi + 1) * per);
+            for (size_t l = a; l <= b; ++l) {
+                uint32_t gd = (uint32_t)((l - 1) * nshards + shard + 1);
+                uint64_t v[3], v1;
+                uint32_t k = xgm_corpus_values(seed, gd, v, &v1);
+                n0[l] = (uint8_t)k;
+                for (uint32_t i = 0; i < k; ++i) v0[3 * l + i] = v[i];
+                slots[1].vals[l - 1] = v1;
+            }
+        });
+        uint32_t acc = 0;
+        slots[0].voff[0] = slots[0].voff[1] = 0;
+        for (size_t l = 1; l <= nlocal; ++l) {
+            slots[0].voff[l] = acc;
+            acc += n0[l];
+            slots[1].voff[l] = (uint32_t)(l - 1);
+        }
+        slots[0].voff[(size_t)nlocal + 1] = acc;
+        slots[1].voff[(size_t)nlocal + 1] = nlocal;
+        slots[0].vals.resize(acc);
+        for (size_t l = 1; l <= nlocal; ++l)
+            for (uint32_t i = 0; i < n0[l]; ++i) slots[0].vals[slots[0].voff[l] + i] = v0[3 * l + i];
+    }
+    xgm_zipf_free(&z);
+    xgm_status st = upload_index(ix.get(), chunks, first, doclen, slots, device);
+    if (st != XGM_OK) return st;
+    *out = ix.release();
+    return XGM_OK;
+}
+
+/* ---- XGMFLAT1 loader -------------------------------------------------------------------- */
+
+static bool rd(FILE* f, void* p, size_t n) { return fread(p, 1, n, f) == n; }
+
+extern "C" xgm_status xgm_index_load_flat(const char* path, int device, xgm_index** out) {
+    if (!path || !out) return fail(XGM_E_INVALID, "null argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(XGM_E_IO, "cannot open %s", path);
+    char magic[8];
+    uint32_t doccount, lastdocid, nterms, nslots, lb, ub;
+    uint64_t total_length;
+    if (!rd(f, magic, 8) || memcmp(magic, "XGMFLAT1", 8) || !rd(f, &doccount, 4) || !rd(f, &lastdocid, 4) ||
+        !rd(f, &total_length, 8) || !rd(f, &nterms, 4) || !rd(f, &nslots, 4) || !rd(f, &lb, 4) || !rd(f, &ub, 4)) {
+        fclose(f);
+        return fail(XGM_E_IO, "%s: bad XGMFLAT1 header", path);
+    }
+    xgm_builder* b = nullptr;
+    xgm_status st = xgm_builder_new(&b);
+    if (st != XGM_OK) { fclose(f); return st; }
+    std::vector<uint32_t> dl((size_t)lastdocid + 1);
+    if (!rd(f, dl.data(), dl.size() * 4)) { fclose(f); delete b; return fail(XGM_E_IO, "%s: truncated", path); }
+    xgm_builder_set_docs(b, doccount, lastdocid, total_length, lb, ub, dl.data());
+    std::vector<uint32_t> dids, wdfs;
+    std::string name;
+    for (uint32_t t = 0; t < nterms; ++t) {
+        uint32_t nl, tf, wub, n;
+        uint64_t cf;
+        if (!rd(f, &nl, 4)) goto trunc;
+        name.resize(nl);
+        if (!rd(f, &name[0], nl) || !rd(f, &tf, 4) || !rd(f, &cf, 8) || !rd(f, &wub, 4) || !rd(f, &n, 4)) goto trunc;
+        dids.resize(n); wdfs.resize(n);
+        if (!rd(f, dids.data(), (size_t)n * 4) || !rd(f, wdfs.data(), (size_t)n * 4)) goto trunc;
+        st = xgm_builder_add_term(b, name.data(), nl, dids.data(), wdfs.data(), n, cf, wub, nullptr);
+        if (st != XGM_OK) { fclose(f); delete b; return st; }
+        /* the reference's own bound is authoritative even when it is 0 */
+        b->terms.back().wdf_ub = wub;
+        b->ub_given.back() = true;
+    }
+    /* value slots: numeric slots hold sortable_serialise()d doubles; decoding them is the shim's job
+     * (INTEGRATION.md); the flat file keeps raw bytes, so slots are added through
+     * xgm_builder_add_value_slot by the caller when needed. */
+    fclose(f);
+    return xgm_builder_finish(b, device, out);
+trunc:
+    fclose(f);
+    delete b;
+    return fail(XGM_E_IO, "%s: truncated", path);
+}
+
+extern "C" xgm_status xgm_index_info_get(const xgm_index* ix, xgm_index_info* o) {
+    if (!ix || !o) return fail(XGM_E_INVALID, "null argument");
+    memset(o, 0, sizeof(*o));
+    o->doccount = ix->doccount; o->lastdocid = ix->lastdocid; o->total_length = ix->total_length;
+    o->doclen_lower_bound = ix->doclen_lb; o->doclen_upper_bound = ix->doclen_ub;
+    o->nterms = (uint32_t)ix->terms.size(); o->npostings = ix->npostings; o->nblocks = ix->nblocks;
+    o->bytes_docids = ix->bytes_docs; o->bytes_wdfs = ix->bytes_tfs; o->bytes_headers = ix->bytes_hdr;
+    o->bytes_doclen = ix->bytes_doclen; o->device = ix->device; o->revision = ix->revision;
+    return XGM_OK;
+}
+
+static bool lookup_term(const xgm_index* ix, const char* term, uint32_t len, uint32_t* id) {
+    if (ix->synthetic_names) {
+        if (len < 2 || term[0] != 'T') return false;
+        uint64_t r = 0;
+        for (uint32_t i = 1; i < len; ++i) {
+            if (term[i] < '0' || term[i] > '9') return false;
+            r = r * 10 + (uint64_t)(term[i] - '0');
+            if (r > 0xffffffffull) return false;
+        }
+        if (r >= ix->terms.size()) return false;
+        char b[16];
+        int k = xgm_corpus_term((uint32_t)r, b);
+        if ((uint32_t)k != len || memcmp(b, term, len) != 0) return false;
+        *id = (uint32_t)r;
+        return true;
+    }
+    auto it = ix->dict.find(std::string(term, len));
+    if (it == ix->dict.end()) return false;
+    *id = it->second;
+    return true;
+}
+
+extern "C" xgm_status xgm_term_stats_get(const xgm_index* ix, const char* term, uint32_t len, xgm_term_stats* o) {
+    if (!ix || !term || !o) return fail(XGM_E_INVALID, "null argument");
+    memset(o, 0, sizeof(*o));
+    o->term_id = 0xffffffffu;
+    uint32_t id;
+    if (!lookup_term(ix, term, len, &id)) return XGM_OK;
+    const TermInfo& t = ix->terms[id];
+    o->term_id = id; o->termfreq = t.termfreq; o->collfreq = t.collfreq; o->wdf_upper_bound = t.wdf_ub; o->bytes = t.bytes;
+    return XGM_OK;
+}
+
+static void fill_index_params(const xgm_index* ix, XgmKernelParams& p) {
+    memset(&p, 0, sizeof(p));
+    p.hdr = ix->d_hdr; p.docs = ix->d_docs; p.tfs = ix->d_tfs; p.doclen = ix->d_doclen; p.lastdocid = ix->lastdocid;
+    for (int s = 0; s < XGM_MAX_SLOTS; ++s) { p.slots[s].voff = ix->d_voff[s]; p.slots[s].vals = ix->d_vals[s]; }
+}
+
+extern "C" xgm_status xgm_index_decode_term(const xgm_index* ix, uint32_t term_id, uint32_t* docids, uint32_t* wdfs,
+                                            uint32_t capacity, uint32_t* n) {
+    if (!ix || !n) return fail(XGM_E_INVALID, "null argument");
+    if (term_id >= ix->terms.size()) return fail(XGM_E_INVALID, "term id out of range");
+    const TermInfo& t = ix->terms[term_id];
+    *n = t.termfreq;
+    if (t.termfreq == 0) return XGM_OK;
+    if (capacity < t.termfreq || !docids || !wdfs) return fail(XGM_E_INVALID, "capacity %u < termfreq %u", capacity, t.termfreq);
+    CUDA_TRY(cudaSetDevice(ix->device));
+    uint32_t *dd = nullptr, *dw = nullptr;
+    size_t cap = (size_t)t.nblocks * XGM_BLOCK;
+    CUDA_TRY(cudaMalloc(&dd, cap * 4));
+    CUDA_TRY(cudaMalloc(&dw, cap * 4));
+    XgmKernelParams p;
+    fill_index_params(ix, p);
+    cudaError_t e = xgm_launch_decode(p, t.blk_begin, t.nblocks, dd, dw, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(docids, dd, (size_t)t.termfreq * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(wdfs, dw, (size_t)t.termfreq * 4, cudaMemcpyDeviceToHost);
+    cudaFree(dd); cudaFree(dw);
+    if (e != cudaSuccess) return fail(XGM_E_CUDA, "decode: %s", cudaGetErrorString(e));
+    return XGM_OK;
+}
+
+/* ------------------------------------------------------------------ searcher */
+
+struct PlannedQuery {
+    uint32_t status = XGM_OK;
+    bool on_device = false;   /* false: answered on the host (empty / bounds-only) */
+    uint32_t first = 0, maxitems = 0, topk = 0, check_at_least = 0;
+    uint32_t tf_min = 0, tf_est = 0, tf_max = 0;
+    uint32_t nterms = 0;
+    double max_possible = 0;
+    uint64_t alg_bytes = 0;
+    uint32_t sort_by = 0;
+};
+
+struct xgm_searcher {
+    const xgm_index* ix = nullptr;
+    uint32_t max_batch = 0, max_topk = 0, match_cap = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    /* pinned host staging */
+    XgmDevQuery* h_queries = nullptr;
+    XgmWorkItem* h_items = nullptr;
+    double* h_out_w = nullptr;
+    uint32_t* h_out_d = nullptr;
+    uint64_t* h_out_k = nullptr;
+    XgmDevResult* h_info = nullptr;
+    size_t items_cap = 0;
+    /* device */
+    XgmDevQuery* d_queries = nullptr;
+    XgmWorkItem* d_items = nullptr;
+    uint32_t* d_ctrl = nullptr; /* [0] work counter, [1..] match counts */
+    double* d_match_w = nullptr;
+    uint32_t* d_match_d = nullptr;
+    uint64_t* d_match_k = nullptr;
+    double* d_out_w = nullptr;
+    uint32_t* d_out_d = nullptr;
+    uint64_t* d_out_k = nullptr;
+    XgmDevResult* d_info = nullptr;
+    /* last batch */
+    std::vector<PlannedQuery> plan;
+    uint32_t nq = 0, nitems = 0;
+    bool pending = false, any_sort = false;
+    xgm_batch_stats stats{};
+    int grid = 0;
+    XgmKernelParams params;
+};
+
+extern "C" void xgm_searcher_free(xgm_searcher* s) {
+    if (!s) return;
+    cudaSetDevice(s->ix->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFreeHost(s->h_queries); cudaFreeHost(s->h_items); cudaFreeHost(s->h_out_w); cudaFreeHost(s->h_out_d);
+    cudaFreeHost(s->h_out_k); cudaFreeHost(s->h_info);
+    cudaFree(s->d_queries); cudaFree(s->d_items); cudaFree(s->d_ctrl); cudaFree(s->d_match_w); cudaFree(s->d_match_d);
+    cudaFree(s->d_match_k); cudaFree(s->d_out_w); cudaFree(s->d_out_d); cudaFree(s->d_out_k); cudaFree(s->d_info);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->ev2) cudaEventDestroy(s->ev2);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+static xgm_status ensure_items(xgm_searcher* s, size_t need) {
+    if (need <= s->items_cap) return XGM_OK;
+    size_t cap = std::max<size_t>(need * 2, 4096);
+    if (s->pending) CUDA_TRY(cudaStreamSynchronize(s->stream));
+    XgmWorkItem* nh = nullptr;
+    CUDA_TRY(cudaMallocHost(&nh, cap * sizeof(XgmWorkItem)));
+    if (s->h_items) { memcpy(nh, s->h_items, s->items_cap * sizeof(XgmWorkItem)); cudaFreeHost(s->h_items); }
+    s->h_items = nh;
+    cudaFree(s->d_items);
+    s->d_items = nullptr;
+    CUDA_TRY(cudaMalloc(&s->d_items, cap * sizeof(XgmWorkItem)));
+    s->items_cap = cap;
+    return XGM_OK;
+}
+
+extern "C" xgm_status xgm_searcher_new(const xgm_index* ix, uint32_t max_batch, uint32_t max_topk, xgm_searcher** out) {
+    if (!ix || !out || max_batch == 0 || max_topk == 0) return fail(XGM_E_INVALID, "bad arguments");
+    if (max_topk > XGM_MAX_TOPK) return fail(XGM_E_INVALID, "max_topk %u > %u", max_topk, XGM_MAX_TOPK);
+    CUDA_TRY(cudaSetDevice(ix->device));
+    std::unique_ptr<xgm_searcher, void (*)(xgm_searcher*)> s(new xgm_searcher(), xgm_searcher_free);
+    s->ix = ix; s->max_batch = max_batch; s->max_topk = max_topk;
+    s->match_cap = std::max<uint32_t>(2048, 2 * max_topk);
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&s->ev0)); CUDA_TRY(cudaEventCreate(&s->ev1)); CUDA_TRY(cudaEventCreate(&s->ev2));
+    size_t nq = max_batch, ns = (size_t)max_batch * max_topk, nm = (size_t)max_batch * s->match_cap;
+    CUDA_TRY(cudaMallocHost(&s->h_queries, nq * sizeof(XgmDevQuery)));
+    CUDA_TRY(cudaMallocHost(&s->h_out_w, ns * 8)); CUDA_TRY(cudaMallocHost(&s->h_out_d, ns * 4));
+    CUDA_TRY(cudaMallocHost(&s->h_out_k, ns * 8)); CUDA_TRY(cudaMallocHost(&s->h_info, nq * sizeof(XgmDevResult)));
+    CUDA_TRY(cudaMalloc(&s->d_queries, nq * sizeof(XgmDevQuery)));
+    CUDA_TRY(cudaMalloc(&s->d_ctrl, (nq + 1) * 4));
+    CUDA_TRY(cudaMalloc(&s->d_match_w, nm * 8)); CUDA_TRY(cudaMalloc(&s->d_match_d, nm * 4)); CUDA_TRY(cudaMalloc(&s->d_match_k, nm * 8));
+    CUDA_TRY(cudaMalloc(&s->d_out_w, ns * 8)); CUDA_TRY(cudaMalloc(&s->d_out_d, ns * 4)); CUDA_TRY(cudaMalloc(&s->d_out_k, ns * 8));
+    CUDA_TRY(cudaMalloc(&s->d_info, nq * sizeof(XgmDevResult)));
+    xgm_status st = ensure_items(s.get(), 4096);
+    if (st != XGM_OK) return st;
+    int occ = xgm_and_occupancy_blocks_per_sm();
+    if (occ < 1) occ = 1;
+    s->grid = ix->sm_count * occ;
+    *out = s.release();
+    return XGM_OK;
+}
+
+extern "C" void* xgm_searcher_stream(xgm_searcher* s) { return s ? (void*)s->stream : nullptr; }
+
+/* ComparePostListTermFreqAscending on (tf, original index) — same std::partial_sort_copy call as
+ * MultiAndPostList's constructor (multiandpostlist.h:126-131) so ties land identically (libstdc++). */
+struct TfIdx { uint32_t tf, idx; };
+
+/* Heap::make/pop/replace of src/xapian/common/heap.h (libc++-style sift-down) replayed on
+ * (termfreq, node) pairs exactly as OrContext::postlist does (queryinternal.cc:440-489). */
+struct OrEnt { uint32_t tf; int node; };
+static inline bool or_cmp(const OrEnt& a, const OrEnt& b) { return a.tf > b.tf; }
+static void or_sift_down(OrEnt* first, long len, long start) {
+    long child = start;
+    if (len < 2 || (len - 2) / 2 < child) return;
+    child = 2 * child + 1;
+    if (child + 1 < len && or_cmp(first[child], first[child + 1])) ++child;
+    if (or_cmp(first[child], first[start])) return;
+    OrEnt top = first[start];
+    do {
+        first[start] = first[child];
+        start = child;
+        if ((len - 2) / 2 < child) break;
+        child = 2 * child + 1;
+        if (child + 1 < len && or_cmp(first[child], first[child + 1])) ++child;
+    } while (!or_cmp(first[child], top));
+    first[start] = top;
+}
+
+struct OrTree { int lch[2 * XGM_MAX_TERMS], rch[2 * XGM_MAX_TERMS]; int root; };
+
+static void build_or_tree(const uint32_t* tf, uint32_t n, OrTree& tr) {
+    OrEnt h[XGM_MAX_TERMS];
+    for (uint32_t i = 0; i < n; ++i) { h[i].tf = tf[i]; h[i].node = (int)i; }
+    long len = n;
+    for (long s = (len - 2) / 2; s >= 0; --s) or_sift_down(h, len, s);
+    int next = (int)n;
+    for (;;) {
+        int r = h[0].node;
+        uint32_t rtf = h[0].tf;
+        std::swap(h[0], h[len - 1]);
+        or_sift_down(h, len - 1, 0);
+        --len;
+        int node = next++;
+        tr.lch[node] = h[0].node;
+        tr.rch[node] = r;
+        if (len == 1) { tr.root = node; break; }
+        h[0].node = node;
+        h[0].tf += rtf;
+        or_sift_down(h, len, 0);
+    }
+}
+
+/* BM25Weight::init (bm25weight.cc:46-130) via Weight::init_ (weight.cc:59-83); host-side because it
+ * needs log() and runs once per term per query. */
+static double bm25_termweight(uint32_t N, uint32_t tf, uint32_t wqf, double factor, double k1, double k3) {
+    double tw = ((double)(N - tf) + 0.5) / ((double)tf + 0.5);
+    if (tw < 2) tw = tw * 0.5 + 1;
+    double w = std::log(tw) * factor;
+    if (k3 != 0) {
+        double wqf_double = wqf;
+        w *= (k3 + 1) * wqf_double / (k3 + wqf_double);
+    }
+    w *= (k1 + 1);
+    return w;
+}
+
+/* BM25Weight::get_maxpart bm25weight.cc:183-207 */
+static double bm25_maxpart(double termweight, double len_factor, double k1, double b, double min_normlen,
+                           uint32_t wdf_ub, uint32_t doclen_lb) {
+    double denom = k1;
+    if (k1 != 0.0 && b != 0.0) {
+        uint32_t m = std::max(wdf_ub, doclen_lb);
+        double normlen_lb = std::max(m * len_factor, min_normlen);
+        denom *= (normlen_lb * b + (1 - b));
+    }
+    double wdf_max = wdf_ub;
+    denom += wdf_max;
+    return termweight * (wdf_max / denom);
+}
+
+static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, PlannedQuery& pq, XgmDevQuery& dq,
+                             std::vector<XgmWorkItem>& items, uint32_t blocks_per_item) {
+    const xgm_index* ix = s->ix;
+    pq = PlannedQuery();
+    memset(&dq, 0, sizeof(dq));
+    if (q.nterms == 0 || q.nterms > XGM_MAX_TERMS) { pq.status = XGM_E_UNIMPLEMENTED; return XGM_OK; }
+    if (q.op != XGM_OP_AND && q.op != XGM_OP_OR) { pq.status = XGM_E_UNIMPLEMENTED; return XGM_OK; }
+    if (q.sort_by > XGM_SORT_REL_VAL || q.filter > XGM_FILTER_MULTI_RANGE) { pq.status = XGM_E_INVALID; return XGM_OK; }
+    if ((q.filter && q.filter_slot >= XGM_MAX_SLOTS) || (q.sort_by && q.sort_slot >= XGM_MAX_SLOTS)) { pq.status = XGM_E_INVALID; return XGM_OK; }
+    const uint32_t n = q.nterms;
+    uint32_t ids[XGM_MAX_TERMS];
+    uint32_t ltf[XGM_MAX_TERMS];
+    for (uint32_t j = 0; j < n; ++j) {
+        uint32_t id = 0xffffffffu;
+        if (q.term_ids) id = q.term_ids[j];
+        else if (q.terms && q.terms[j]) {
+            uint32_t len = q.term_lens ? q.term_lens[j] : (uint32_t)strlen(q.terms[j]);
+            if (!lookup_term(ix, q.terms[j], len, &id)) id = 0xffffffffu;
+        } else { pq.status = XGM_E_INVALID; return XGM_OK; }
+        if (id != 0xffffffffu && id >= ix->terms.size()) { pq.status = XGM_E_INVALID; return XGM_OK; }
+        ids[j] = id;
+        ltf[j] = id == 0xffffffffu ? 0 : ix->terms[id].termfreq;
+        for (uint32_t i = 0; i < j; ++i)
+            if (ids[i] == id && id != 0xffffffffu) { pq.status = XGM_E_UNIMPLEMENTED; return XGM_OK; } /* repeated leaf */
+    }
+    /* Enquire::Internal::get_mset clamping, api/enquire.cc:420-426 */
+    uint32_t docs = ix->doccount;
+    uint32_t first = std::min(q.first, docs);
+    uint32_t maxitems = std::min(q.maxitems, docs - first);
+    uint32_t cal = std::min(q.check_at_least, docs);
+    cal = std::max(cal, first + maxitems);
+    pq.first = first; pq.maxitems = maxitems; pq.topk = first + maxitems; pq.check_at_least = cal;
+    pq.nterms = n; pq.sort_by = q.sort_by;
+    if (pq.topk > s->max_topk) { pq.status = XGM_E_INVALID; return XGM_OK; }
+
+    double k1 = q.k1, k3 = q.k3, b = q.b, mnl = q.min_normlen;
+    if (k1 == 0 && k3 == 0 && b == 0 && mnl == 0) { k1 = 1; k3 = 1; b = 0.5; mnl = 0.5; }
+    uint32_t N = q.stats ? q.stats->collection_size : ix->doccount;
+    uint64_t tl = q.stats ? q.stats->total_length : ix->total_length;
+    double len_factor = 0;
+    if (!(b == 0 || k1 == 0)) {
+        double avg = N == 0 ? 0.0 : (double)tl / N;
+        len_factor = avg != 0 ? 1 / avg : 0;
+    }
+    double tw[XGM_MAX_TERMS], maxpart[XGM_MAX_TERMS];
+    for (uint32_t j = 0; j < n; ++j) {
+        uint32_t gtf = q.stats ? q.stats->termfreq[j] : ltf[j];
+        tw[j] = bm25_termweight(N, gtf, q.wqf ? q.wqf[j] : 1, 1.0, k1, k3);
+        uint32_t wub = ids[j] == 0xffffffffu ? 0 : ix->terms[ids[j]].wdf_ub;
+        maxpart[j] = bm25_maxpart(tw[j], len_factor, k1, b, mnl, wub, ix->doclen_lb);
+    }
+    dq.op = q.op; dq.nterms = n; dq.topk = pq.topk; dq.check_at_least = cal;
+    dq.len_factor = len_factor; dq.k1 = k1; dq.b = b; dq.one_minus_b = 1 - b; dq.min_normlen = mnl;
+    dq.filter = q.filter; dq.filter_slot = q.filter_slot; dq.range_lo = q.range_lo; dq.range_hi = q.range_hi;
+    dq.sort_by = q.sort_by; dq.sort_slot = q.sort_slot; dq.sort_reverse = q.sort_reverse; dq.sort_use_max = q.sort_use_max;
+    double dbsize = ix->doccount;
+    uint32_t order[XGM_MAX_TERMS];
+    bool any_absent = false;
+    for (uint32_t j = 0; j < n; ++j) any_absent |= (ltf[j] == 0);
+    if (q.op == XGM_OP_AND || n == 1) {
+        TfIdx in[XGM_MAX_TERMS], outv[XGM_MAX_TERMS];
+        for (uint32_t j = 0; j < n; ++j) { in[j].tf = ltf[j]; in[j].idx = j; }
+        std::partial_sort_copy(in, in + n, outv, outv + n, [](const TfIdx& a, const TfIdx& c) { return a.tf < c.tf; });
+        for (uint32_t j = 0; j < n; ++j) order[j] = outv[j].idx;
+        /* MultiAndPostList::recalc_maxweight / get_termfreq_{min,max,est}, multiandpostlist.cc:55-105,161-171 */
+        double mp = 0;
+        for (uint32_t i = 0; i < n; ++i) mp += maxpart[order[i]];
+        pq.max_possible = n == 1 ? maxpart[0] : mp;
+        uint32_t sum = ltf[order[0]];
+        if (sum) {
+            for (uint32_t i = 1; i < n; ++i) {
+                uint32_t old = sum;
+                sum += ltf[order[i]];
+                if (sum >= old && sum <= ix->doccount) { sum = 0; break; }
+                sum -= ix->doccount;
+            }
+        }
+        pq.tf_min = sum;
+        pq.tf_max = ltf[order[0]];
+        for (uint32_t i = 1; i < n; ++i) pq.tf_max = std::min(pq.tf_max, ltf[order[i]]);
+        double r = ltf[order[0]];
+        for (uint32_t i = 1; i < n; ++i) r = (r * ltf[order[i]]) / dbsize;
+        pq.tf_est = ix->doccount ? (uint32_t)(r + 0.5) : 0;
+        dq.route = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            uint32_t j = order[i];
+            dq.terms[i].termweight = tw[j];
+            if (ids[j] != 0xffffffffu) { dq.terms[i].blk_begin = ix->terms[ids[j]].blk_begin; dq.terms[i].nblocks = ix->terms[ids[j]].nblocks; }
+        }
+    } else {
+        /* OR of leaves: Huffman-shaped tree of binary OrPostLists */
+        OrTree tr;
+        build_or_tree(ltf, n, tr);
+        /* postfix program + folded bounds */
+        int stack[4 * XGM_MAX_TERMS], sp = 0, outrev[2 * XGM_MAX_TERMS], nr = 0;
+        stack[sp++] = tr.root;
+        while (sp) {
+            int x = stack[--sp];
+            outrev[nr++] = x;
+            if (x >= (int)n) { stack[sp++] = tr.lch[x]; stack[sp++] = tr.rch[x]; }
+        }
+        double sm[2 * XGM_MAX_TERMS], se[2 * XGM_MAX_TERMS];
+        uint32_t smin[2 * XGM_MAX_TERMS], smax[2 * XGM_MAX_TERMS];
+        int p = 0;
+        dq.prog_len = 0;
+        for (int i = nr - 1; i >= 0; --i) {
+            int x = outrev[i];
+            if (x < (int)n) {
+                dq.prog[dq.prog_len++] = (int8_t)x;
+                sm[p] = maxpart[x]; se[p] = smin[p] = smax[p] = ltf[x]; ++p;
+            } else {
+                dq.prog[dq.prog_len++] = -1;
+                --p;
+                sm[p - 1] = sm[p - 1] + sm[p];
+                smin[p - 1] = std::max(smin[p - 1], smin[p]);
+                uint32_t lm = smax[p - 1], t = lm + smax[p];
+                if (t > ix->doccount || t < lm) t = ix->doccount;
+                smax[p - 1] = t;
+                double a = (double)(uint32_t)se[p - 1], c2 = (double)(uint32_t)se[p];
+                se[p - 1] = dbsize == 0.0 ? 0 : (uint32_t)(a + c2 - (a * c2 / dbsize) + 0.5);
+            }
+        }
+        pq.max_possible = sm[0]; pq.tf_min = smin[0]; pq.tf_max = smax[0]; pq.tf_est = (uint32_t)se[0];
+        dq.route = 1;
+        for (uint32_t j = 0; j < n; ++j) {
+            dq.terms[j].termweight = tw[j];
+            if (ids[j] != 0xffffffffu) { dq.terms[j].blk_begin = ix->terms[ids[j]].blk_begin; dq.terms[j].nblocks = ix->terms[ids[j]].nblocks; }
+        }
+    }
+    /* algorithmic bytes, SURVEY.md §8(d): compressed columns + 16 B per block header of every query
+     * term (full lists, no credit for skipping) + 16 B per result; 4 B per candidate added at wait() */
+    for (uint32_t j = 0; j < n; ++j)
+        if (ids[j] != 0xffffffffu) pq.alg_bytes += ix->terms[ids[j]].bytes;
+    pq.alg_bytes += 16ull * pq.topk;
+
+    if (cal == 0 || pq.topk == 0) { pq.on_device = false; return XGM_OK; } /* bounds only, matcher.cc:437-461 */
+    if (dq.route == 0 && any_absent) { pq.on_device = false; return XGM_OK; } /* AND with an absent term: empty */
+    if (dq.route == 1) { pq.status = XGM_E_UNIMPLEMENTED; return XGM_OK; }    /* dense kernel: next milestone */
+    pq.on_device = true;
+    uint32_t nb = dq.terms[0].nblocks;
+    for (uint32_t b0 = 0; b0 < nb; b0 += blocks_per_item) {
+        XgmWorkItem wi;
+        wi.query = qi; wi.b0 = b0; wi.b1 = std::min(nb, b0 + blocks_per_item); wi.pad = 0;
+        items.push_back(wi);
+    }
+    return XGM_OK;
+}
+
+static xgm_status launch_batch(xgm_searcher* s) {
+    XgmKernelParams& p = s->params;
+    CUDA_TRY(cudaMemsetAsync(s->d_ctrl, 0, ((size_t)s->nq + 1) * 4, s->stream));
+    CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+    if (s->nitems) CUDA_TRY(xgm_launch_and(p, s->grid, s->stream));
+    CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+    CUDA_TRY(xgm_launch_topk(p, s->nq, s->stream));
+    CUDA_TRY(cudaEventRecord(s->ev2, s->stream));
+    s->stats.kernel_launches = (s->nitems ? 1u : 0u) + 1u;
+    return XGM_OK;
+}
+
+extern "C" xgm_status xgm_search_submit(xgm_searcher* s, const xgm_query* queries, uint32_t nq) {
+    if (!s || !queries || nq == 0) return fail(XGM_E_INVALID, "bad arguments");
+    if (nq > s->max_batch) return fail(XGM_E_INVALID, "batch %u > max_batch %u", nq, s->max_batch);
+    if (s->pending) return fail(XGM_E_INVALID, "previous batch not waited for");
+    CUDA_TRY(cudaSetDevice(s->ix->device));
+    s->plan.resize(nq);
+    s->nq = nq;
+    /* work granularity: enough items to balance ~grid*8 warps, at most 32 driver blocks per item */
+    uint64_t total_drv_blocks = 0;
+    std::vector<XgmWorkItem> items;
+    items.reserve(4096);
+    /* first pass with a provisional granularity needs the driver block counts; plan twice is wasteful,
+     * so use a fixed small granularity scaled by batch size */
+    uint32_t bpi = nq >= 256 ? 16 : (nq >= 16 ? 4 : 1);
+    s->any_sort = false;
+    uint64_t alg = 0, postings = 0;
+    for (uint32_t i = 0; i < nq; ++i) {
+        xgm_status st = plan_query(s, queries[i], i, s->plan[i], s->h_queries[i], items, bpi);
+        if (st != XGM_OK) return st;
+        if (s->plan[i].sort_by) s->any_sort = true;
+        alg += s->plan[i].alg_bytes;
+        total_drv_blocks += s->h_queries[i].terms[0].nblocks;
+    }
+    (void)total_drv_blocks; (void)postings;
+    xgm_status st = ensure_items(s, items.size());
+    if (st != XGM_OK) return st;
+    if (!items.empty()) memcpy(s->h_items, items.data(), items.size() * sizeof(XgmWorkItem));
+    s->nitems = (uint32_t)items.size();
+    s->stats = xgm_batch_stats{};
+    s->stats.algorithmic_bytes = alg;
+    s->stats.work_items = s->nitems;
+    XgmKernelParams& p = s->params;
+    fill_index_params(s->ix, p);
+    p.queries = s->d_queries; p.items = s->d_items; p.nitems = s->nitems; p.nq = nq;
+    p.work_counter = s->d_ctrl; p.match_count = s->d_ctrl + 1; p.match_cap = s->match_cap;
+    p.match_w = s->d_match_w; p.match_d = s->d_match_d; p.match_k = s->d_match_k;
+    p.out_stride = s->max_topk; p.out_w = s->d_out_w; p.out_d = s->d_out_d; p.out_k = s->d_out_k; p.out_info = s->d_info;
+    CUDA_TRY(cudaMemcpyAsync(s->d_queries, s->h_queries, (size_t)nq * sizeof(XgmDevQuery), cudaMemcpyHostToDevice, s->stream));
+    if (s->nitems)
+        CUDA_TRY(cudaMemcpyAsync(s->d_items, s->h_items, (size_t)s->nitems * sizeof(XgmWorkItem), cudaMemcpyHostToDevice, s->stream));
+    st = launch_batch(s);
+    if (st != XGM_OK) return st;
+    size_t ns = (size_t)nq * s->max_topk;
+    CUDA_TRY(cudaMemcpyAsync(s->h_info, s->d_info, (size_t)nq * sizeof(XgmDevResult), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->h_out_w, s->d_out_w, ns * 8, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->h_out_d, s->d_out_d, ns * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (s->any_sort) CUDA_TRY(cudaMemcpyAsync(s->h_out_k, s->d_out_k, ns * 8, cudaMemcpyDeviceToHost, s->stream));
+    s->pending = true;
+    return XGM_OK;
+}
+
+static void finish_info(const PlannedQuery& pq, const XgmDevResult* dr, const double* w, xgm_mset_info* o) {
+    memset(o, 0, sizeof(*o));
+    o->first = pq.first;
+    o->status = pq.status;
+    o->max_possible = pq.max_possible;
+    if (pq.status != XGM_OK) return;
+    uint32_t lb = pq.tf_min, est = pq.tf_est, ub = pq.tf_max;
+    uint32_t size = 0, known = 0;
+    double max_w = 0;
+    if (pq.on_device) {
+        size = dr->n; known = dr->known; o->exact_matches = dr->exact;
+        max_w = dr->max_w;
+        (void)w;
+        /* ProtoMSet::finalise, protomset.h:484-612 (no collapser / decider / percent cut-off) */
+        if (size != pq.topk) lb = est = ub = size;
+        else if (known < pq.check_at_least) lb = est = ub = known;
+        else { lb = std::max(lb, known); est = std::max(est, known); }
+        if (dr->flags & 1u) o->status = XGM_E_UNIMPLEMENTED; /* overflow: needs the dense kernel */
+    } else if (pq.check_at_least != 0) {
+        lb = est = ub = 0; /* empty result set: !full() branch */
+    }
+    o->matches_lower_bound = o->uncollapsed_lower_bound = lb;
+    o->matches_estimated = o->uncollapsed_estimated = est;
+    o->matches_upper_bound = o->uncollapsed_upper_bound = ub;
+    o->max_attained = max_w;
+    o->n = size > pq.first ? size - pq.first : 0;
+    if (size != 0 && max_w != 0.0) {
+        /* ProtoMSet::finalise_percentages protomset.h:466-471: AND → every subquery matched */
+        double percent_scale = (double)dr->max_subqs / (double)pq.nterms;
+        percent_scale /= max_w;
+        o->percent_scale_factor = percent_scale * 100.0;
+    }
+}
+
+extern "C" xgm_status xgm_search_wait(xgm_searcher* s, uint32_t* docids, double* weights, uint64_t* sort_keys,
+                                      uint32_t stride, xgm_mset_info* info) {
+    if (!s || !info) return fail(XGM_E_INVALID, "null argument");
+    if (!s->pending) return fail(XGM_E_INVALID, "no batch submitted");
+    CUDA_TRY(cudaSetDevice(s->ix->device));
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    s->pending = false;
+    if (e != cudaSuccess) return fail(XGM_E_CUDA, "batch failed: %s", cudaGetErrorString(e));
+    cudaEventElapsedTime(&s->stats.match_kernel_ms, s->ev0, s->ev1);
+    cudaEventElapsedTime(&s->stats.topk_kernel_ms, s->ev1, s->ev2);
+    for (uint32_t i = 0; i < s->nq; ++i) {
+        const PlannedQuery& pq = s->plan[i];
+        const size_t off = (size_t)i * s->max_topk;
+        finish_info(pq, &s->h_info[i], s->h_out_w + off, &info[i]);
+        if (pq.status == XGM_OK && pq.on_device) s->stats.algorithmic_bytes += 4ull * s->h_info[i].exact;
+        uint32_t n = info[i].n;
+        if (n > stride) return fail(XGM_E_INVALID, "stride %u too small for %u results", stride, n);
+        if (n && docids && weights) {
+            memcpy(docids + (size_t)i * stride, s->h_out_d + off + pq.first, (size_t)n * 4);
+            memcpy(weights + (size_t)i * stride, s->h_out_w + off + pq.first, (size_t)n * 8);
+            if (sort_keys && pq.sort_by) memcpy(sort_keys + (size_t)i * stride, s->h_out_k + off + pq.first, (size_t)n * 8);
+        }
+    }
+    return XGM_OK;
+}
+
+extern "C" xgm_status xgm_search_batch(xgm_searcher* s, const xgm_query* queries, uint32_t nq, uint32_t* docids,
+                                       double* weights, uint64_t* sort_keys, uint32_t stride, xgm_mset_info* info) {
+    xgm_status st = xgm_search_submit(s, queries, nq);
+    if (st != XGM_OK) return st;
+    return xgm_search_wait(s, docids, weights, sort_keys, stride, info);
+}
+
+extern "C" xgm_status xgm_search(xgm_searcher* s, const xgm_query* query, uint32_t* docids, double* weights,
+                                 uint64_t* sort_keys, uint32_t capacity, xgm_mset_info* info) {
+    return xgm_search_batch(s, query, 1, docids, weights, sort_keys, capacity, info);
+}
+
+extern "C" xgm_status xgm_search_replay(xgm_searcher* s) {
+    if (!s || s->nq == 0) return fail(XGM_E_INVALID, "no resident batch");
+    if (s->pending) return fail(XGM_E_INVALID, "previous batch not waited for");
+    CUDA_TRY(cudaSetDevice(s->ix->device));
+    return launch_batch(s);
+}
+
+extern "C" xgm_status xgm_search_device_results(xgm_searcher* s, void** weights, void** docids, void** counts, uint32_t* stride) {
+    if (!s) return fail(XGM_E_INVALID, "null argument");
+    if (weights) *weights = s->d_out_w;
+    if (docids) *docids = s->d_out_d;
+    if (counts) *counts = s->d_info;
+    if (stride) *stride = s->max_topk;
+    return XGM_OK;
+}
+
+extern "C" xgm_status xgm_search_last_stats(xgm_searcher* s, xgm_batch_stats* out) {
+    if (!s || !out) return fail(XGM_E_INVALID, "null argument");
+    if (!s->pending && s->nq) {
+        cudaEventSynchronize(s->ev2);
+        cudaEventElapsedTime(&s->stats.match_kernel_ms, s->ev0, s->ev1);
+        cudaEventElapsedTime(&s->stats.topk_kernel_ms, s->ev1, s->ev2);
+    }
+    *out = s->stats;
+    return XGM_OK;
+}
+
+/* ------------------------------------------------------------------ multi-shard merge */
+
+extern "C" void xgm_unshard(uint32_t* docids, uint32_t n, uint32_t shard, uint32_t nshards) {
+    /* unshard(), src/xapian/backends/multi.h:66-70 */
+    for (uint32_t i = 0; i < n; ++i) docids[i] = (docids[i] - 1) * nshards + shard + 1;
+}
+
+namespace {
+struct MItem { double w; uint32_t d; uint64_t k; };
+struct MCmp {
+    uint32_t sort_by, reverse;
+    bool operator()(const MItem& a, const MItem& b) const {
+        if (sort_by == XGM_SORT_VAL_REL || sort_by == XGM_SORT_VAL) {
+            if (a.k > b.k) return reverse != 0;
+            if (a.k < b.k) return reverse == 0;
+            if (sort_by == XGM_SORT_VAL) return a.d < b.d;
+        }
+        if (a.w > b.w) return true;
+        if (a.w < b.w) return false;
+        if (sort_by == XGM_SORT_REL_VAL) {
+            if (a.k > b.k) return reverse != 0;
+            if (a.k < b.k) return reverse == 0;
+        }
+        return a.d < b.d;
+    }
+};
+}
+
+/* Matcher::merge_mset (matcher.cc:653-782) + MSet::Internal::merge_stats (api/mset.cc:376-395). The
+ * reference pops a heap of per-shard cursors under mcmp; under a strict total order that equals
+ * merging the sorted runs, done here with std::merge-style selection. */
+extern "C" xgm_status xgm_merge_msets(const uint32_t* const* docids, const double* const* weights,
+                                      const uint64_t* const* sort_keys, const xgm_mset_info* infos, uint32_t nparts,
+                                      uint32_t first, uint32_t maxitems, uint32_t sort_by, uint32_t sort_reverse,
+                                      uint32_t* out_docids, double* out_weights, uint64_t* out_sort_keys,
+                                      xgm_mset_info* out_info) {
+    if (!docids || !weights || !infos || !out_info || (maxitems && (!out_docids || !out_weights)))
+        return fail(XGM_E_INVALID, "null argument");
+    xgm_mset_info o;
+    memset(&o, 0, sizeof(o));
+    std::vector<MItem> all;
+    for (uint32_t p = 0; p < nparts; ++p) {
+        const xgm_mset_info& m = infos[p];
+        o.matches_lower_bound += m.matches_lower_bound; o.matches_estimated += m.matches_estimated;
+        o.matches_upper_bound += m.matches_upper_bound;
+        o.uncollapsed_lower_bound += m.uncollapsed_lower_bound; o.uncollapsed_estimated += m.uncollapsed_estimated;
+        o.uncollapsed_upper_bound += m.uncollapsed_upper_bound;
+        o.exact_matches += m.exact_matches;
+        o.max_possible = std::max(o.max_possible, m.max_possible);
+        if (m.max_attained > o.max_attained) { o.max_attained = m.max_attained; o.percent_scale_factor = m.percent_scale_factor; }
+        if (m.status != XGM_OK) o.status = m.status;
+        for (uint32_t i = 0; i < m.n; ++i)
+            all.push_back(MItem{weights[p][i], docids[p][i], (sort_keys && sort_keys[p]) ? sort_keys[p][i] : 0ull});
+    }
+    MCmp cmp{sort_by, sort_reverse};
+    std::sort(all.begin(), all.end(), cmp);
+    size_t n = all.size() > first ? all.size() - first : 0;
+    n = std::min<size_t>(n, maxitems);
+    for (size_t i = 0; i < n; ++i) {
+        out_docids[i] = all[first + i].d;
+        out_weights[i] = all[first + i].w;
+        if (out_sort_keys) out_sort_keys[i] = all[first + i].k;
+    }
+    o.n = (uint32_t)n;
+    o.first = first;
+    *out_info = o;
+    return XGM_OK;
+}
+
+extern "C" xgm_status xgm_merge_topk_device(const void*, const void*, const void*, uint32_t, uint32_t, uint32_t, uint32_t,
+                                            void*, void*, void*, void*) {
+    return fail(XGM_E_UNIMPLEMENTED, "device merge not built yet");
+}
