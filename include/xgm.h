@@ -155,8 +155,17 @@ typedef struct xgm_mset_info {
     uint32_t uncollapsed_lower_bound, uncollapsed_estimated, uncollapsed_upper_bound;
     uint32_t exact_matches;        /* documents matching the boolean structure */
     uint32_t status;               /* xgm_status for this query */
+    uint32_t flags;                /* XGM_MSET_* */
+    uint32_t reserved;
     double max_possible, max_attained, percent_scale_factor;
 } xgm_mset_info;
+
+/* ProtoMSet::known_matching_docs depends on the docid-order history of the match (SURVEY.md §7 hard
+ * part 3).  It is reproduced exactly whenever the whole match set fits the searcher's candidate
+ * buffer; for larger match sets that were pruned on the device the lower bound / estimate are
+ * conservative (still valid bounds) and this flag is set.  Docids, weights, max_possible,
+ * max_attained, the upper bound and exact_matches are always exact. */
+#define XGM_MSET_BOUNDS_APPROX 1u
 
 /* ---- searching ---------------------------------------------------------------------------- */
 /* A searcher owns a CUDA stream and pinned/device staging for batches of up to max_batch queries
@@ -195,6 +204,7 @@ typedef struct xgm_batch_stats {
     uint32_t kernel_launches;
     float match_kernel_ms;        /* CUDA-event time of the decode+intersect+score kernel(s) */
     float topk_kernel_ms;
+    uint64_t h2d_bytes, d2h_bytes; /* bytes the batch moved over PCIe (plan in, results out) */
 } xgm_batch_stats;
 xgm_status xgm_search_last_stats(xgm_searcher*, xgm_batch_stats* out);
 
@@ -208,7 +218,10 @@ xgm_status xgm_merge_msets(const uint32_t* const* docids, const double* const* w
                            uint32_t* out_docids, double* out_weights, uint64_t* out_sort_keys,
                            xgm_mset_info* out_info);
 /* Device-side merge after an all-gather of per-GPU top-k records: gathered weights/docids hold
- * nparts*nq*stride records laid out [part][query][rank]; local docids are unsharded on the fly. */
+ * nparts*nq*stride records laid out [part][query][rank], gathered_counts the per-part result records
+ * (the buffer xgm_search_device_results returns as `counts`, 32 bytes per query, first u32 = n);
+ * local docids are unsharded on the fly (part p = shard p of nparts). Outputs: [nq][k] weights and
+ * docids, [nq] counts. Relevance order only. */
 xgm_status xgm_merge_topk_device(const void* gathered_weights, const void* gathered_docids,
                                  const void* gathered_counts, uint32_t nparts, uint32_t nq, uint32_t stride,
                                  uint32_t k, void* out_weights, void* out_docids, void* out_counts,

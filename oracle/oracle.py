@@ -330,6 +330,54 @@ def ref_build(out_dir: str, ndocs: int, vocab: int, seed: int = 12345, nshards: 
     return json.loads(subprocess.check_output(cmd, env=e).decode().strip().splitlines()[-1])
 
 
+def ref_build_parallel(out_dir: str, ndocs: int, vocab: int, seed: int = 12345, procs: int = 8,
+                       values: bool = False, compact: bool = True) -> dict:
+    """Write the corpus as `procs` contiguous docid-range glass DBs in parallel (one writer process
+    each), then Database::compact them into one DB whose docids are the corpus docids.  Returns timing
+    info; the result lives in out_dir/db (or out_dir/part*/ when compact=False)."""
+    import time
+    os.makedirs(out_dir, exist_ok=True)
+    marker = os.path.join(out_dir, "READY.json")
+    if os.path.exists(marker):
+        return json.load(open(marker))
+    procs = max(1, min(procs, ndocs))
+    per = (ndocs + procs - 1) // procs
+    e = dict(os.environ)
+    e.setdefault("XAPIAN_FLUSH_THRESHOLD", "200000")
+    t0 = time.time()
+    ps, parts = [], []
+    for i in range(procs):
+        a, b = i * per + 1, min(ndocs, (i + 1) * per)
+        if a > b:
+            break
+        d = os.path.join(out_dir, f"part{i:03d}")
+        parts.append(d)
+        cmd = [REF_RUNNER, "build", "--out", d, "--docs", str(ndocs), "--vocab", str(vocab), "--seed", str(seed),
+               "--range-first", str(a), "--range-last", str(b)]
+        if values:
+            cmd.append("--values")
+        ps.append(subprocess.Popen(cmd, env=e, stdout=subprocess.DEVNULL))
+    for p in ps:
+        if p.wait() != 0:
+            raise RuntimeError("reference build failed")
+    t1 = time.time()
+    info = dict(ndocs=ndocs, vocab=vocab, seed=seed, procs=len(parts), build_s=round(t1 - t0, 2))
+    if compact and len(parts) > 1:
+        cmd = [REF_RUNNER, "compact", "--out", os.path.join(out_dir, "db")]
+        for d in parts:
+            cmd += ["--db", d]
+        subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+        info["compact_s"] = round(time.time() - t1, 2)
+        info["dbs"] = [os.path.join(out_dir, "db")]
+        import shutil
+        for d in parts:
+            shutil.rmtree(d, ignore_errors=True)
+    else:
+        info["dbs"] = parts
+    json.dump(info, open(marker, "w"))
+    return info
+
+
 def query_line(op: str, terms: Sequence[str], first: int, maxitems: int, check_at_least: int = 0,
                vr: Optional[tuple] = None, sort: Optional[tuple] = None) -> str:
     s = f"{op} {first} {maxitems} {check_at_least} {len(terms)} " + " ".join(terms)

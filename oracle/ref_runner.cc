@@ -6,7 +6,11 @@
  * bench.py.  The product never links or executes this.
  *
  *   ref_runner build  --out DIR --docs N --vocab V --seed S [--nshards n --shard s] [--values]
- *                     [--termlist]                      write a glass DB through WritableDatabase
+ *                     [--termlist] [--range-first a --range-last b]
+ *                                                       write a glass DB through WritableDatabase
+ *                                                       (--range-*: only global docids a..b, as local 1..)
+ *   ref_runner compact --db DIR [--db DIR ...] --out DIR   Database::compact (renumbering by offset, so
+ *                                                       contiguous docid-range parts give back the corpus)
  *   ref_runner query  --db DIR [--db DIR ...] [--twophase] --queries FILE [--threads T]
  *                     [--repeat R] [--dump FILE]        Enquire::get_mset over the query list
  *   ref_runner export --db DIR --out FILE               dump postings/doclens/values through the
@@ -73,6 +77,10 @@ static int cmd_build(const Args& a) {
     uint32_t nshards = (uint32_t)strtoul(a.get("--nshards", "1").c_str(), nullptr, 10);
     uint32_t shard = (uint32_t)strtoul(a.get("--shard", "0").c_str(), nullptr, 10);
     bool values = a.flag("--values");
+    uint32_t rfirst = (uint32_t)strtoul(a.get("--range-first", "1").c_str(), nullptr, 10);
+    uint32_t rlast = (uint32_t)strtoul(a.get("--range-last", "0").c_str(), nullptr, 10);
+    if (rlast == 0 || rlast > N) rlast = N;
+    if (rfirst < 1) rfirst = 1;
     int flags = Xapian::DB_CREATE_OR_OVERWRITE | Xapian::DB_BACKEND_GLASS;
     if (!a.flag("--termlist")) flags |= Xapian::DB_NO_TERMLIST;
 
@@ -85,7 +93,9 @@ static int cmd_build(const Args& a) {
     Xapian::WritableDatabase db(out, flags);
     uint32_t ranks[XGM_CORPUS_MAX_LEN], wdf[XGM_CORPUS_MAX_LEN];
     uint32_t local = 0;
-    for (uint32_t d = shard + 1; d <= N; d += nshards) {
+    uint32_t dstart = shard + 1;
+    while (dstart < rfirst) dstart += nshards;
+    for (uint32_t d = dstart; d <= rlast; d += nshards) {
         uint32_t len = xgm_corpus_doc(&z, seed, d, ranks);
         uint32_t n = xgm_corpus_collapse(ranks, len, wdf);
         Xapian::Document doc;
@@ -108,6 +118,17 @@ static int cmd_build(const Args& a) {
     xgm_zipf_free(&z);
     printf("{\"cmd\":\"build\",\"out\":\"%s\",\"docs\":%u,\"shard\":%u,\"nshards\":%u,\"seconds\":%.3f}\n",
            out.c_str(), local, shard, nshards, now_s() - t0);
+    return 0;
+}
+
+static int cmd_compact(const Args& a) {
+    std::vector<std::string> dbs = a.all("--db");
+    if (dbs.empty()) die("need --db");
+    double t0 = now_s();
+    Xapian::Database db;
+    for (auto& p : dbs) db.add_database(Xapian::Database(p));
+    db.compact(a.get("--out"), 0, 0);
+    printf("{\"cmd\":\"compact\",\"parts\":%zu,\"seconds\":%.3f}\n", dbs.size(), now_s() - t0);
     return 0;
 }
 
@@ -349,6 +370,7 @@ int main(int argc, char** argv) {
         if (cmd == "build") return cmd_build(a);
         if (cmd == "query") return cmd_query(a);
         if (cmd == "export") return cmd_export(a);
+        if (cmd == "compact") return cmd_compact(a);
     } catch (const Xapian::Error& e) {
         die("xapian: " + e.get_description());
     }

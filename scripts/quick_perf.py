@@ -32,6 +32,21 @@ for it in range(5):
                           topk_ms=round(st.topk_kernel_ms, 3), items=st.work_items, alg_MB=round(st.algorithmic_bytes / 1e6, 1),
                           alg_GBps=round(st.algorithmic_bytes / 1e6 / max(st.match_kernel_ms, 1e-6), 1), overflow=nover,
                           mean_hits=float(np.mean([inf[i].exact_matches for i in range(nq)])))))
+# OR 5-term top-1000 (config C3)
+nqo = 200
+oq = [xgm.Query(xgm.OP_OR, [f"T{r:06d}" for r in rng.sample(range(1000), 5)], maxitems=1000) for _ in range(nqo)]
+ob = xgm.QueryBatch(oq)
+so = xgm.Searcher(ix, max_batch=nqo, max_topk=1000)
+for it in range(3):
+    t0 = time.time()
+    so.submit(ob)
+    d2, w2, k2, inf2 = so.wait_raw()
+    dt = time.time() - t0
+    st = so.last_stats()
+    print(json.dumps(dict(or_iter=it, e2e_ms=round(dt * 1e3, 3), qps=round(nqo / dt), match_ms=round(st.match_kernel_ms, 3),
+                          topk_ms=round(st.topk_kernel_ms, 3), items=st.work_items, bad=sum(1 for i in range(nqo) if inf2[i].status != 0),
+                          approx=sum(1 for i in range(nqo) if inf2[i].flags & 1),
+                          mean_hits=float(np.mean([inf2[i].exact_matches for i in range(nqo)])))))
 # replay timing (device only)
 import ctypes
 for it in range(3):

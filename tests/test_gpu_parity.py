@@ -36,12 +36,18 @@ def to_o(q):
 def run_and_compare(ix, orc, queries, max_topk=128, check_counts=True):
     s = xgm.Searcher(ix, max_batch=max(1, len(queries)), max_topk=max_topk)
     res = s.search([to_x(q) for q in queries])
-    noverflow = 0
+    napprox = 0
     for i, (q, m) in enumerate(zip(queries, res)):
         ref = orc.match(to_o(q))
-        assert_mset_equal(m, ref, ctx=f"query {i} {q}", check_counts=check_counts)
+        approx = bool(m.flags & 1)
+        napprox += approx
+        assert_mset_equal(m, ref, ctx=f"query {i} {q}", check_counts=check_counts and not approx)
+        # always exact, pruned or not
+        assert m.exact_matches == ref.exact and m.matches_upper_bound == ref.ub
+        if approx:  # conservative but valid bounds
+            assert m.matches_lower_bound <= ref.lb and m.matches_lower_bound <= m.matches_estimated_raw <= ref.ub
     s.close()
-    return res
+    return res, napprox
 
 
 def test_index_info_and_roundtrip(small):
@@ -102,3 +108,39 @@ def test_single_query_calls_match_batch(small):
     for q, b in zip(qs, batch):
         one = s.search([to_x(q)])[0]
         assert np.array_equal(one.docids, b.docids) and one.weights.tobytes() == b.weights.tobytes()
+
+
+def test_or_5term_top1000(small):
+    ix, orc, nd, V = small
+    rng = random.Random(6)
+    qs = gen_queries(rng, 60, 1000, nd, ops=("OR",), ks=(5,), maxitems=(1000,))
+    run_and_compare(ix, orc, qs, max_topk=1000)
+
+
+def test_or_various_shapes_exact_counts(small):
+    ix, orc, nd, V = small
+    rng = random.Random(7)
+    qs = gen_queries(rng, 120, 2000, nd, ops=("OR",), ks=(2, 3, 5, 8), maxitems=(1, 10, 100), first=(0, 0, 5))
+    qs += gen_queries(rng, 60, 2000, nd, ops=("OR",), ks=(2, 4), maxitems=(10, 100), check_all=True)
+    res, napprox = run_and_compare(ix, orc, qs)
+
+
+def test_dense_terms_force_pruning(small):
+    """Queries over the most frequent terms have far more matches than the candidate buffer:
+    the threshold pruning must still return the exact top-k."""
+    ix, orc, nd, V = small
+    rng = random.Random(8)
+    qs = []
+    for _ in range(40):
+        qs.append(dict(op="AND", terms=rng.sample(range(8), rng.choice([1, 2, 3])), first=0,
+                       maxitems=rng.choice([10, 100]), check_at_least=0))
+        qs.append(dict(op="OR", terms=rng.sample(range(12), rng.choice([2, 3, 5])), first=rng.choice([0, 4]),
+                       maxitems=rng.choice([10, 100]), check_at_least=0))
+    res, napprox = run_and_compare(ix, orc, qs)
+    assert napprox > 0  # the pruned path was really exercised
+
+
+def test_or_medium_index(medium):
+    ix, orc, nd, V = medium
+    rng = random.Random(9)
+    run_and_compare(ix, orc, gen_queries(rng, 40, 1000, nd, ops=("OR",), ks=(5,), maxitems=(1000,)), max_topk=1000)

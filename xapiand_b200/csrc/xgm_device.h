@@ -17,7 +17,7 @@ struct XgmDevResult {
     uint32_t n;      /* entries written to out_* (<= topk) */
     uint32_t exact;  /* documents matching the boolean structure */
     uint32_t known;  /* ProtoMSet::known_matching_docs */
-    uint32_t flags;  /* bit0: match buffer overflowed (query must be re-run on the dense kernel) */
+    uint32_t flags;  /* bit0: candidates were lost (buffer overflow); bit1: match-count bounds approximate */
     double max_w;    /* dense kernel: best weight seen */
     uint32_t max_subqs;
     uint32_t pad;
@@ -33,13 +33,17 @@ struct XgmKernelParams {
     XgmDevSlot slots[XGM_MAX_SLOTS];
     /* batch */
     const XgmDevQuery* queries;
-    const XgmWorkItem* items;
-    uint32_t nitems;
+    const XgmWorkItem* items;     /* AND kernel work list */
+    const XgmWorkItem* items_or;  /* OR kernel work list */
+    uint32_t nitems, nitems_or;
     uint32_t nq;
-    uint32_t* work_counter;
-    /* per-query match buffers (sparse AND kernel) */
+    uint32_t* work_counter;       /* [0] AND items, [1] OR items, [2],[3] same for the second pass, [4] #queries to re-run */
+    uint32_t pass;                /* 0 = first pass, 1 = re-run of overflowed queries with their exact b* */
+    XgmQState* qstate;            /* [nq] */
+    uint32_t* hist;               /* [nq][XGM_NBINS] */
+    /* per-query match buffers */
     uint32_t match_cap;
-    uint32_t* match_count;
+    uint32_t keep_cap;            /* survivors the top-k kernel can rank in shared memory */
     double* match_w;
     uint32_t* match_d;
     uint64_t* match_k;
@@ -52,10 +56,15 @@ struct XgmKernelParams {
 };
 
 cudaError_t xgm_launch_and(const XgmKernelParams& p, int grid, cudaStream_t s);
+cudaError_t xgm_launch_or(const XgmKernelParams& p, int grid, cudaStream_t s);
+int xgm_or_occupancy_blocks_per_sm();
 cudaError_t xgm_launch_topk(const XgmKernelParams& p, uint32_t nq, cudaStream_t s);
 cudaError_t xgm_launch_decode(const XgmKernelParams& p, uint32_t blk_begin, uint32_t nblocks, uint32_t* out_d,
                               uint32_t* out_w, cudaStream_t s);
-size_t xgm_topk_smem_bytes(uint32_t match_cap);
+size_t xgm_topk_smem_bytes(uint32_t keep_cap);
+cudaError_t xgm_launch_merge(const double* gw, const uint32_t* gd, const XgmDevResult* ginfo, uint32_t nparts, uint32_t nq,
+                             uint32_t stride, uint32_t k, double* out_w, uint32_t* out_d, uint32_t* out_n,
+                             cudaStream_t s);
 int xgm_and_occupancy_blocks_per_sm();
 
 #endif

@@ -21,6 +21,7 @@
 #define XGM_BLOCK 128u
 #define XGM_SENTINEL 0xFFFFFFFFu
 #define XGM_DEV_MAX_TERMS 16u
+#define XGM_NBINS 1024u  /* histogram bins of the top-k pruning threshold */
 
 struct XgmBlockHdr {
     uint32_t first;    /* docid of the block's first posting */
@@ -47,8 +48,9 @@ struct XgmDevQuery {
     uint32_t sort_by, sort_slot, sort_reverse, sort_use_max;
     uint32_t prog_len;
     int8_t prog[2 * XGM_DEV_MAX_TERMS]; /* OR: postfix program over leaves (>=0) and '+' (-1) */
-    uint32_t route;                     /* 0 = sparse AND kernel, 1 = dense tile kernel */
+    uint32_t route;                     /* 0 = AND kernel, 1 = OR kernel */
     uint32_t pad;
+    double bucket_scale;                /* XGM_NBINS / max_possible (or / (max sort key + 1)) */
     XgmDevTerm terms[XGM_DEV_MAX_TERMS]; /* AND: ascending termfreq (MultiAndPostList order) */
 };
 
@@ -58,11 +60,14 @@ struct XgmWorkItem {
     uint32_t pad;
 };
 
-/* per-query match record */
-struct XgmMatch {
-    double w;
-    uint32_t did;
-    uint32_t aux;
+/* per-query running state of a batch (zeroed before every launch) */
+struct XgmQState {
+    uint32_t total;            /* documents matching the boolean structure */
+    uint32_t stored;           /* matches appended to the query's buffer (not yet prunable when seen) */
+    uint32_t bstar;            /* pruning bucket: matches below it cannot reach the top-k any more */
+    uint32_t rerun;            /* set by the top-k kernel: buffer overflowed, second pass with exact b* */
+    unsigned long long maxw;   /* bit pattern of the best weight over all matches */
+    unsigned long long pad2;
 };
 
 #endif

@@ -109,6 +109,7 @@ struct xgm_index {
     uint32_t* d_doclen = nullptr;
     uint32_t* d_voff[XGM_MAX_SLOTS] = {};
     uint64_t* d_vals[XGM_MAX_SLOTS] = {};
+    uint64_t slot_max[XGM_MAX_SLOTS] = {};
     int sm_count = 148;
 };
 
@@ -250,6 +251,7 @@ static xgm_status upload_index(xgm_index* ix, std::vector<Chunk>& chunks, const 
         CUDA_TRY(cudaMalloc(&ix->d_vals[s], std::max<size_t>(1, slots[s].vals.size()) * 8));
         if (!slots[s].vals.empty())
             CUDA_TRY(cudaMemcpy(ix->d_vals[s], slots[s].vals.data(), slots[s].vals.size() * 8, cudaMemcpyHostToDevice));
+        for (uint64_t v : slots[s].vals) ix->slot_max[s] = std::max(ix->slot_max[s], v);
     }
     ix->nblocks = 0;
     ix->npostings = 0;
@@ -595,7 +597,7 @@ extern "C" xgm_status xgm_index_decode_term(const xgm_index* ix, uint32_t term_i
     if (term_id >= ix->terms.size()) return fail(XGM_E_INVALID, "term id out of range");
     const TermInfo& t = ix->terms[term_id];
     *n = t.termfreq;
-    if (t.termfreq == 0) return XGM_OK;
+    if (t.termfreq == 0 || (!docids && !wdfs && capacity == 0)) return XGM_OK;
     if (capacity < t.termfreq || !docids || !wdfs) return fail(XGM_E_INVALID, "capacity %u < termfreq %u", capacity, t.termfreq);
     CUDA_TRY(cudaSetDevice(ix->device));
     uint32_t *dd = nullptr, *dw = nullptr;
@@ -633,15 +635,19 @@ struct xgm_searcher {
     /* pinned host staging */
     XgmDevQuery* h_queries = nullptr;
     XgmWorkItem* h_items = nullptr;
+    XgmWorkItem* h_items_or = nullptr;
     double* h_out_w = nullptr;
     uint32_t* h_out_d = nullptr;
     uint64_t* h_out_k = nullptr;
     XgmDevResult* h_info = nullptr;
-    size_t items_cap = 0;
+    size_t items_cap = 0, items_or_cap = 0;
+    uint32_t keep_cap = 0;
+    size_t ctrl_bytes = 0;
     /* device */
     XgmDevQuery* d_queries = nullptr;
     XgmWorkItem* d_items = nullptr;
-    uint32_t* d_ctrl = nullptr; /* [0] work counter, [1..] match counts */
+    XgmWorkItem* d_items_or = nullptr;
+    unsigned char* d_ctrl = nullptr; /* [16 B work counters][nq x XgmQState][nq x XGM_NBINS x u32] */
     double* d_match_w = nullptr;
     uint32_t* d_match_d = nullptr;
     uint64_t* d_match_k = nullptr;
@@ -651,10 +657,10 @@ struct xgm_searcher {
     XgmDevResult* d_info = nullptr;
     /* last batch */
     std::vector<PlannedQuery> plan;
-    uint32_t nq = 0, nitems = 0;
+    uint32_t nq = 0, nitems = 0, nitems_or = 0;
     bool pending = false, any_sort = false;
     xgm_batch_stats stats{};
-    int grid = 0;
+    int grid = 0, grid_or = 0;
     XgmKernelParams params;
 };
 
@@ -662,9 +668,9 @@ extern "C" void xgm_searcher_free(xgm_searcher* s) {
     if (!s) return;
     cudaSetDevice(s->ix->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    cudaFreeHost(s->h_queries); cudaFreeHost(s->h_items); cudaFreeHost(s->h_out_w); cudaFreeHost(s->h_out_d);
+    cudaFreeHost(s->h_queries); cudaFreeHost(s->h_items); cudaFreeHost(s->h_items_or); cudaFreeHost(s->h_out_w); cudaFreeHost(s->h_out_d);
     cudaFreeHost(s->h_out_k); cudaFreeHost(s->h_info);
-    cudaFree(s->d_queries); cudaFree(s->d_items); cudaFree(s->d_ctrl); cudaFree(s->d_match_w); cudaFree(s->d_match_d);
+    cudaFree(s->d_queries); cudaFree(s->d_items); cudaFree(s->d_items_or); cudaFree(s->d_ctrl); cudaFree(s->d_match_w); cudaFree(s->d_match_d);
     cudaFree(s->d_match_k); cudaFree(s->d_out_w); cudaFree(s->d_out_d); cudaFree(s->d_out_k); cudaFree(s->d_info);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -673,18 +679,21 @@ extern "C" void xgm_searcher_free(xgm_searcher* s) {
     delete s;
 }
 
-static xgm_status ensure_items(xgm_searcher* s, size_t need) {
-    if (need <= s->items_cap) return XGM_OK;
+static xgm_status ensure_items(xgm_searcher* s, size_t need, bool is_or) {
+    size_t& have = is_or ? s->items_or_cap : s->items_cap;
+    XgmWorkItem*& h = is_or ? s->h_items_or : s->h_items;
+    XgmWorkItem*& d = is_or ? s->d_items_or : s->d_items;
+    if (need <= have) return XGM_OK;
     size_t cap = std::max<size_t>(need * 2, 4096);
-    if (s->pending) CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
     XgmWorkItem* nh = nullptr;
     CUDA_TRY(cudaMallocHost(&nh, cap * sizeof(XgmWorkItem)));
-    if (s->h_items) { memcpy(nh, s->h_items, s->items_cap * sizeof(XgmWorkItem)); cudaFreeHost(s->h_items); }
-    s->h_items = nh;
-    cudaFree(s->d_items);
-    s->d_items = nullptr;
-    CUDA_TRY(cudaMalloc(&s->d_items, cap * sizeof(XgmWorkItem)));
-    s->items_cap = cap;
+    if (h) cudaFreeHost(h);
+    h = nh;
+    cudaFree(d);
+    d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, cap * sizeof(XgmWorkItem)));
+    have = cap;
     return XGM_OK;
 }
 
@@ -694,7 +703,9 @@ extern "C" xgm_status xgm_searcher_new(const xgm_index* ix, uint32_t max_batch, 
     CUDA_TRY(cudaSetDevice(ix->device));
     std::unique_ptr<xgm_searcher, void (*)(xgm_searcher*)> s(new xgm_searcher(), xgm_searcher_free);
     s->ix = ix; s->max_batch = max_batch; s->max_topk = max_topk;
-    s->match_cap = std::max<uint32_t>(2048, 2 * max_topk);
+    s->match_cap = std::max<uint32_t>(8192, 8 * max_topk);
+    s->keep_cap = std::max<uint32_t>(2048, std::min<uint32_t>(8192, 2 * max_topk + 1024));
+    if (s->keep_cap > s->match_cap) s->keep_cap = s->match_cap;
     CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&s->ev0)); CUDA_TRY(cudaEventCreate(&s->ev1)); CUDA_TRY(cudaEventCreate(&s->ev2));
     size_t nq = max_batch, ns = (size_t)max_batch * max_topk, nm = (size_t)max_batch * s->match_cap;
@@ -702,15 +713,21 @@ extern "C" xgm_status xgm_searcher_new(const xgm_index* ix, uint32_t max_batch, 
     CUDA_TRY(cudaMallocHost(&s->h_out_w, ns * 8)); CUDA_TRY(cudaMallocHost(&s->h_out_d, ns * 4));
     CUDA_TRY(cudaMallocHost(&s->h_out_k, ns * 8)); CUDA_TRY(cudaMallocHost(&s->h_info, nq * sizeof(XgmDevResult)));
     CUDA_TRY(cudaMalloc(&s->d_queries, nq * sizeof(XgmDevQuery)));
-    CUDA_TRY(cudaMalloc(&s->d_ctrl, (nq + 1) * 4));
+    s->ctrl_bytes = 32 + nq * sizeof(XgmQState) + nq * XGM_NBINS * 4;
+    CUDA_TRY(cudaMalloc(&s->d_ctrl, s->ctrl_bytes));
     CUDA_TRY(cudaMalloc(&s->d_match_w, nm * 8)); CUDA_TRY(cudaMalloc(&s->d_match_d, nm * 4)); CUDA_TRY(cudaMalloc(&s->d_match_k, nm * 8));
     CUDA_TRY(cudaMalloc(&s->d_out_w, ns * 8)); CUDA_TRY(cudaMalloc(&s->d_out_d, ns * 4)); CUDA_TRY(cudaMalloc(&s->d_out_k, ns * 8));
     CUDA_TRY(cudaMalloc(&s->d_info, nq * sizeof(XgmDevResult)));
-    xgm_status st = ensure_items(s.get(), 4096);
+    xgm_status st = ensure_items(s.get(), 4096, false);
+    if (st != XGM_OK) return st;
+    st = ensure_items(s.get(), 4096, true);
     if (st != XGM_OK) return st;
     int occ = xgm_and_occupancy_blocks_per_sm();
     if (occ < 1) occ = 1;
     s->grid = ix->sm_count * occ;
+    occ = xgm_or_occupancy_blocks_per_sm();
+    if (occ < 1) occ = 1;
+    s->grid_or = ix->sm_count * occ;
     *out = s.release();
     return XGM_OK;
 }
@@ -795,7 +812,8 @@ static double bm25_maxpart(double termweight, double len_factor, double k1, doub
 }
 
 static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, PlannedQuery& pq, XgmDevQuery& dq,
-                             std::vector<XgmWorkItem>& items, uint32_t blocks_per_item) {
+                             std::vector<XgmWorkItem>& items, std::vector<XgmWorkItem>& items_or,
+                             uint32_t blocks_per_item) {
     const xgm_index* ix = s->ix;
     pq = PlannedQuery();
     memset(&dq, 0, sizeof(dq));
@@ -884,10 +902,16 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
             if (ids[j] != 0xffffffffu) { dq.terms[i].blk_begin = ix->terms[ids[j]].blk_begin; dq.terms[i].nblocks = ix->terms[ids[j]].nblocks; }
         }
     } else {
-        /* OR of leaves: Huffman-shaped tree of binary OrPostLists */
+        /* OR of leaves: Huffman-shaped tree of binary OrPostLists, built from the leaves in query order
+         * (OrContext::postlist, queryinternal.cc:440-489). On the device the leaves are stored in
+         * ascending-termfreq order (position = ownership priority); the program refers to positions. */
         OrTree tr;
         build_or_tree(ltf, n, tr);
-        /* postfix program + folded bounds */
+        TfIdx in[XGM_MAX_TERMS];
+        for (uint32_t j = 0; j < n; ++j) { in[j].tf = ltf[j]; in[j].idx = j; }
+        std::stable_sort(in, in + n, [](const TfIdx& a, const TfIdx& c) { return a.tf < c.tf; });
+        uint32_t posof[XGM_MAX_TERMS];
+        for (uint32_t i = 0; i < n; ++i) { order[i] = in[i].idx; posof[in[i].idx] = i; }
         int stack[4 * XGM_MAX_TERMS], sp = 0, outrev[2 * XGM_MAX_TERMS], nr = 0;
         stack[sp++] = tr.root;
         while (sp) {
@@ -902,7 +926,7 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
         for (int i = nr - 1; i >= 0; --i) {
             int x = outrev[i];
             if (x < (int)n) {
-                dq.prog[dq.prog_len++] = (int8_t)x;
+                dq.prog[dq.prog_len++] = (int8_t)posof[x];
                 sm[p] = maxpart[x]; se[p] = smin[p] = smax[p] = ltf[x]; ++p;
             } else {
                 dq.prog[dq.prog_len++] = -1;
@@ -918,9 +942,10 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
         }
         pq.max_possible = sm[0]; pq.tf_min = smin[0]; pq.tf_max = smax[0]; pq.tf_est = (uint32_t)se[0];
         dq.route = 1;
-        for (uint32_t j = 0; j < n; ++j) {
-            dq.terms[j].termweight = tw[j];
-            if (ids[j] != 0xffffffffu) { dq.terms[j].blk_begin = ix->terms[ids[j]].blk_begin; dq.terms[j].nblocks = ix->terms[ids[j]].nblocks; }
+        for (uint32_t i = 0; i < n; ++i) {
+            uint32_t j = order[i];
+            dq.terms[i].termweight = tw[j];
+            if (ids[j] != 0xffffffffu) { dq.terms[i].blk_begin = ix->terms[ids[j]].blk_begin; dq.terms[i].nblocks = ix->terms[ids[j]].nblocks; }
         }
     }
     /* algorithmic bytes, SURVEY.md §8(d): compressed columns + 16 B per block header of every query
@@ -929,28 +954,55 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
         if (ids[j] != 0xffffffffu) pq.alg_bytes += ix->terms[ids[j]].bytes;
     pq.alg_bytes += 16ull * pq.topk;
 
+    /* pruning buckets: linear in the primary sort key (weight, or the sort value for VAL sorts) */
+    if (q.sort_by == XGM_SORT_REL || q.sort_by == XGM_SORT_REL_VAL)
+        dq.bucket_scale = pq.max_possible > 0 ? (double)XGM_NBINS / pq.max_possible : 0.0;
+    else
+        dq.bucket_scale = (double)XGM_NBINS / ((double)ix->slot_max[q.sort_slot] + 1.0);
+
     if (cal == 0 || pq.topk == 0) { pq.on_device = false; return XGM_OK; } /* bounds only, matcher.cc:437-461 */
     if (dq.route == 0 && any_absent) { pq.on_device = false; return XGM_OK; } /* AND with an absent term: empty */
-    if (dq.route == 1) { pq.status = XGM_E_UNIMPLEMENTED; return XGM_OK; }    /* dense kernel: next milestone */
     pq.on_device = true;
-    uint32_t nb = dq.terms[0].nblocks;
-    for (uint32_t b0 = 0; b0 < nb; b0 += blocks_per_item) {
-        XgmWorkItem wi;
-        wi.query = qi; wi.b0 = b0; wi.b1 = std::min(nb, b0 + blocks_per_item); wi.pad = 0;
-        items.push_back(wi);
+    if (dq.route == 0) {
+        uint32_t nb = dq.terms[0].nblocks;
+        for (uint32_t b0 = 0; b0 < nb; b0 += blocks_per_item) {
+            XgmWorkItem wi;
+            wi.query = qi; wi.b0 = b0; wi.b1 = std::min(nb, b0 + blocks_per_item); wi.pad = 0;
+            items.push_back(wi);
+        }
+    } else {
+        for (uint32_t leaf = 0; leaf < n; ++leaf) {
+            uint32_t nb = dq.terms[leaf].nblocks;
+            for (uint32_t b0 = 0; b0 < nb; b0 += blocks_per_item) {
+                XgmWorkItem wi;
+                wi.query = qi; wi.b0 = b0; wi.b1 = std::min(nb, b0 + blocks_per_item); wi.pad = leaf;
+                items_or.push_back(wi);
+            }
+        }
     }
     return XGM_OK;
 }
 
 static xgm_status launch_batch(xgm_searcher* s) {
     XgmKernelParams& p = s->params;
-    CUDA_TRY(cudaMemsetAsync(s->d_ctrl, 0, ((size_t)s->nq + 1) * 4, s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->d_ctrl, 0, 32 + (size_t)s->max_batch * sizeof(XgmQState), s->stream));
+    CUDA_TRY(cudaMemsetAsync(p.hist, 0, (size_t)s->nq * XGM_NBINS * 4, s->stream));
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
-    if (s->nitems) CUDA_TRY(xgm_launch_and(p, s->grid, s->stream));
+    s->stats.kernel_launches = 0;
+    p.pass = 0;
+    if (s->nitems) { CUDA_TRY(xgm_launch_and(p, s->grid, s->stream)); s->stats.kernel_launches++; }
+    if (s->nitems_or) { CUDA_TRY(xgm_launch_or(p, s->grid_or, s->stream)); s->stats.kernel_launches++; }
     CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
     CUDA_TRY(xgm_launch_topk(p, s->nq, s->stream));
+    s->stats.kernel_launches++;
+    /* second pass: only queries whose candidate buffer overflowed do any work (device-side flag) */
+    XgmKernelParams p2 = p;
+    p2.pass = 1;
+    if (s->nitems) { CUDA_TRY(xgm_launch_and(p2, s->grid, s->stream)); s->stats.kernel_launches++; }
+    if (s->nitems_or) { CUDA_TRY(xgm_launch_or(p2, s->grid_or, s->stream)); s->stats.kernel_launches++; }
+    CUDA_TRY(xgm_launch_topk(p2, s->nq, s->stream));
+    s->stats.kernel_launches++;
     CUDA_TRY(cudaEventRecord(s->ev2, s->stream));
-    s->stats.kernel_launches = (s->nitems ? 1u : 0u) + 1u;
     return XGM_OK;
 }
 
@@ -963,7 +1015,7 @@ extern "C" xgm_status xgm_search_submit(xgm_searcher* s, const xgm_query* querie
     s->nq = nq;
     /* work granularity: enough items to balance ~grid*8 warps, at most 32 driver blocks per item */
     uint64_t total_drv_blocks = 0;
-    std::vector<XgmWorkItem> items;
+    std::vector<XgmWorkItem> items, items_or;
     items.reserve(4096);
     /* first pass with a provisional granularity needs the driver block counts; plan twice is wasteful,
      * so use a fixed small granularity scaled by batch size */
@@ -971,29 +1023,54 @@ extern "C" xgm_status xgm_search_submit(xgm_searcher* s, const xgm_query* querie
     s->any_sort = false;
     uint64_t alg = 0, postings = 0;
     for (uint32_t i = 0; i < nq; ++i) {
-        xgm_status st = plan_query(s, queries[i], i, s->plan[i], s->h_queries[i], items, bpi);
+        xgm_status st = plan_query(s, queries[i], i, s->plan[i], s->h_queries[i], items, items_or, bpi);
         if (st != XGM_OK) return st;
-        if (s->plan[i].sort_by) s->any_sort = true;
+        if (s->plan[i].sort_by || s->h_queries[i].route == 1) s->any_sort = true; /* keys/aux needed on the host */
         alg += s->plan[i].alg_bytes;
         total_drv_blocks += s->h_queries[i].terms[0].nblocks;
     }
     (void)total_drv_blocks; (void)postings;
-    xgm_status st = ensure_items(s, items.size());
+    xgm_status st = ensure_items(s, items.size(), false);
     if (st != XGM_OK) return st;
-    if (!items.empty()) memcpy(s->h_items, items.data(), items.size() * sizeof(XgmWorkItem));
+    st = ensure_items(s, items_or.size(), true);
+    if (st != XGM_OK) return st;
+    /* Interleave the work lists across queries (all queries' first item, then all second items, ...):
+     * the warps in flight at any moment then belong to many queries, so each query's pruning threshold
+     * has risen before most of its matches are produced, and long queries do not form a tail. */
+    auto interleave = [nq](const std::vector<XgmWorkItem>& in, XgmWorkItem* out) {
+        if (in.empty()) return;
+        std::vector<uint32_t> seq(in.size()), per_q(nq, 0);
+        uint32_t maxseq = 0;
+        for (size_t i = 0; i < in.size(); ++i) { seq[i] = per_q[in[i].query]++; maxseq = std::max(maxseq, seq[i]); }
+        std::vector<size_t> start((size_t)maxseq + 2, 0);
+        for (size_t i = 0; i < in.size(); ++i) start[seq[i] + 1]++;
+        for (size_t k = 1; k < start.size(); ++k) start[k] += start[k - 1];
+        for (size_t i = 0; i < in.size(); ++i) out[start[seq[i]]++] = in[i];
+    };
+    interleave(items, s->h_items);
+    interleave(items_or, s->h_items_or);
     s->nitems = (uint32_t)items.size();
+    s->nitems_or = (uint32_t)items_or.size();
     s->stats = xgm_batch_stats{};
     s->stats.algorithmic_bytes = alg;
-    s->stats.work_items = s->nitems;
+    s->stats.work_items = s->nitems + s->nitems_or;
+    s->stats.h2d_bytes = (uint64_t)nq * sizeof(XgmDevQuery) + (uint64_t)(s->nitems + s->nitems_or) * sizeof(XgmWorkItem);
+    s->stats.d2h_bytes = (uint64_t)nq * sizeof(XgmDevResult) + (uint64_t)nq * s->max_topk * (8 + 4 + (s->any_sort ? 8 : 0));
     XgmKernelParams& p = s->params;
     fill_index_params(s->ix, p);
     p.queries = s->d_queries; p.items = s->d_items; p.nitems = s->nitems; p.nq = nq;
-    p.work_counter = s->d_ctrl; p.match_count = s->d_ctrl + 1; p.match_cap = s->match_cap;
+    p.items_or = s->d_items_or; p.nitems_or = s->nitems_or;
+    p.work_counter = reinterpret_cast<uint32_t*>(s->d_ctrl);
+    p.qstate = reinterpret_cast<XgmQState*>(s->d_ctrl + 32);
+    p.hist = reinterpret_cast<uint32_t*>(s->d_ctrl + 32 + (size_t)s->max_batch * sizeof(XgmQState));
+    p.match_cap = s->match_cap; p.keep_cap = s->keep_cap;
     p.match_w = s->d_match_w; p.match_d = s->d_match_d; p.match_k = s->d_match_k;
     p.out_stride = s->max_topk; p.out_w = s->d_out_w; p.out_d = s->d_out_d; p.out_k = s->d_out_k; p.out_info = s->d_info;
     CUDA_TRY(cudaMemcpyAsync(s->d_queries, s->h_queries, (size_t)nq * sizeof(XgmDevQuery), cudaMemcpyHostToDevice, s->stream));
     if (s->nitems)
         CUDA_TRY(cudaMemcpyAsync(s->d_items, s->h_items, (size_t)s->nitems * sizeof(XgmWorkItem), cudaMemcpyHostToDevice, s->stream));
+    if (s->nitems_or)
+        CUDA_TRY(cudaMemcpyAsync(s->d_items_or, s->h_items_or, (size_t)s->nitems_or * sizeof(XgmWorkItem), cudaMemcpyHostToDevice, s->stream));
     st = launch_batch(s);
     if (st != XGM_OK) return st;
     size_t ns = (size_t)nq * s->max_topk;
@@ -1005,7 +1082,8 @@ extern "C" xgm_status xgm_search_submit(xgm_searcher* s, const xgm_query* querie
     return XGM_OK;
 }
 
-static void finish_info(const PlannedQuery& pq, const XgmDevResult* dr, const double* w, xgm_mset_info* o) {
+static void finish_info(const PlannedQuery& pq, const XgmDevResult* dr, const double* w, const uint64_t* keys, bool is_or,
+                        xgm_mset_info* o) {
     memset(o, 0, sizeof(*o));
     o->first = pq.first;
     o->status = pq.status;
@@ -1022,7 +1100,8 @@ static void finish_info(const PlannedQuery& pq, const XgmDevResult* dr, const do
         if (size != pq.topk) lb = est = ub = size;
         else if (known < pq.check_at_least) lb = est = ub = known;
         else { lb = std::max(lb, known); est = std::max(est, known); }
-        if (dr->flags & 1u) o->status = XGM_E_UNIMPLEMENTED; /* overflow: needs the dense kernel */
+        if (dr->flags & 5u) o->status = XGM_E_UNIMPLEMENTED; /* candidates lost: pathological tie mass */
+        if (dr->flags & 2u) o->flags |= XGM_MSET_BOUNDS_APPROX;
     } else if (pq.check_at_least != 0) {
         lb = est = ub = 0; /* empty result set: !full() branch */
     }
@@ -1033,7 +1112,10 @@ static void finish_info(const PlannedQuery& pq, const XgmDevResult* dr, const do
     o->n = size > pq.first ? size - pq.first : 0;
     if (size != 0 && max_w != 0.0) {
         /* ProtoMSet::finalise_percentages protomset.h:466-471: AND → every subquery matched */
-        double percent_scale = (double)dr->max_subqs / (double)pq.nterms;
+        /* AND: every leaf matches; OR sorted by relevance: leaves matching the best document */
+        uint32_t subqs = dr->max_subqs;
+        if (is_or && pq.sort_by == XGM_SORT_REL && keys) subqs = (uint32_t)keys[0];
+        double percent_scale = (double)subqs / (double)pq.nterms;
         percent_scale /= max_w;
         o->percent_scale_factor = percent_scale * 100.0;
     }
@@ -1052,7 +1134,8 @@ extern "C" xgm_status xgm_search_wait(xgm_searcher* s, uint32_t* docids, double*
     for (uint32_t i = 0; i < s->nq; ++i) {
         const PlannedQuery& pq = s->plan[i];
         const size_t off = (size_t)i * s->max_topk;
-        finish_info(pq, &s->h_info[i], s->h_out_w + off, &info[i]);
+        finish_info(pq, &s->h_info[i], s->h_out_w + off, s->any_sort ? s->h_out_k + off : nullptr,
+                    s->h_queries[i].route == 1, &info[i]);
         if (pq.status == XGM_OK && pq.on_device) s->stats.algorithmic_bytes += 4ull * s->h_info[i].exact;
         uint32_t n = info[i].n;
         if (n > stride) return fail(XGM_E_INVALID, "stride %u too small for %u results", stride, n);
@@ -1155,6 +1238,7 @@ extern "C" xgm_status xgm_merge_msets(const uint32_t* const* docids, const doubl
         o.max_possible = std::max(o.max_possible, m.max_possible);
         if (m.max_attained > o.max_attained) { o.max_attained = m.max_attained; o.percent_scale_factor = m.percent_scale_factor; }
         if (m.status != XGM_OK) o.status = m.status;
+        o.flags |= m.flags;
         for (uint32_t i = 0; i < m.n; ++i)
             all.push_back(MItem{weights[p][i], docids[p][i], (sort_keys && sort_keys[p]) ? sort_keys[p][i] : 0ull});
     }
@@ -1173,7 +1257,15 @@ extern "C" xgm_status xgm_merge_msets(const uint32_t* const* docids, const doubl
     return XGM_OK;
 }
 
-extern "C" xgm_status xgm_merge_topk_device(const void*, const void*, const void*, uint32_t, uint32_t, uint32_t, uint32_t,
-                                            void*, void*, void*, void*) {
-    return fail(XGM_E_UNIMPLEMENTED, "device merge not built yet");
+extern "C" xgm_status xgm_merge_topk_device(const void* gw, const void* gd, const void* ginfo, uint32_t nparts, uint32_t nq,
+                                            uint32_t stride, uint32_t k, void* out_w, void* out_d, void* out_n,
+                                            void* cuda_stream) {
+    if (!gw || !gd || !ginfo || !out_w || !out_d || !out_n || nparts == 0 || nq == 0 || k == 0 || k > stride)
+        return fail(XGM_E_INVALID, "bad arguments");
+    if ((size_t)nparts * k * 12 > 200 * 1024) return fail(XGM_E_INVALID, "nparts*k too large for the merge kernel");
+    CUDA_TRY(xgm_launch_merge(static_cast<const double*>(gw), static_cast<const uint32_t*>(gd),
+                              static_cast<const XgmDevResult*>(ginfo), nparts, nq, stride, k, static_cast<double*>(out_w),
+                              static_cast<uint32_t*>(out_d), static_cast<uint32_t*>(out_n),
+                              static_cast<cudaStream_t>(cuda_stream)));
+    return XGM_OK;
 }

@@ -4,6 +4,7 @@
  *                     GlassPostList::next/skip_to glass_postlist.cc:768-991, MultiAndPostList::
  *                     find_next_match multiandpostlist.cc:179-206, get_weight :149-159,
  *                     BM25Weight::get_sumpart bm25weight.cc:170-181, doclen fetch postlisttree.h:184-195)
+ *   xgm_or_kernel     owner-leaf union with the reference's tree-order sum (OrPostList, orpostlist.cc:93-204)
  *   xgm_topk_kernel   ProtoMSet top-k + match counting (protomset.h:295-400,484-683; msetcmp.cc:54-98)
  *   xgm_decode_kernel round-trip decode of one term (index self-check)
  *
@@ -133,30 +134,41 @@ __device__ __forceinline__ double bm25_sumpart(double termweight, const XgmDevQu
 
 /* ------------------------------------------------------------------ skip-table search */
 
-/* Largest block index i in [cur, n) with hdr[i].first <= target, given the sentinel at hdr[n].
- * Returns cur when hdr[cur].first > target (caller checks). Warp-galloping: first look at the next 32
- * headers (sequential access pattern of a leapfrog), then a 32-ary search over the rest. */
+/* Largest block index i in [cur, n) with hdr[i].first <= target (sentinel at hdr[n]); returns cur
+ * when hdr[cur].first > target (caller checks bh.first).  Also returns that block's header and the
+ * first docid of the following block.  Warp-galloping: one coalesced look at the next 32 headers
+ * (the common case of a leapfrog moving forward), then a 32-ary search over the rest of the list. */
 __device__ __forceinline__ uint32_t warp_seek(const XgmBlockHdr* __restrict__ hdr, uint32_t cur, uint32_t n,
-                                              uint32_t target, uint32_t lane) {
-    uint32_t i = cur + lane;
-    uint32_t f = (i <= n) ? __ldg(&hdr[i].first) : XGM_SENTINEL;
-    uint32_t cnt = __popc(__ballot_sync(FULL, f <= target));
-    if (cnt < 32) return cnt ? cur + cnt - 1 : cur;
-    uint32_t lo = cur + 31, hi = n; /* hdr[lo].first <= target < hdr[hi].first (sentinel) */
+                                              uint32_t target, uint32_t lane, XgmBlockHdr& bh, uint32_t& next_first) {
+    const uint32_t i = cur + lane;
+    uint4 hv = make_uint4(XGM_SENTINEL, 0u, 0u, 0u);
+    if (i <= n) hv = __ldg(reinterpret_cast<const uint4*>(hdr + i));
+    const uint32_t cnt = __popc(__ballot_sync(FULL, hv.x <= target));
+    if (cnt < 32) {
+        const uint32_t src = cnt ? cnt - 1 : 0;
+        bh.first = __shfl_sync(FULL, hv.x, src);
+        bh.doc_off = __shfl_sync(FULL, hv.y, src);
+        bh.tf_off = __shfl_sync(FULL, hv.z, src);
+        bh.meta = __shfl_sync(FULL, hv.w, src);
+        next_first = __shfl_sync(FULL, hv.x, src + 1);
+        return cur + src;
+    }
+    uint32_t lo = cur + 31, hi = n; /* hdr[lo].first <= target < hdr[hi].first */
     while (hi - lo > 1) {
-        uint32_t span = hi - lo;
-        uint32_t step = (span + 31) / 32;
-        uint32_t p = lo + (lane + 1) * step;
-        if (p > hi) p = hi;
-        uint32_t fp = __ldg(&hdr[p].first);
-        uint32_t c = __popc(__ballot_sync(FULL, fp <= target));
-        uint32_t nlo = lo + c * step;
-        uint32_t nhi = lo + (c + 1) * step;
-        if (nlo > hi) nlo = hi; /* cannot happen: hdr[hi] > target */
+        const uint32_t step = (hi - lo + 31) / 32;
+        uint32_t pidx = lo + (lane + 1) * step;
+        if (pidx > hi) pidx = hi;
+        const uint32_t fp = __ldg(&hdr[pidx].first);
+        const uint32_t c = __popc(__ballot_sync(FULL, fp <= target));
+        uint32_t nlo = lo + c * step, nhi = lo + (c + 1) * step;
+        if (nlo > hi) nlo = hi;
         if (nhi > hi) nhi = hi;
         lo = nlo;
         hi = nhi;
     }
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(hdr + lo));
+    bh.first = h.x; bh.doc_off = h.y; bh.tf_off = h.z; bh.meta = h.w;
+    next_first = __ldg(&hdr[lo + 1].first);
     return lo;
 }
 
@@ -181,7 +193,6 @@ __device__ __forceinline__ bool doc_passes_filter(const XgmKernelParams& p, cons
 }
 
 __device__ __forceinline__ uint64_t doc_sort_key(const XgmKernelParams& p, const XgmDevQuery* q, uint32_t did) {
-    if (q->sort_by == 0) return 0;
     const XgmDevSlot& s = p.slots[q->sort_slot];
     if (!s.voff) return 0;
     uint32_t a = __ldg(&s.voff[did]), b = __ldg(&s.voff[did + 1]);
@@ -189,34 +200,226 @@ __device__ __forceinline__ uint64_t doc_sort_key(const XgmKernelParams& p, const
     return __ldg(&s.vals[q->sort_use_max ? b - 1 : a]);
 }
 
-/* ------------------------------------------------------------------ sparse AND kernel */
+/* ------------------------------------------------------------------ match emission + top-k pruning */
 
-#define AND_WARPS 8
+/* Monotone bucket of a match under the query's primary sort key: a higher bucket always ranks
+ * before a lower one, so once at least topk matches sit in buckets >= b*, anything below b* can never
+ * enter the MSet (the parallel analogue of ProtoMSet's rising min_weight, protomset.h:377-398). */
+__device__ __forceinline__ uint32_t match_bucket(const XgmDevQuery* q, double w, uint64_t key) {
+    if (q->sort_by == 0 || q->sort_by == 3) {
+        double x = w * q->bucket_scale;
+        uint32_t b = x >= (double)(XGM_NBINS - 1) ? XGM_NBINS - 1 : (uint32_t)x;
+        return b;
+    }
+    double x = (double)key * q->bucket_scale;
+    uint32_t b = x >= (double)(XGM_NBINS - 1) ? XGM_NBINS - 1 : (uint32_t)x;
+    return q->sort_reverse ? b : (XGM_NBINS - 1 - b);
+}
+
+/* Warp-wide: lanes hold up to 4 matches each (mask `alive`), weight acc[k], docid c[k], aux[k]
+ * (number of matching leaves). Counts every match, keeps those not yet prunable. */
+__device__ __noinline__ void emit_matches_impl(const XgmKernelParams& p, const XgmDevQuery* q, uint32_t qi, uint32_t lane,
+                                              uint32_t alive, double a0, double a1, double a2, double a3, uint32_t c0,
+                                              uint32_t c1, uint32_t c2, uint32_t c3, uint32_t x0, uint32_t x1,
+                                              uint32_t x2, uint32_t x3) {
+    const double acc[4] = {a0, a1, a2, a3};
+    const uint32_t c[4] = {c0, c1, c2, c3};
+    const uint32_t aux[4] = {x0, x1, x2, x3};
+    XgmQState* st = &p.qstate[qi];
+    uint32_t* hist = p.hist + (size_t)qi * XGM_NBINS;
+    /* exact match count and best weight over ALL matches (ProtoMSet::update_max_weight, protomset.h:174-183) */
+    double lmax = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if ((alive >> k & 1u) && acc[k] > lmax) lmax = acc[k];
+    unsigned long long mb = (unsigned long long)__double_as_longlong(lmax);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(FULL, mb, o);
+        mb = t > mb ? t : mb;
+    }
+    const uint32_t nall = __reduce_add_sync(FULL, __popc(alive));
+    const uint32_t bstar = *reinterpret_cast<volatile uint32_t*>(&st->bstar);
+    uint64_t key[4] = {0, 0, 0, 0};
+    uint32_t bkt[4] = {0, 0, 0, 0};
+    uint32_t keep = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (alive >> k & 1u) {
+            if (q->sort_by != 0) key[k] = doc_sort_key(p, q, c[k]);
+            bkt[k] = match_bucket(q, acc[k], key[k]);
+            if (bkt[k] >= bstar) keep |= 1u << k;
+        }
+    }
+    const uint32_t n = __popc(keep);
+    uint32_t incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL, incl, o);
+        if ((int)lane >= o) incl += t;
+    }
+    const uint32_t nkeep = __shfl_sync(FULL, incl, 31);
+    uint32_t base = 0;
+    if (lane == 0) {
+        if (p.pass == 0) {
+            atomicAdd(&st->total, nall);
+            atomicMax(&st->maxw, mb);
+        }
+        if (nkeep) base = atomicAdd(&st->stored, nkeep);
+    }
+    base = __shfl_sync(FULL, base, 0);
+    if (nkeep == 0) return;
+    uint32_t idx = base + (incl - n);
+    const size_t qoff = (size_t)qi * p.match_cap;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (keep >> k & 1u) {
+            if (p.pass == 0) atomicAdd(&hist[bkt[k]], 1u);
+            if (idx < p.match_cap) {
+                p.match_w[qoff + idx] = acc[k];
+                p.match_d[qoff + idx] = c[k];
+                p.match_k[qoff + idx] = q->sort_by != 0 ? key[k] : (uint64_t)aux[k];
+            }
+            ++idx;
+        }
+    }
+    /* raise b* whenever the stored count crosses a multiple of 256 (and topk matches exist) */
+    const uint32_t after = base + nkeep;
+    if (p.pass == 0 && (base >> 8) != (after >> 8) && after >= q->topk) {
+        __threadfence();
+        const volatile uint32_t* vh = hist;
+        uint32_t mine = 0;
+        for (int i = 0; i < XGM_NBINS / 32; ++i) mine += vh[lane * (XGM_NBINS / 32) + i];
+        /* suffix sum over lanes: sfx = sum of lanes >= lane */
+        uint32_t sfx = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_down_sync(FULL, sfx, o);
+            if ((int)lane + o < 32) sfx += t;
+        }
+        const uint32_t ok = __ballot_sync(FULL, sfx >= q->topk);
+        if (ok) {
+            const uint32_t L = 31 - __clz(ok);
+            if (lane == L) {
+                uint32_t cum = sfx - mine;
+                uint32_t nb = L * (XGM_NBINS / 32);
+                for (int i = XGM_NBINS / 32 - 1; i >= 0; --i) {
+                    cum += vh[L * (XGM_NBINS / 32) + i];
+                    if (cum >= q->topk) { nb = L * (XGM_NBINS / 32) + i; break; }
+                }
+                atomicMax(&st->bstar, nb);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void emit_matches(const XgmKernelParams& p, const XgmDevQuery* q, uint32_t qi, uint32_t lane,
+                                             uint32_t alive, const double acc[4], const uint32_t c[4],
+                                             const uint32_t aux[4]) {
+    if (!__any_sync(FULL, alive != 0)) return;
+    emit_matches_impl(p, q, qi, lane, alive, acc[0], acc[1], acc[2], acc[3], c[0], c[1], c[2], c[3], aux[0], aux[1],
+                      aux[2], aux[3]);
+}
+
+/* ------------------------------------------------------------------ shared per-warp scratch */
+
+#define MATCH_WARPS 8
 
 struct __align__(16) WarpScratch {
-    uint32_t stage[STAGE_WORDS]; /* packed words of the block being decoded */
-    uint32_t dbuf[XGM_BLOCK];    /* decoded docids of the probed block */
-    uint64_t bar;
+    uint32_t stage[STAGE_WORDS];      /* packed words of the block being probed */
+    uint32_t dstage[2][STAGE_WORDS];  /* double-buffered packed docids of the driver list */
+    uint32_t dbuf[XGM_BLOCK];         /* decoded docids of the probed block */
+    uint64_t bar;                     /* completion barrier of `stage` */
+    uint64_t dbar[2];                 /* completion barriers of `dstage` */
     uint64_t pad;
 };
 
-__global__ void __launch_bounds__(AND_WARPS * 32) xgm_and_kernel(XgmKernelParams p) {
-    __shared__ WarpScratch scratch[AND_WARPS];
+__device__ __forceinline__ void issue_stage(const uint4* col, uint32_t off16, uint32_t bits, uint32_t* st, uint64_t* bar,
+                                            uint32_t lane) {
+    if (bits != 0 && lane == 0) {
+        mbar_expect_tx(bar, bits * 16u);
+        bulk_g2s(st, col + off16, bits * 16u, bar);
+    }
+}
+
+/* Resolve the unresolved candidates of one warp against list `lh` (skip table) — the reference's
+ * skip_to/check sequence of MultiAndPostList::find_next_match, multiandpostlist.cc:179-206, done for
+ * 128 candidates at once.  HIT(k, pos, bh) is invoked for candidates found at position pos of block bh,
+ * MISS(k) for candidates proven absent. */
+template <class Hit, class Miss>
+__device__ __forceinline__ uint32_t probe_list(const XgmKernelParams& p, const XgmBlockHdr* __restrict__ lh,
+                                               uint32_t lnblk, uint32_t cur, WarpScratch& ws, uint32_t& phase,
+                                               uint32_t lane, const uint32_t c[4], uint32_t unresolved, Hit hit,
+                                               Miss miss) {
+    for (;;) {
+        const uint32_t m = (unresolved & 1u) ? c[0] : (unresolved & 2u) ? c[1] : (unresolved & 4u) ? c[2]
+                           : (unresolved & 8u) ? c[3] : XGM_SENTINEL;
+        const uint32_t tmin = __reduce_min_sync(FULL, m);
+        if (tmin == XGM_SENTINEL) break;
+        if (cur >= lnblk) { /* list exhausted */
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (unresolved >> k & 1u) miss(k);
+            unresolved = 0;
+            break;
+        }
+        XgmBlockHdr bh;
+        uint32_t next_first;
+        cur = warp_seek(lh, cur, lnblk, tmin, lane, bh, next_first);
+        if (tmin < bh.first) { /* candidates below this block fall into a gap of the list */
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if ((unresolved >> k & 1u) && c[k] < bh.first) {
+                    unresolved &= ~(1u << k);
+                    miss(k);
+                }
+            continue;
+        }
+        uint32_t bd[4];
+        stage_block(p.docs, bh.doc_off, XGM_HDR_DOC_BITS(bh.meta), ws.stage, &ws.bar, phase, lane);
+        decode_docids(ws.stage, XGM_HDR_DOC_BITS(bh.meta), bh.first, lane, bd);
+        const uint32_t bcount = XGM_HDR_COUNT(bh.meta);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ws.dbuf[4 * lane + k] = (4 * lane + k < bcount) ? bd[k] : XGM_SENTINEL;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if ((unresolved >> k & 1u) && c[k] < next_first) {
+                const uint32_t cd = c[k];
+                uint32_t pos = 0;
+#pragma unroll
+                for (uint32_t s = 64; s >= 1; s >>= 1)
+                    if (ws.dbuf[pos + s - 1] < cd) pos += s;
+                unresolved &= ~(1u << k);
+                if (ws.dbuf[pos] == cd) hit(k, pos, bh);
+                else miss(k);
+            }
+        }
+        __syncwarp();
+    }
+    return cur;
+}
+
+/* ------------------------------------------------------------------ sparse AND kernel */
+
+__global__ void __launch_bounds__(MATCH_WARPS * 32, 3) xgm_and_kernel(XgmKernelParams p) {
+    __shared__ WarpScratch scratch[MATCH_WARPS];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     WarpScratch& ws = scratch[warp];
-    if (lane == 0) mbar_init(&ws.bar, 1);
+    if (lane == 0) { mbar_init(&ws.bar, 1); mbar_init(&ws.dbar[0], 1); mbar_init(&ws.dbar[1], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    uint32_t phase = 0;
-
+    uint32_t phase = 0, dphase0 = 0, dphase1 = 0;
     const XgmBlockHdr* __restrict__ hdr = p.hdr;
 
+    if (p.pass != 0 && *reinterpret_cast<volatile uint32_t*>(p.work_counter + 4) == 0) return; /* nothing to re-run */
     for (;;) {
         uint32_t item = 0;
-        if (lane == 0) item = atomicAdd(p.work_counter, 1u);
+        if (lane == 0) item = atomicAdd(p.work_counter + 2 * p.pass, 1u);
         item = __shfl_sync(FULL, item, 0);
         if (item >= p.nitems) break;
         const XgmWorkItem wi = p.items[item];
+        if (p.pass != 0 && p.qstate[wi.query].rerun == 0) continue;
         const XgmDevQuery* q = &p.queries[wi.query];
         const uint32_t nterms = q->nterms;
         /* lane j keeps list j's skip-table cursor */
@@ -228,12 +431,26 @@ __global__ void __launch_bounds__(AND_WARPS * 32) xgm_and_kernel(XgmKernelParams
         const uint32_t drv_begin = __shfl_sync(FULL, my_begin, 0);
         const double tw0 = q->terms[0].termweight;
 
+        /* software pipeline over the driver list: block db+1 is in flight while db is intersected */
+        XgmBlockHdr dh = hdr[drv_begin + wi.b0];
+        __syncwarp();
+        issue_stage(p.docs, dh.doc_off, XGM_HDR_DOC_BITS(dh.meta), ws.dstage[0], &ws.dbar[0], lane);
+        uint32_t buf = 0;
         for (uint32_t db = wi.b0; db < wi.b1; ++db) {
-            const XgmBlockHdr dh = hdr[drv_begin + db];
+            XgmBlockHdr nh = dh;
+            if (db + 1 < wi.b1) {
+                nh = hdr[drv_begin + db + 1];
+                __syncwarp();
+                issue_stage(p.docs, nh.doc_off, XGM_HDR_DOC_BITS(nh.meta), ws.dstage[buf ^ 1], &ws.dbar[buf ^ 1], lane);
+            }
+            const uint32_t dbits = XGM_HDR_DOC_BITS(dh.meta);
+            if (dbits) {
+                if (buf == 0) { mbar_wait(&ws.dbar[0], dphase0); dphase0 ^= 1u; }
+                else { mbar_wait(&ws.dbar[1], dphase1); dphase1 ^= 1u; }
+            }
             const uint32_t dcount = XGM_HDR_COUNT(dh.meta);
             uint32_t c[4];
-            stage_block(p.docs, dh.doc_off, XGM_HDR_DOC_BITS(dh.meta), ws.stage, &ws.bar, phase, lane);
-            decode_docids(ws.stage, XGM_HDR_DOC_BITS(dh.meta), dh.first, lane, c);
+            decode_docids(ws.dstage[buf], dbits, dh.first, lane, c);
             uint32_t alive = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -254,6 +471,7 @@ __global__ void __launch_bounds__(AND_WARPS * 32) xgm_and_kernel(XgmKernelParams
                         acc[k] = bm25_sumpart(tw0, q, tf, dl[k]);
                     }
                 }
+                __syncwarp();
             }
 
             for (uint32_t j = 1; j < nterms; ++j) {
@@ -261,67 +479,21 @@ __global__ void __launch_bounds__(AND_WARPS * 32) xgm_and_kernel(XgmKernelParams
                 const uint32_t lbegin = __shfl_sync(FULL, my_begin, j);
                 const uint32_t lnblk = __shfl_sync(FULL, my_nblk, j);
                 uint32_t cur = __shfl_sync(FULL, my_cur, j);
-                const XgmBlockHdr* lh = hdr + lbegin;
                 const double twj = q->terms[j].termweight;
-                uint32_t unresolved = alive;
-                for (;;) {
-                    /* smallest unresolved candidate across the warp (candidates ascend with k, lane) */
-                    uint32_t m = (unresolved & 1u) ? c[0] : (unresolved & 2u) ? c[1] : (unresolved & 4u) ? c[2]
-                                 : (unresolved & 8u) ? c[3] : XGM_SENTINEL;
-                    const uint32_t tmin = __reduce_min_sync(FULL, m);
-                    if (tmin == XGM_SENTINEL) break;
-                    if (cur >= lnblk) { /* list exhausted: nothing else can match */
-                        alive &= ~unresolved;
-                        unresolved = 0;
-                        break;
-                    }
-                    cur = warp_seek(lh, cur, lnblk, tmin, lane);
-                    const XgmBlockHdr bh = lh[cur];
-                    const uint32_t next_first = __ldg(&lh[cur + 1].first);
-                    if (tmin < bh.first) {
-                        /* candidates below this block's first docid fall in a gap: dead */
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if ((unresolved >> k & 1u) && c[k] < bh.first) {
-                                unresolved &= ~(1u << k);
-                                alive &= ~(1u << k);
-                            }
-                        continue;
-                    }
-                    /* decode the block and publish its docids for the per-candidate searches */
-                    uint32_t bd[4];
-                    stage_block(p.docs, bh.doc_off, XGM_HDR_DOC_BITS(bh.meta), ws.stage, &ws.bar, phase, lane);
-                    decode_docids(ws.stage, XGM_HDR_DOC_BITS(bh.meta), bh.first, lane, bd);
-                    const uint32_t bcount = XGM_HDR_COUNT(bh.meta);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) ws.dbuf[4 * lane + k] = (4 * lane + k < bcount) ? bd[k] : XGM_SENTINEL;
-                    __syncwarp();
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if ((unresolved >> k & 1u) && c[k] < next_first) {
-                            const uint32_t cd = c[k];
-                            uint32_t pos = 0;
-#pragma unroll
-                            for (uint32_t s = 64; s >= 1; s >>= 1)
-                                if (ws.dbuf[pos + s - 1] < cd) pos += s;
-                            unresolved &= ~(1u << k);
-                            if (ws.dbuf[pos] == cd) {
-                                if (j == 1) {
-                                    /* first confirmation: fetch doclen and the driver's own wdf lazily */
-                                    dl[k] = __ldg(&p.doclen[cd]);
-                                    uint32_t tf0 = unpack_gl(p.tfs, dh.tf_off, 4 * lane + k, XGM_HDR_TF_BITS(dh.meta));
-                                    acc[k] = bm25_sumpart(tw0, q, tf0, dl[k]);
-                                }
-                                uint32_t tfj = unpack_gl(p.tfs, bh.tf_off, pos, XGM_HDR_TF_BITS(bh.meta));
-                                /* MultiAndPostList::get_weight: result += plist[i]->get_weight(), in order */
-                                acc[k] = __dadd_rn(acc[k], bm25_sumpart(twj, q, tfj, dl[k]));
-                            } else {
-                                alive &= ~(1u << k);
-                            }
+                cur = probe_list(
+                    p, hdr + lbegin, lnblk, cur, ws, phase, lane, c, alive,
+                    [&](int k, uint32_t pos, const XgmBlockHdr& bh) {
+                        if (j == 1) {
+                            /* first confirmation: fetch doclen and the driver's own wdf lazily */
+                            dl[k] = __ldg(&p.doclen[c[k]]);
+                            uint32_t tf0 = unpack_gl(p.tfs, dh.tf_off, 4 * lane + k, XGM_HDR_TF_BITS(dh.meta));
+                            acc[k] = bm25_sumpart(tw0, q, tf0, dl[k]);
                         }
-                    }
-                    __syncwarp();
-                }
+                        uint32_t tfj = unpack_gl(p.tfs, bh.tf_off, pos, XGM_HDR_TF_BITS(bh.meta));
+                        /* MultiAndPostList::get_weight: result += plist[i]->get_weight(), in plist order */
+                        acc[k] = __dadd_rn(acc[k], bm25_sumpart(twj, q, tfj, dl[k]));
+                    },
+                    [&](int k) { alive &= ~(1u << k); });
                 if (lane == j) my_cur = cur;
             }
 
@@ -331,33 +503,135 @@ __global__ void __launch_bounds__(AND_WARPS * 32) xgm_and_kernel(XgmKernelParams
                 for (int k = 0; k < 4; ++k)
                     if ((alive >> k & 1u) && !doc_passes_filter(p, q, c[k])) alive &= ~(1u << k);
             }
+            const uint32_t aux[4] = {nterms, nterms, nterms, nterms};
+            emit_matches(p, q, wi.query, lane, alive, acc, c, aux);
+            dh = nh;
+            buf ^= 1u;
+        }
+    }
+}
 
-            /* emit matches: warp-aggregated reservation in the query's match buffer */
-            if (__any_sync(FULL, alive != 0)) {
-                uint32_t n = __popc(alive);
-                uint32_t incl = n;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    uint32_t t = __shfl_up_sync(FULL, incl, o);
-                    if ((int)lane >= o) incl += t;
-                }
-                uint32_t total = __shfl_sync(FULL, incl, 31);
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&p.match_count[wi.query], total);
-                base = __shfl_sync(FULL, base, 0) + (incl - n);
-                const size_t qoff = (size_t)wi.query * p.match_cap;
+/* ------------------------------------------------------------------ OR kernel */
+
+#define OR_WARPS 4
+
+struct __align__(16) OrScratch {
+    WarpScratch w;
+    uint32_t tft[XGM_DEV_MAX_TERMS][XGM_BLOCK]; /* wdf of candidate x in leaf i (valid where present) */
+};
+
+/* OR of leaves (OrPostList tree, orpostlist.cc:93-204).  Each document of the union is produced exactly
+ * once, by the rarest leaf that contains it ("owner"): work items walk one leaf's blocks, probe the
+ * other leaves for the same 128 docids, drop documents owned by a rarer leaf, and evaluate the
+ * reference's tree-shaped sum (l, r or l+r per node, queryinternal.cc:440-489) for the rest. */
+__global__ void __launch_bounds__(OR_WARPS * 32) xgm_or_kernel(XgmKernelParams p) {
+    __shared__ OrScratch scratch[OR_WARPS];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    OrScratch& os = scratch[warp];
+    WarpScratch& ws = os.w;
+    if (lane == 0) { mbar_init(&ws.bar, 1); mbar_init(&ws.dbar[0], 1); mbar_init(&ws.dbar[1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    uint32_t phase = 0;
+    const XgmBlockHdr* __restrict__ hdr = p.hdr;
+
+    if (p.pass != 0 && *reinterpret_cast<volatile uint32_t*>(p.work_counter + 4) == 0) return;
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(p.work_counter + 1 + 2 * p.pass, 1u);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= p.nitems_or) break;
+        const XgmWorkItem wi = p.items_or[item];
+        if (p.pass != 0 && p.qstate[wi.query].rerun == 0) continue;
+        const XgmDevQuery* q = &p.queries[wi.query];
+        const uint32_t nterms = q->nterms;
+        const uint32_t drv = wi.pad; /* driver leaf (position in ascending-termfreq order) */
+        uint32_t my_begin = 0, my_nblk = 0, my_cur = 0;
+        if (lane < nterms) {
+            my_begin = q->terms[lane].blk_begin;
+            my_nblk = q->terms[lane].nblocks;
+        }
+        const uint32_t drv_begin = __shfl_sync(FULL, my_begin, drv);
+
+        for (uint32_t db = wi.b0; db < wi.b1; ++db) {
+            const XgmBlockHdr dh = hdr[drv_begin + db];
+            const uint32_t dcount = XGM_HDR_COUNT(dh.meta);
+            uint32_t c[4];
+            stage_block(p.docs, dh.doc_off, XGM_HDR_DOC_BITS(dh.meta), ws.stage, &ws.bar, phase, lane);
+            decode_docids(ws.stage, XGM_HDR_DOC_BITS(dh.meta), dh.first, lane, c);
+            stage_block(p.tfs, dh.tf_off, XGM_HDR_TF_BITS(dh.meta), ws.stage, &ws.bar, phase, lane);
+            uint32_t owned = 0;
+            uint32_t present[4];
+            {
+                const uint32_t tb = XGM_HDR_TF_BITS(dh.meta);
+                const uint32_t tmask = bitmask(tb);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (alive >> k & 1u) {
-                        if (base < p.match_cap) {
-                            p.match_w[qoff + base] = acc[k];
-                            p.match_d[qoff + base] = c[k];
-                            if (q->sort_by) p.match_k[qoff + base] = doc_sort_key(p, q, c[k]);
-                        }
-                        ++base;
+                    present[k] = 1u << drv;
+                    if (4 * lane + k < dcount) {
+                        owned |= 1u << k;
+                        os.tft[drv][4 * lane + k] = tb ? unpack_sm(ws.stage, 4 * lane + k, tb, tmask) : 0u;
                     }
                 }
             }
+            __syncwarp();
+            for (uint32_t j = 0; j < nterms; ++j) {
+                if (j == drv) continue;
+                if (!__any_sync(FULL, owned != 0)) break;
+                const uint32_t lbegin = __shfl_sync(FULL, my_begin, j);
+                const uint32_t lnblk = __shfl_sync(FULL, my_nblk, j);
+                uint32_t cur = __shfl_sync(FULL, my_cur, j);
+                cur = probe_list(
+                    p, hdr + lbegin, lnblk, cur, ws, phase, lane, c, owned,
+                    [&](int k, uint32_t pos, const XgmBlockHdr& bh) {
+                        if (j < drv) {
+                            owned &= ~(1u << k); /* a rarer leaf owns this document */
+                        } else {
+                            os.tft[j][4 * lane + k] = unpack_gl(p.tfs, bh.tf_off, pos, XGM_HDR_TF_BITS(bh.meta));
+                            present[k] |= 1u << j;
+                        }
+                    },
+                    [&](int) {});
+                if (lane == j) my_cur = cur;
+            }
+            if (q->filter) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if ((owned >> k & 1u) && !doc_passes_filter(p, q, c[k])) owned &= ~(1u << k);
+            }
+            /* weight = fold of the tree over the leaves present (OrPostList::get_weight, orpostlist.cc:93-103) */
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            uint32_t aux[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (owned >> k & 1u) {
+                    const uint32_t dlen = __ldg(&p.doclen[c[k]]);
+                    double stk[XGM_DEV_MAX_TERMS];
+                    uint32_t has = 0; /* bit s: stack slot s holds a value */
+                    int sp = 0;
+                    for (uint32_t i = 0; i < q->prog_len; ++i) {
+                        const int op = q->prog[i];
+                        if (op >= 0) {
+                            if (present[k] >> op & 1u) {
+                                stk[sp] = bm25_sumpart(q->terms[op].termweight, q, os.tft[op][4 * lane + k], dlen);
+                                has |= 1u << sp;
+                            } else {
+                                has &= ~(1u << sp);
+                            }
+                            ++sp;
+                        } else {
+                            --sp;
+                            const bool hl = has >> (sp - 1) & 1u, hr = has >> sp & 1u;
+                            if (hl && hr) stk[sp - 1] = __dadd_rn(stk[sp - 1], stk[sp]);
+                            else if (hr) { stk[sp - 1] = stk[sp]; has |= 1u << (sp - 1); }
+                        }
+                    }
+                    acc[k] = stk[0];
+                    aux[k] = __popc(present[k]);
+                }
+            }
+            emit_matches(p, q, wi.query, lane, owned, acc, c, aux);
+            __syncwarp();
         }
     }
 }
@@ -382,37 +656,70 @@ __device__ __forceinline__ bool ranks_before(uint32_t sort_by, uint32_t reverse,
     return da < db;
 }
 
-#define TOPK_THREADS 128
+#define TOPK_THREADS 256
 
-/* One CTA per query. Rank-sort: every match counts how many matches rank before it; ranks < topk
- * are written to their final position. The same pass counts what ProtoMSet::add would have counted
- * in known_matching_docs while walking the matches in docid order (protomset.h:340-400 together
- * with the `weight < min_weight → continue` of matcher.cc:496-498): a match is counted iff it is
- * among the first max(check_at_least, topk+1) in docid order or fewer than topk earlier matches have
- * a strictly greater weight. */
+/* One CTA per query. Survivors (bucket >= final b*) are compacted into shared memory and rank-sorted:
+ * every match counts how many matches rank before it; ranks < topk are written to their final
+ * position.  When nothing was pruned the same pass reproduces ProtoMSet's known_matching_docs: walking
+ * the matches in docid order, a match is counted iff it is among the first max(check_at_least, topk+1)
+ * or fewer than topk earlier matches have a strictly greater weight (protomset.h:340-400 with the
+ * `weight < min_weight → continue` of matcher.cc:496-498). */
 __global__ void __launch_bounds__(TOPK_THREADS) xgm_topk_kernel(XgmKernelParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t qi = blockIdx.x;
     const XgmDevQuery* q = &p.queries[qi];
-    if (q->route != 0) return;
-    const uint32_t total = p.match_count[qi];
-    const uint32_t n = total < p.match_cap ? total : p.match_cap;
+    const XgmQState st = p.qstate[qi];
+    if (p.pass != 0 && st.rerun == 0) return;
+    const uint32_t stored = st.stored < p.match_cap ? st.stored : p.match_cap;
     double* sw = reinterpret_cast<double*>(smem_raw);
-    uint64_t* sk = reinterpret_cast<uint64_t*>(sw + p.match_cap);
-    uint32_t* sd = reinterpret_cast<uint32_t*>(sk + p.match_cap);
-    __shared__ uint32_t s_known;
-    __shared__ unsigned long long s_maxw;
+    uint64_t* sk = reinterpret_cast<uint64_t*>(sw + p.keep_cap);
+    uint32_t* sd = reinterpret_cast<uint32_t*>(sk + p.keep_cap);
+    __shared__ uint32_t s_known, s_n;
     const size_t qoff = (size_t)qi * p.match_cap;
     const uint32_t sort_by = q->sort_by, reverse = q->sort_reverse;
-    for (uint32_t i = threadIdx.x; i < n; i += TOPK_THREADS) {
-        sw[i] = p.match_w[qoff + i];
-        sd[i] = p.match_d[qoff + i];
-        sk[i] = sort_by ? p.match_k[qoff + i] : 0ull;
-    }
-    if (threadIdx.x == 0) { s_known = 0; s_maxw = 0ull; }
+    const bool complete = (st.total == st.stored) && (st.stored <= p.keep_cap); /* every match is here */
+    if (threadIdx.x == 0) { s_known = 0; s_n = 0; }
     __syncthreads();
+    for (uint32_t i = threadIdx.x; i < stored; i += TOPK_THREADS) {
+        const double w = p.match_w[qoff + i];
+        const uint64_t k = p.match_k[qoff + i];
+        if (complete || match_bucket(q, w, k) >= st.bstar) {
+            const uint32_t pos = atomicAdd(&s_n, 1u);
+            if (pos < p.keep_cap) {
+                sw[pos] = w;
+                sd[pos] = p.match_d[qoff + i];
+                sk[pos] = k;
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t kept = s_n;
+    const uint32_t n = kept < p.keep_cap ? kept : p.keep_cap;
     const uint32_t topk = q->topk;
-    double local_max = 0.0;
+    if (p.pass == 0 && (st.stored > p.match_cap || kept > p.keep_cap)) {
+        /* Candidates were lost (many warps emitted before b* could rise).  The histogram is complete
+         * for every bin >= the b* in force, so the exact b* (highest bin with >= topk matches at or
+         * above it) is known now: schedule a second pass that stores only those matches. */
+        if (threadIdx.x == 0) {
+            const uint32_t* hist = p.hist + (size_t)qi * XGM_NBINS;
+            uint32_t cum = 0, b = XGM_NBINS;
+            while (b > 0 && cum < topk) { --b; cum += hist[b]; }
+            XgmDevResult r;
+            r.n = 0; r.exact = st.total; r.known = 0; r.max_w = __longlong_as_double((long long)st.maxw);
+            r.max_subqs = q->nterms; r.pad = 0;
+            if (cum >= topk && cum <= p.keep_cap && cum <= p.match_cap && b >= st.bstar) {
+                p.qstate[qi].bstar = b;
+                p.qstate[qi].stored = 0;
+                p.qstate[qi].rerun = 1;
+                atomicAdd(p.work_counter + 4, 1u);
+                r.flags = 4u; /* pending second pass */
+            } else {
+                r.flags = 1u; /* a single bucket holds more ties than the buffers: give up on this query */
+            }
+            p.out_info[qi] = r;
+        }
+        return;
+    }
     const uint32_t free_count = q->check_at_least > topk + 1 ? q->check_at_least : topk + 1;
     uint32_t known = 0;
     const size_t ooff = (size_t)qi * p.out_stride;
@@ -432,41 +739,100 @@ __global__ void __launch_bounds__(TOPK_THREADS) xgm_topk_kernel(XgmKernelParams 
         if (rank < topk) {
             p.out_w[ooff + rank] = wi;
             p.out_d[ooff + rank] = di;
-            if (p.out_k) p.out_k[ooff + rank] = ki;
+            p.out_k[ooff + rank] = ki;
         }
         if (sort_by == 1 || sort_by == 2 || before < free_count || greater_before < topk) ++known;
-        local_max = wi > local_max ? wi : local_max;
     }
     atomicAdd(&s_known, known);
-    /* weights are >= 0, so the IEEE bit pattern orders like the value */
-    atomicMax(&s_maxw, (unsigned long long)__double_as_longlong(local_max));
     __syncthreads();
     if (threadIdx.x == 0) {
         XgmDevResult r;
         r.n = n < topk ? n : topk;
-        r.exact = total;
-        r.known = s_known;
-        r.flags = total > p.match_cap ? 1u : 0u;
-        r.max_w = __longlong_as_double((long long)s_maxw);
-        r.max_subqs = q->nterms; /* AND: every leaf matches (count_matching_subqs) */
+        r.exact = st.total;
+        r.flags = 0;
+        if (st.stored > p.match_cap || kept > p.keep_cap) r.flags |= 1u; /* lost candidates: result unusable */
+        if (complete) {
+            r.known = s_known;
+        } else {
+            /* pruned run: ProtoMSet's count depends on docid-order history we did not keep; report the
+             * guaranteed part and flag the bounds as approximate */
+            r.known = st.total < free_count ? st.total : free_count;
+            r.flags |= 2u;
+        }
+        r.max_w = __longlong_as_double((long long)st.maxw);
+        r.max_subqs = q->nterms;
         r.pad = 0;
         p.out_info[qi] = r;
     }
 }
 
+/* ------------------------------------------------------------------ multi-shard merge */
+
+/* Matcher::merge_mset (matcher.cc:653-782) on the device, after an all-gather of the per-GPU top-k
+ * records: one CTA per query rank-sorts the nparts*k candidates under (weight desc, docid asc) with
+ * docids mapped through unshard() (backends/multi.h:66-70). */
+__global__ void __launch_bounds__(256) xgm_merge_kernel(const double* __restrict__ gw, const uint32_t* __restrict__ gd,
+                                                        const XgmDevResult* __restrict__ ginfo, uint32_t nparts,
+                                                        uint32_t nq, uint32_t stride, uint32_t k, double* out_w,
+                                                        uint32_t* out_d, uint32_t* out_n) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sw = reinterpret_cast<double*>(smem_raw);
+    uint32_t* sd = reinterpret_cast<uint32_t*>(sw + (size_t)nparts * k);
+    __shared__ uint32_t s_n;
+    const uint32_t qi = blockIdx.x;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (uint32_t part = 0; part < nparts; ++part) {
+        const uint32_t n = min(ginfo[(size_t)part * nq + qi].n, k);
+        const size_t off = ((size_t)part * nq + qi) * stride;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t pos = atomicAdd(&s_n, 1u);
+            sw[pos] = gw[off + i];
+            sd[pos] = (gd[off + i] - 1u) * nparts + part + 1u;
+        }
+    }
+    __syncthreads();
+    const uint32_t n = s_n;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const double wi = sw[i];
+        const uint32_t di = sd[i];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < n; ++j) rank += (sw[j] > wi || (sw[j] == wi && sd[j] < di)) ? 1u : 0u;
+        if (rank < k) {
+            out_w[(size_t)qi * k + rank] = wi;
+            out_d[(size_t)qi * k + rank] = di;
+        }
+    }
+    if (threadIdx.x == 0) out_n[qi] = n < k ? n : k;
+}
+
+cudaError_t xgm_launch_merge(const double* gw, const uint32_t* gd, const XgmDevResult* ginfo, uint32_t nparts, uint32_t nq,
+                             uint32_t stride, uint32_t k, double* out_w, uint32_t* out_d, uint32_t* out_n,
+                             cudaStream_t s) {
+    size_t smem = (size_t)nparts * k * 12;
+    static size_t attr_bytes = 48 * 1024;
+    if (smem > attr_bytes) {
+        cudaError_t e = cudaFuncSetAttribute(xgm_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_bytes = smem;
+    }
+    xgm_merge_kernel<<<nq, 256, smem, s>>>(gw, gd, ginfo, nparts, nq, stride, k, out_w, out_d, out_n);
+    return cudaGetLastError();
+}
+
 /* ------------------------------------------------------------------ decode (round-trip check) */
 
-__global__ void __launch_bounds__(AND_WARPS * 32) xgm_decode_kernel(XgmKernelParams p, uint32_t blk_begin,
-                                                                    uint32_t nblocks, uint32_t* out_d,
-                                                                    uint32_t* out_w) {
-    __shared__ WarpScratch scratch[AND_WARPS];
+__global__ void __launch_bounds__(MATCH_WARPS * 32) xgm_decode_kernel(XgmKernelParams p, uint32_t blk_begin,
+                                                                      uint32_t nblocks, uint32_t* out_d,
+                                                                      uint32_t* out_w) {
+    __shared__ WarpScratch scratch[MATCH_WARPS];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     WarpScratch& ws = scratch[warp];
     if (lane == 0) mbar_init(&ws.bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     uint32_t phase = 0;
-    for (uint32_t b = blockIdx.x * AND_WARPS + warp; b < nblocks; b += gridDim.x * AND_WARPS) {
+    for (uint32_t b = blockIdx.x * MATCH_WARPS + warp; b < nblocks; b += gridDim.x * MATCH_WARPS) {
         const XgmBlockHdr h = p.hdr[blk_begin + b];
         const uint32_t count = XGM_HDR_COUNT(h.meta);
         uint32_t d[4];
@@ -489,19 +855,24 @@ __global__ void __launch_bounds__(AND_WARPS * 32) xgm_decode_kernel(XgmKernelPar
 /* ------------------------------------------------------------------ launchers */
 
 cudaError_t xgm_launch_and(const XgmKernelParams& p, int grid, cudaStream_t s) {
-    xgm_and_kernel<<<grid, AND_WARPS * 32, 0, s>>>(p);
+    xgm_and_kernel<<<grid, MATCH_WARPS * 32, 0, s>>>(p);
     return cudaGetLastError();
 }
 
-size_t xgm_topk_smem_bytes(uint32_t match_cap) { return (size_t)match_cap * (8 + 8 + 4); }
+cudaError_t xgm_launch_or(const XgmKernelParams& p, int grid, cudaStream_t s) {
+    xgm_or_kernel<<<grid, OR_WARPS * 32, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+size_t xgm_topk_smem_bytes(uint32_t keep_cap) { return (size_t)keep_cap * (8 + 8 + 4); }
 
 cudaError_t xgm_launch_topk(const XgmKernelParams& p, uint32_t nq, cudaStream_t s) {
-    size_t smem = xgm_topk_smem_bytes(p.match_cap);
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
+    size_t smem = xgm_topk_smem_bytes(p.keep_cap);
+    static size_t attr_bytes = 48 * 1024; /* raised monotonically; benign race: same value per device */
+    if (smem > attr_bytes) {
         cudaError_t e = cudaFuncSetAttribute(xgm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_bytes = smem;
     }
     xgm_topk_kernel<<<nq, TOPK_THREADS, smem, s>>>(p);
     return cudaGetLastError();
@@ -509,15 +880,21 @@ cudaError_t xgm_launch_topk(const XgmKernelParams& p, uint32_t nq, cudaStream_t 
 
 cudaError_t xgm_launch_decode(const XgmKernelParams& p, uint32_t blk_begin, uint32_t nblocks, uint32_t* out_d,
                               uint32_t* out_w, cudaStream_t s) {
-    int grid = (int)((nblocks + AND_WARPS - 1) / AND_WARPS);
+    int grid = (int)((nblocks + MATCH_WARPS - 1) / MATCH_WARPS);
     if (grid > 148 * 8) grid = 148 * 8;
     if (grid < 1) grid = 1;
-    xgm_decode_kernel<<<grid, AND_WARPS * 32, 0, s>>>(p, blk_begin, nblocks, out_d, out_w);
+    xgm_decode_kernel<<<grid, MATCH_WARPS * 32, 0, s>>>(p, blk_begin, nblocks, out_d, out_w);
     return cudaGetLastError();
 }
 
 int xgm_and_occupancy_blocks_per_sm() {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, xgm_and_kernel, AND_WARPS * 32, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, xgm_and_kernel, MATCH_WARPS * 32, 0);
+    return n;
+}
+
+int xgm_or_occupancy_blocks_per_sm() {
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, xgm_or_kernel, OR_WARPS * 32, 0);
     return n;
 }

@@ -73,12 +73,14 @@ class MSetInfo(C.Structure):
                 ("matches_estimated", C.c_uint32), ("matches_upper_bound", C.c_uint32),
                 ("uncollapsed_lower_bound", C.c_uint32), ("uncollapsed_estimated", C.c_uint32),
                 ("uncollapsed_upper_bound", C.c_uint32), ("exact_matches", C.c_uint32), ("status", C.c_uint32),
+                ("flags", C.c_uint32), ("reserved", C.c_uint32),
                 ("max_possible", C.c_double), ("max_attained", C.c_double), ("percent_scale_factor", C.c_double)]
 
 
 class BatchStats(C.Structure):
     _fields_ = [("algorithmic_bytes", C.c_uint64), ("postings", C.c_uint64), ("work_items", C.c_uint32),
-                ("kernel_launches", C.c_uint32), ("match_kernel_ms", C.c_float), ("topk_kernel_ms", C.c_float)]
+                ("kernel_launches", C.c_uint32), ("match_kernel_ms", C.c_float), ("topk_kernel_ms", C.c_float),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
 _lib = None
@@ -221,6 +223,7 @@ class MSet:
     percent_scale_factor: float
     exact_matches: int
     status: int
+    flags: int = 0
 
     def size(self) -> int:
         return len(self.docids)
@@ -392,7 +395,7 @@ class Searcher:
             a, b = i * self.max_topk, i * self.max_topk + m.n
             out.append(MSet(d[a:b].copy(), w[a:b].copy(), k[a:b].copy(), m.first, m.matches_lower_bound,
                             m.matches_estimated, m.matches_upper_bound, m.max_possible, m.max_attained,
-                            m.percent_scale_factor, m.exact_matches, m.status))
+                            m.percent_scale_factor, m.exact_matches, m.status, m.flags))
         return out
 
     def search(self, queries: Union[QueryBatch, Sequence[Query]]) -> List[MSet]:
@@ -448,7 +451,7 @@ def merge_msets(parts: Sequence[MSet], first: int, maxitems: int, sort_by: int =
         m.matches_lower_bound = m.uncollapsed_lower_bound = p.matches_lower_bound
         m.matches_estimated = m.uncollapsed_estimated = p.matches_estimated_raw
         m.matches_upper_bound = m.uncollapsed_upper_bound = p.matches_upper_bound
-        m.exact_matches, m.status = p.exact_matches, p.status
+        m.exact_matches, m.status, m.flags = p.exact_matches, p.status, p.flags
         m.max_possible, m.max_attained = p.max_possible, p.max_attained
         m.percent_scale_factor = p.percent_scale_factor
     od = np.zeros(maxitems, np.uint32)
@@ -459,4 +462,4 @@ def merge_msets(parts: Sequence[MSet], first: int, maxitems: int, sort_by: int =
                                  _ptr(od), _ptr(ow), _ptr(ok), C.byref(oi)))
     return MSet(od[:oi.n], ow[:oi.n], ok[:oi.n], first, oi.matches_lower_bound, oi.matches_estimated,
                 oi.matches_upper_bound, oi.max_possible, oi.max_attained, oi.percent_scale_factor,
-                oi.exact_matches, oi.status)
+                oi.exact_matches, oi.status, oi.flags)
