@@ -91,6 +91,7 @@ def main():
         sh.append(dict(op=op, terms=rng.sample(range(300), k), first=rng.choice([0, 0, 5]), maxitems=rng.choice([10, 100]),
                        check_at_least=rng.choice([0, 20000])))
     run_set("shard4_20k", 20000, 5000, sh, nshards=4, twophase=True)
+    run_set("shard2_20k", 20000, 5000, sh[:30], nshards=2, twophase=True)
     # value range filter + sort by value then relevance (stock OP_VALUE_RANGE / set_sort_by_value_then_relevance)
     vq = []
     for i in range(60):

@@ -1,0 +1,127 @@
+"""GPU tests against the golden fixtures the COMPILED REFERENCE produced (tests/golden/*.json)."""
+import struct
+
+import numpy as np
+import pytest
+
+from tests.golden_util import load, sortable_key_to_int
+from xapiand_b200 import xgm
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(x):
+    return struct.pack("<d", float(x))
+
+
+def x_query(q, stats=None, first=None, maxitems=None):
+    kw = dict(first=q["first"] if first is None else first, maxitems=q["maxitems"] if maxitems is None else maxitems,
+              check_at_least=q["check_at_least"], stats=stats)
+    if "vr" in q:
+        kw.update(filter=xgm.FILTER_VALUE_RANGE, filter_slot=0, range_lo=q["vr"][1], range_hi=q["vr"][2])
+    if "sort" in q:
+        kw.update(sort_by=xgm.SORT_VAL_REL, sort_slot=q["sort"][0], sort_reverse=bool(q["sort"][1]))
+    return xgm.Query(xgm.OP_AND if q["op"] == "AND" else xgm.OP_OR, q["terms"], **kw)
+
+
+def check(m, q, ctx, counts=True):
+    assert m.status == 0, ctx
+    assert list(m.docids) == q["docids"], f"{ctx}: docids"
+    assert all(bits(a) == bits(b) for a, b in zip(m.weights, q["weights"])), f"{ctx}: weights not bit-equal"
+    assert bits(m.max_attained) == bits(q["max_attained"]), f"{ctx}: max_attained"
+    if counts:
+        assert bits(m.max_possible) == bits(q["max_possible"]), f"{ctx}: max_possible"
+        assert m.matches_upper_bound == q["ub"], f"{ctx}: upper bound"
+        if not (m.flags & 1):
+            assert (m.matches_lower_bound, m.get_matches_estimated()) == (q["lb"], q["est"]), f"{ctx}: bounds"
+
+
+@pytest.mark.parametrize("tag", ["c1_1k_100", "mid_20k"])
+def test_cuda_matches_reference_single_db(tag):
+    fx = load(tag)
+    ix = xgm.Index.synthetic(fx["ndocs"], fx["vocab"], fx["seed"])
+    s = xgm.Searcher(ix, max_batch=len(fx["queries"]), max_topk=256)
+    res = s.search([x_query(q) for q in fx["queries"]])
+    for i, (q, m) in enumerate(zip(fx["queries"], res)):
+        check(m, q, f"{tag}[{i}] {q['op']} {q['terms']}")
+
+
+@pytest.mark.parametrize("tag", ["shard4_20k", "shard2_20k"])
+def test_cuda_matches_reference_twophase_shards(tag):
+    """Xapiand's DocMatcher scheme: per-shard search with global statistics, unshard, merge."""
+    fx = load(tag)
+    n = fx["nshards"]
+    shards = [xgm.Index.synthetic(fx["ndocs"], fx["vocab"], fx["seed"], nshards=n, shard=s) for s in range(n)]
+    infos = [ix.info() for ix in shards]
+    coll = sum(i.doccount for i in infos)
+    tlen = sum(i.total_length for i in infos)
+    searchers = [xgm.Searcher(ix, max_batch=len(fx["queries"]), max_topk=256) for ix in shards]
+    per_shard = []
+    gstats = []
+    for q in fx["queries"]:
+        gtf = [sum(ix.term_stats(f"T{t:06d}").termfreq for ix in shards) for t in q["terms"]]
+        gstats.append((coll, tlen, gtf))
+    for si, s in enumerate(searchers):
+        res = s.search([x_query(q, stats=gstats[i], first=0, maxitems=q["first"] + q["maxitems"])
+                        for i, q in enumerate(fx["queries"])])
+        for m in res:
+            m.docids = xgm.unshard(m.docids, si, n)
+        per_shard.append(res)
+    for i, q in enumerate(fx["queries"]):
+        merged = xgm.merge_msets([per_shard[si][i] for si in range(n)], q["first"], q["maxitems"])
+        check(merged, q, f"{tag}[{i}] {q}")
+
+
+def test_cuda_matches_reference_value_filter_and_sort():
+    fx = load("values_5k")
+    ix = xgm.Index.synthetic(fx["ndocs"], fx["vocab"], fx["seed"], values=True)
+    s = xgm.Searcher(ix, max_batch=len(fx["queries"]), max_topk=128)
+    res = s.search([x_query(q) for q in fx["queries"]])
+    for i, (q, m) in enumerate(zip(fx["queries"], res)):
+        ctx = f"values[{i}] {q}"
+        check(m, q, ctx, counts=False)
+        if "sort" in q:
+            keys = [sortable_key_to_int(k) for k in q.get("sort_keys", [])]
+            mine = list(m.sort_keys)
+            for a in range(len(keys) - 1):
+                assert (keys[a] < keys[a + 1]) == (mine[a] < mine[a + 1]), ctx
+                assert (keys[a] == keys[a + 1]) == (mine[a] == mine[a + 1]), ctx
+
+
+def test_multi_range_filter_and_sort_variants_against_oracle():
+    """Xapiand's MultipleValueRange semantics (src/multivalue/range.cc:351-368) and sort by the
+    smallest / largest value of a multi-valued slot (keymaker.cc:67-92), against the oracle."""
+    import random
+    from oracle import oracle as O
+    nd, V = 20000, 3000
+    ix = xgm.Index.synthetic(nd, V, values=True)
+    orc = O.Index.synthetic(nd, V, values=True)
+    rng = random.Random(11)
+    xq, oq = [], []
+    for i in range(120):
+        terms = rng.sample(range(80), 2)
+        lo = rng.randrange(0, 950000)
+        hi = lo + rng.choice([5000, 50000, 300000])
+        use_max = bool(i % 2)
+        rev = bool((i // 2) % 2)
+        sort = i % 3 != 0
+        cal = rng.choice([0, nd])
+        xq.append(xgm.Query(xgm.OP_AND, terms, maxitems=rng.choice([10, 100]), check_at_least=cal,
+                            filter=xgm.FILTER_MULTI_RANGE, filter_slot=0, range_lo=lo, range_hi=hi,
+                            sort_by=xgm.SORT_VAL_REL if sort else xgm.SORT_REL, sort_slot=0, sort_reverse=rev,
+                            sort_use_max=use_max))
+        oq.append(O.Query(op=O.OP_AND, terms=terms, maxitems=xq[-1].maxitems, check_at_least=cal,
+                          filter=O.FILTER_MULTI_RANGE, range_lo=lo, range_hi=hi,
+                          sort_by=O.SORT_VAL_REL if sort else O.SORT_REL, sort_slot=2 if use_max else 0, sort_reverse=rev))
+    s = xgm.Searcher(ix, max_batch=len(xq), max_topk=128)
+    res = s.search(xq)
+    for i, (m, q) in enumerate(zip(res, oq)):
+        ref = orc.match(q)
+        ctx = f"multi[{i}] {xq[i]}"
+        assert m.status == 0, ctx
+        assert list(m.docids) == list(ref.docids), ctx
+        assert np.asarray(m.weights).tobytes() == np.asarray(ref.weights).tobytes(), ctx
+        assert m.exact_matches == ref.exact, ctx
+        assert bits(m.max_attained) == bits(ref.max_attained), ctx
+        if q.sort_by != O.SORT_REL:
+            assert list(m.sort_keys) == list(ref.sortvals), ctx

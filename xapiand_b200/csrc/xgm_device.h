@@ -29,6 +29,8 @@ struct XgmKernelParams {
     const uint4* docs;
     const uint4* tfs;
     const uint32_t* doclen;
+    const uint32_t* bitmaps;
+    const uint32_t* ranks;
     uint32_t lastdocid;
     XgmDevSlot slots[XGM_MAX_SLOTS];
     /* batch */
@@ -37,7 +39,7 @@ struct XgmKernelParams {
     const XgmWorkItem* items_or;  /* OR kernel work list */
     uint32_t nitems, nitems_or;
     uint32_t nq;
-    uint32_t* work_counter;       /* [0] AND items, [1] OR items, [2],[3] same for the second pass, [4] #queries to re-run */
+    uint32_t* work_counter;       /* [0] AND items, [1] OR items, [2],[3] same for the second pass, [4] #queries to re-run, [5] overflow-pool entries reserved */
     uint32_t pass;                /* 0 = first pass, 1 = re-run of overflowed queries with their exact b* */
     XgmQState* qstate;            /* [nq] */
     uint32_t* hist;               /* [nq][XGM_NBINS] */
@@ -47,6 +49,11 @@ struct XgmKernelParams {
     double* match_w;
     uint32_t* match_d;
     uint64_t* match_k;
+    /* overflow pool: second-pass candidates of queries whose first-pass buffer overflowed */
+    uint32_t pool_total;
+    double* pool_w;
+    uint32_t* pool_d;
+    uint64_t* pool_k;
     /* results */
     uint32_t out_stride;
     double* out_w;
@@ -56,6 +63,8 @@ struct XgmKernelParams {
 };
 
 cudaError_t xgm_launch_and(const XgmKernelParams& p, int grid, cudaStream_t s);
+cudaError_t xgm_launch_and2(const XgmKernelParams& p, int grid, cudaStream_t s);
+int xgm_and2_occupancy_blocks_per_sm();
 cudaError_t xgm_launch_or(const XgmKernelParams& p, int grid, cudaStream_t s);
 int xgm_or_occupancy_blocks_per_sm();
 cudaError_t xgm_launch_topk(const XgmKernelParams& p, uint32_t nq, cudaStream_t s);

@@ -11,6 +11,11 @@
  *           is 16*doc_bits bytes, so every block starts 16-byte aligned (cp.async.bulk granularity).
  *   tfs[]   per block 128 x tf_bits bits of wdf, same packing, separate column: the intersection
  *           only touches it for documents that survive.
+ *   bitmaps[]/ranks[]  optional per-term membership bitmap (bit d = docid d has the term) plus a rank
+ *           directory (postings before every 256-docid group), kept for terms frequent enough that the
+ *           bitmap costs at most XGM_BITMAP_K bits per posting.  HBM is plentiful (180 GB) and the
+ *           leapfrog of an AND is at heart a membership test: probing a bitmap replaces decoding the
+ *           longer lists entirely; the rank directory gives the posting's index, hence its wdf.
  *   doclen[] dense u32 per docid (the reference keeps a second vbyte stream under key "\0\xe0",
  *           glass_postlist.cc:194-205,994-1021).
  */
@@ -34,10 +39,14 @@ struct XgmBlockHdr {
 #define XGM_HDR_TF_BITS(m) (((m) >> 8) & 0xffu)
 #define XGM_HDR_COUNT(m) ((((m) >> 16) & 0xffu) + 1u)
 
+#define XGM_NO_BITMAP 0xFFFFFFFFFFFFFFFFull
+
 struct XgmDevTerm {
     uint32_t blk_begin;   /* index of the term's first header in hdr[] */
     uint32_t nblocks;     /* real blocks (the sentinel sits at blk_begin + nblocks) */
     double termweight;    /* BM25Weight::init result, bm25weight.cc:46-130 (computed on the host) */
+    uint64_t bm_off;      /* membership bitmap of the term (u32 words into bitmaps[]), XGM_NO_BITMAP if none */
+    uint64_t rk_off;      /* its rank directory (u32 entries into ranks[]): postings before each 256-docid group */
 };
 
 struct XgmDevQuery {
@@ -67,7 +76,8 @@ struct XgmQState {
     uint32_t bstar;            /* pruning bucket: matches below it cannot reach the top-k any more */
     uint32_t rerun;            /* set by the top-k kernel: buffer overflowed, second pass with exact b* */
     unsigned long long maxw;   /* bit pattern of the best weight over all matches */
-    unsigned long long pad2;
+    uint32_t pool_off;         /* second pass: this query's slice of the overflow pool (entries) */
+    uint32_t pool_cap;         /* exact number of matches at or above b* (from the completed histogram) */
 };
 
 #endif

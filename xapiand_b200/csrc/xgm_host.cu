@@ -83,6 +83,7 @@ struct TermInfo {
     uint32_t wdf_ub = 0;
     uint64_t collfreq = 0;
     uint64_t bytes = 0; /* docs + tfs + headers */
+    uint64_t bm_off = XGM_NO_BITMAP, rk_off = 0; /* membership bitmap + rank directory (u32 units) */
 };
 
 struct HostSlot {
@@ -97,7 +98,8 @@ struct xgm_index {
     uint64_t total_length = 0;
     uint32_t doclen_lb = 0, doclen_ub = 0;
     uint64_t npostings = 0, nblocks = 0;
-    uint64_t bytes_docs = 0, bytes_tfs = 0, bytes_hdr = 0, bytes_doclen = 0;
+    uint64_t bytes_docs = 0, bytes_tfs = 0, bytes_hdr = 0, bytes_doclen = 0, bytes_bitmaps = 0;
+    uint32_t nbitmaps = 0;
     uint64_t revision = 1;
     std::vector<TermInfo> terms;
     std::unordered_map<std::string, uint32_t> dict;
@@ -107,6 +109,8 @@ struct xgm_index {
     uint4* d_docs = nullptr;
     uint4* d_tfs = nullptr;
     uint32_t* d_doclen = nullptr;
+    uint32_t* d_bitmaps = nullptr;
+    uint32_t* d_ranks = nullptr;
     uint32_t* d_voff[XGM_MAX_SLOTS] = {};
     uint64_t* d_vals[XGM_MAX_SLOTS] = {};
     uint64_t slot_max[XGM_MAX_SLOTS] = {};
@@ -118,7 +122,21 @@ struct Chunk {
     std::vector<XgmBlockHdr> hdr;
     std::vector<uint32_t> docs; /* packed words, 4*bits words per block */
     std::vector<uint32_t> tfs;
+    std::vector<uint32_t> bitmaps; /* membership bitmaps of the frequent terms of this chunk */
+    std::vector<uint32_t> ranks;
 };
+
+/* Terms with termfreq >= lastdocid / K get a membership bitmap (K bits per posting at most).
+ * XGM_BITMAP_K=0 disables the bitmaps (everything goes through the block-decoding intersection). */
+static uint32_t bitmap_k() {
+    const char* e = getenv("XGM_BITMAP_K");
+    return e ? (uint32_t)strtoul(e, nullptr, 10) : 256u;
+}
+static uint32_t bitmap_min_df(uint32_t lastdocid) {
+    uint32_t k = bitmap_k();
+    if (k == 0) return 0xffffffffu;
+    return std::max<uint32_t>(64u, lastdocid / k);
+}
 
 static inline void pack_bits(std::vector<uint32_t>& out, const uint32_t* v, uint32_t n, uint32_t bits) {
     /* 128 slots x bits, little-endian bit order; slots >= n are zero */
@@ -136,7 +154,24 @@ static inline void pack_bits(std::vector<uint32_t>& out, const uint32_t* v, uint
 }
 
 /* Append one term's postings to a chunk in the block format of xgm_format.h. */
-static void compress_term(Chunk& c, const uint32_t* docids, const uint32_t* wdfs, uint32_t n, TermInfo& ti) {
+static void compress_term(Chunk& c, const uint32_t* docids, const uint32_t* wdfs, uint32_t n, TermInfo& ti,
+                          uint32_t lastdocid = 0, uint32_t min_bitmap_df = 0xffffffffu) {
+    if (n >= min_bitmap_df && n > 0 && lastdocid >= docids[n - 1]) {
+        const size_t ngroups = (size_t)lastdocid / 256 + 1;
+        ti.bm_off = c.bitmaps.size(); /* chunk-relative, fixed up later */
+        ti.rk_off = c.ranks.size();
+        c.bitmaps.resize(c.bitmaps.size() + ngroups * 8, 0u);
+        c.ranks.resize(c.ranks.size() + ngroups + 1, 0u);
+        uint32_t* bm = c.bitmaps.data() + ti.bm_off;
+        uint32_t* rk = c.ranks.data() + ti.rk_off;
+        for (uint32_t i = 0; i < n; ++i) bm[docids[i] >> 5] |= 1u << (docids[i] & 31);
+        uint32_t acc = 0;
+        for (size_t g = 0; g < ngroups; ++g) {
+            rk[g] = acc;
+            for (int w = 0; w < 8; ++w) acc += (uint32_t)__builtin_popcount(bm[g * 8 + w]);
+        }
+        rk[ngroups] = acc;
+    }
     ti.blk_begin = (uint32_t)c.hdr.size(); /* chunk-relative, fixed up later */
     ti.nblocks = (n + XGM_BLOCK - 1) / XGM_BLOCK;
     ti.termfreq = n;
@@ -207,11 +242,12 @@ static xgm_status upload_index(xgm_index* ix, std::vector<Chunk>& chunks, const 
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     ix->sm_count = prop.multiProcessorCount;
     /* global bases per chunk */
-    size_t nh = 0, nd = 0, nt = 0;
-    std::vector<size_t> hb(chunks.size()), dbase(chunks.size()), tb(chunks.size());
+    size_t nh = 0, nd = 0, nt = 0, nbm = 0, nrk = 0;
+    std::vector<size_t> hb(chunks.size()), dbase(chunks.size()), tb(chunks.size()), bmb(chunks.size()), rkb(chunks.size());
     for (size_t i = 0; i < chunks.size(); ++i) {
-        hb[i] = nh; dbase[i] = nd; tb[i] = nt;
+        hb[i] = nh; dbase[i] = nd; tb[i] = nt; bmb[i] = nbm; rkb[i] = nrk;
         nh += chunks[i].hdr.size(); nd += chunks[i].docs.size(); nt += chunks[i].tfs.size();
+        nbm += chunks[i].bitmaps.size(); nrk += chunks[i].ranks.size();
     }
     if (nh >= 0xffffffffull || nd / 4 >= 0xffffffffull || nt / 4 >= 0xffffffffull)
         return fail(XGM_E_INVALID, "index too large for 32-bit block offsets");
@@ -220,8 +256,22 @@ static xgm_status upload_index(xgm_index* ix, std::vector<Chunk>& chunks, const 
         uint32_t dadd = (uint32_t)(dbase[i] / 4), tadd = (uint32_t)(tb[i] / 4);
         for (auto& h : chunks[i].hdr) { h.doc_off += dadd; h.tf_off += tadd; }
         size_t t_begin = chunk_first_term[i], t_end = chunk_first_term[i + 1];
-        for (size_t t = t_begin; t < t_end; ++t) ix->terms[t].blk_begin += (uint32_t)hb[i];
+        for (size_t t = t_begin; t < t_end; ++t) {
+            ix->terms[t].blk_begin += (uint32_t)hb[i];
+            if (ix->terms[t].bm_off != XGM_NO_BITMAP) { ix->terms[t].bm_off += bmb[i]; ix->terms[t].rk_off += rkb[i]; }
+        }
     });
+    CUDA_TRY(cudaMalloc(&ix->d_bitmaps, std::max<size_t>(nbm, 8) * 4));
+    CUDA_TRY(cudaMalloc(&ix->d_ranks, std::max<size_t>(nrk, 8) * 4));
+    for (size_t i = 0; i < chunks.size(); ++i) {
+        if (!chunks[i].bitmaps.empty())
+            CUDA_TRY(cudaMemcpy(ix->d_bitmaps + bmb[i], chunks[i].bitmaps.data(), chunks[i].bitmaps.size() * 4, cudaMemcpyHostToDevice));
+        if (!chunks[i].ranks.empty())
+            CUDA_TRY(cudaMemcpy(ix->d_ranks + rkb[i], chunks[i].ranks.data(), chunks[i].ranks.size() * 4, cudaMemcpyHostToDevice));
+        std::vector<uint32_t>().swap(chunks[i].bitmaps);
+        std::vector<uint32_t>().swap(chunks[i].ranks);
+    }
+    ix->bytes_bitmaps = (nbm + nrk) * 4;
     /* +16 bytes slack at the end of each column: the unpackers may read one word past a block */
     CUDA_TRY(cudaMalloc(&ix->d_hdr, (nh + 1) * sizeof(XgmBlockHdr)));
     CUDA_TRY(cudaMalloc(&ix->d_docs, nd * 4 + 64));
@@ -255,7 +305,8 @@ static xgm_status upload_index(xgm_index* ix, std::vector<Chunk>& chunks, const 
     }
     ix->nblocks = 0;
     ix->npostings = 0;
-    for (auto& t : ix->terms) { ix->nblocks += t.nblocks; ix->npostings += t.termfreq; }
+    ix->nbitmaps = 0;
+    for (auto& t : ix->terms) { ix->nblocks += t.nblocks; ix->npostings += t.termfreq; ix->nbitmaps += t.bm_off != XGM_NO_BITMAP; }
     ix->bytes_docs = nd * 4;
     ix->bytes_tfs = nt * 4;
     ix->bytes_hdr = nh * sizeof(XgmBlockHdr);
@@ -292,7 +343,8 @@ extern "C" xgm_status xgm_builder_add_term(xgm_builder* b, const char* term, uin
         b->db_wdf_ub = std::max(b->db_wdf_ub, wdfs[i]);
     }
     TermInfo ti;
-    compress_term(b->chunk, docids, wdfs, n, ti);
+    compress_term(b->chunk, docids, wdfs, n, ti, b->have_docs ? b->lastdocid : 0,
+                  b->have_docs ? bitmap_min_df(b->lastdocid) : 0xffffffffu);
     ti.collfreq = collfreq;
     ti.wdf_ub = wdf_ub;
     if (term_id) *term_id = (uint32_t)b->terms.size();
@@ -342,6 +394,7 @@ extern "C" void xgm_index_close(xgm_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     cudaFree(ix->d_hdr); cudaFree(ix->d_docs); cudaFree(ix->d_tfs); cudaFree(ix->d_doclen);
+    cudaFree(ix->d_bitmaps); cudaFree(ix->d_ranks);
     for (int s = 0; s < XGM_MAX_SLOTS; ++s) { cudaFree(ix->d_voff[s]); cudaFree(ix->d_vals[s]); }
     delete ix;
 }
@@ -444,7 +497,7 @@ extern "C" xgm_status xgm_index_build_synthetic(uint32_t ndocs, uint32_t vocab, 
         for (size_t t = first[c]; t < first[c + 1]; ++t) {
             uint32_t n = (uint32_t)(off[t + 1] - off[t]);
             TermInfo& ti = ix->terms[t];
-            compress_term(chunks[c], docids.data() + off[t], wdfs.data() + off[t], n, ti);
+            compress_term(chunks[c], docids.data() + off[t], wdfs.data() + off[t], n, ti, nlocal, bitmap_min_df(nlocal));
             uint64_t cf = 0;
             for (uint64_t p = off[t]; p < off[t + 1]; ++p) cf += wdfs[p];
             ti.collfreq = cf;
@@ -549,6 +602,7 @@ extern "C" xgm_status xgm_index_info_get(const xgm_index* ix, xgm_index_info* o)
     o->nterms = (uint32_t)ix->terms.size(); o->npostings = ix->npostings; o->nblocks = ix->nblocks;
     o->bytes_docids = ix->bytes_docs; o->bytes_wdfs = ix->bytes_tfs; o->bytes_headers = ix->bytes_hdr;
     o->bytes_doclen = ix->bytes_doclen; o->device = ix->device; o->revision = ix->revision;
+    o->bytes_bitmaps = ix->bytes_bitmaps; o->nbitmaps = ix->nbitmaps;
     return XGM_OK;
 }
 
@@ -588,6 +642,7 @@ extern "C" xgm_status xgm_term_stats_get(const xgm_index* ix, const char* term, 
 static void fill_index_params(const xgm_index* ix, XgmKernelParams& p) {
     memset(&p, 0, sizeof(p));
     p.hdr = ix->d_hdr; p.docs = ix->d_docs; p.tfs = ix->d_tfs; p.doclen = ix->d_doclen; p.lastdocid = ix->lastdocid;
+    p.bitmaps = ix->d_bitmaps; p.ranks = ix->d_ranks;
     for (int s = 0; s < XGM_MAX_SLOTS; ++s) { p.slots[s].voff = ix->d_voff[s]; p.slots[s].vals = ix->d_vals[s]; }
 }
 
@@ -625,6 +680,8 @@ struct PlannedQuery {
     double max_possible = 0;
     uint64_t alg_bytes = 0;
     uint32_t sort_by = 0;
+    uint32_t filter = 0;
+    bool count_only = false; /* first >= every possible match count: the MSet is empty, only counts matter */
 };
 
 struct xgm_searcher {
@@ -651,6 +708,10 @@ struct xgm_searcher {
     double* d_match_w = nullptr;
     uint32_t* d_match_d = nullptr;
     uint64_t* d_match_k = nullptr;
+    double* d_pool_w = nullptr;
+    uint32_t* d_pool_d = nullptr;
+    uint64_t* d_pool_k = nullptr;
+    uint32_t pool_total = 0;
     double* d_out_w = nullptr;
     uint32_t* d_out_d = nullptr;
     uint64_t* d_out_k = nullptr;
@@ -660,7 +721,8 @@ struct xgm_searcher {
     uint32_t nq = 0, nitems = 0, nitems_or = 0;
     bool pending = false, any_sort = false;
     xgm_batch_stats stats{};
-    int grid = 0, grid_or = 0;
+    int grid = 0, grid_or = 0, grid_and2 = 0;
+    int and_version = 1; /* 1 = warp-autonomous kernel, 2 = chunked CTA kernel (XGM_AND_KERNEL env) */
     XgmKernelParams params;
 };
 
@@ -671,7 +733,7 @@ extern "C" void xgm_searcher_free(xgm_searcher* s) {
     cudaFreeHost(s->h_queries); cudaFreeHost(s->h_items); cudaFreeHost(s->h_items_or); cudaFreeHost(s->h_out_w); cudaFreeHost(s->h_out_d);
     cudaFreeHost(s->h_out_k); cudaFreeHost(s->h_info);
     cudaFree(s->d_queries); cudaFree(s->d_items); cudaFree(s->d_items_or); cudaFree(s->d_ctrl); cudaFree(s->d_match_w); cudaFree(s->d_match_d);
-    cudaFree(s->d_match_k); cudaFree(s->d_out_w); cudaFree(s->d_out_d); cudaFree(s->d_out_k); cudaFree(s->d_info);
+    cudaFree(s->d_match_k); cudaFree(s->d_pool_w); cudaFree(s->d_pool_d); cudaFree(s->d_pool_k); cudaFree(s->d_out_w); cudaFree(s->d_out_d); cudaFree(s->d_out_k); cudaFree(s->d_info);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->ev2) cudaEventDestroy(s->ev2);
@@ -717,6 +779,11 @@ extern "C" xgm_status xgm_searcher_new(const xgm_index* ix, uint32_t max_batch, 
     CUDA_TRY(cudaMalloc(&s->d_ctrl, s->ctrl_bytes));
     CUDA_TRY(cudaMalloc(&s->d_match_w, nm * 8)); CUDA_TRY(cudaMalloc(&s->d_match_d, nm * 4)); CUDA_TRY(cudaMalloc(&s->d_match_k, nm * 8));
     CUDA_TRY(cudaMalloc(&s->d_out_w, ns * 8)); CUDA_TRY(cudaMalloc(&s->d_out_d, ns * 4)); CUDA_TRY(cudaMalloc(&s->d_out_k, ns * 8));
+    /* overflow pool: room for the tie mass of a few pathological queries per batch (doccount entries at least) */
+    s->pool_total = std::max<uint32_t>(1u << 20, std::min<uint32_t>(1u << 25, 2 * ix->doccount + (1u << 16)));
+    if (const char* e = getenv("XGM_POOL_ENTRIES")) s->pool_total = (uint32_t)strtoul(e, nullptr, 10);
+    CUDA_TRY(cudaMalloc(&s->d_pool_w, (size_t)s->pool_total * 8)); CUDA_TRY(cudaMalloc(&s->d_pool_d, (size_t)s->pool_total * 4));
+    CUDA_TRY(cudaMalloc(&s->d_pool_k, (size_t)s->pool_total * 8));
     CUDA_TRY(cudaMalloc(&s->d_info, nq * sizeof(XgmDevResult)));
     xgm_status st = ensure_items(s.get(), 4096, false);
     if (st != XGM_OK) return st;
@@ -728,6 +795,10 @@ extern "C" xgm_status xgm_searcher_new(const xgm_index* ix, uint32_t max_batch, 
     occ = xgm_or_occupancy_blocks_per_sm();
     if (occ < 1) occ = 1;
     s->grid_or = ix->sm_count * occ;
+    occ = xgm_and2_occupancy_blocks_per_sm();
+    if (occ < 1) occ = 1;
+    s->grid_and2 = ix->sm_count * occ;
+    if (const char* e = getenv("XGM_AND_KERNEL")) s->and_version = atoi(e) == 2 ? 2 : 1;
     *out = s.release();
     return XGM_OK;
 }
@@ -844,8 +915,7 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
     uint32_t cal = std::min(q.check_at_least, docs);
     cal = std::max(cal, first + maxitems);
     pq.first = first; pq.maxitems = maxitems; pq.topk = first + maxitems; pq.check_at_least = cal;
-    pq.nterms = n; pq.sort_by = q.sort_by;
-    if (pq.topk > s->max_topk) { pq.status = XGM_E_INVALID; return XGM_OK; }
+    pq.nterms = n; pq.sort_by = q.sort_by; pq.filter = q.filter;
 
     double k1 = q.k1, k3 = q.k3, b = q.b, mnl = q.min_normlen;
     if (k1 == 0 && k3 == 0 && b == 0 && mnl == 0) { k1 = 1; k3 = 1; b = 0.5; mnl = 0.5; }
@@ -899,7 +969,12 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
         for (uint32_t i = 0; i < n; ++i) {
             uint32_t j = order[i];
             dq.terms[i].termweight = tw[j];
-            if (ids[j] != 0xffffffffu) { dq.terms[i].blk_begin = ix->terms[ids[j]].blk_begin; dq.terms[i].nblocks = ix->terms[ids[j]].nblocks; }
+            dq.terms[i].bm_off = XGM_NO_BITMAP;
+            if (ids[j] != 0xffffffffu) {
+                const TermInfo& tinf = ix->terms[ids[j]];
+                dq.terms[i].blk_begin = tinf.blk_begin; dq.terms[i].nblocks = tinf.nblocks;
+                dq.terms[i].bm_off = tinf.bm_off; dq.terms[i].rk_off = tinf.rk_off;
+            }
         }
     } else {
         /* OR of leaves: Huffman-shaped tree of binary OrPostLists, built from the leaves in query order
@@ -945,7 +1020,12 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
         for (uint32_t i = 0; i < n; ++i) {
             uint32_t j = order[i];
             dq.terms[i].termweight = tw[j];
-            if (ids[j] != 0xffffffffu) { dq.terms[i].blk_begin = ix->terms[ids[j]].blk_begin; dq.terms[i].nblocks = ix->terms[ids[j]].nblocks; }
+            dq.terms[i].bm_off = XGM_NO_BITMAP;
+            if (ids[j] != 0xffffffffu) {
+                const TermInfo& tinf = ix->terms[ids[j]];
+                dq.terms[i].blk_begin = tinf.blk_begin; dq.terms[i].nblocks = tinf.nblocks;
+                dq.terms[i].bm_off = tinf.bm_off; dq.terms[i].rk_off = tinf.rk_off;
+            }
         }
     }
     /* algorithmic bytes, SURVEY.md §8(d): compressed columns + 16 B per block header of every query
@@ -954,13 +1034,17 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
         if (ids[j] != 0xffffffffu) pq.alg_bytes += ix->terms[ids[j]].bytes;
     pq.alg_bytes += 16ull * pq.topk;
 
+    /* `first` at or beyond the largest possible match count: ProtoMSet never fills (protomset.h:497-505),
+     * the MSet is empty and all three bounds equal the exact match count — count on the device only */
+    if (pq.first >= pq.tf_max && cal != 0) { pq.count_only = true; dq.topk = 0; }
+    else if (pq.topk > s->max_topk) { pq.status = XGM_E_INVALID; return XGM_OK; }
     /* pruning buckets: linear in the primary sort key (weight, or the sort value for VAL sorts) */
     if (q.sort_by == XGM_SORT_REL || q.sort_by == XGM_SORT_REL_VAL)
         dq.bucket_scale = pq.max_possible > 0 ? (double)XGM_NBINS / pq.max_possible : 0.0;
     else
         dq.bucket_scale = (double)XGM_NBINS / ((double)ix->slot_max[q.sort_slot] + 1.0);
 
-    if (cal == 0 || pq.topk == 0) { pq.on_device = false; return XGM_OK; } /* bounds only, matcher.cc:437-461 */
+    if (cal == 0) { pq.on_device = false; return XGM_OK; } /* bounds only, matcher.cc:437-461 */
     if (dq.route == 0 && any_absent) { pq.on_device = false; return XGM_OK; } /* AND with an absent term: empty */
     pq.on_device = true;
     if (dq.route == 0) {
@@ -990,7 +1074,10 @@ static xgm_status launch_batch(xgm_searcher* s) {
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
     s->stats.kernel_launches = 0;
     p.pass = 0;
-    if (s->nitems) { CUDA_TRY(xgm_launch_and(p, s->grid, s->stream)); s->stats.kernel_launches++; }
+    auto launch_and = [&](const XgmKernelParams& pp) {
+        return s->and_version == 1 ? xgm_launch_and(pp, s->grid, s->stream) : xgm_launch_and2(pp, s->grid_and2, s->stream);
+    };
+    if (s->nitems) { CUDA_TRY(launch_and(p)); s->stats.kernel_launches++; }
     if (s->nitems_or) { CUDA_TRY(xgm_launch_or(p, s->grid_or, s->stream)); s->stats.kernel_launches++; }
     CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
     CUDA_TRY(xgm_launch_topk(p, s->nq, s->stream));
@@ -998,7 +1085,7 @@ static xgm_status launch_batch(xgm_searcher* s) {
     /* second pass: only queries whose candidate buffer overflowed do any work (device-side flag) */
     XgmKernelParams p2 = p;
     p2.pass = 1;
-    if (s->nitems) { CUDA_TRY(xgm_launch_and(p2, s->grid, s->stream)); s->stats.kernel_launches++; }
+    if (s->nitems) { CUDA_TRY(launch_and(p2)); s->stats.kernel_launches++; }
     if (s->nitems_or) { CUDA_TRY(xgm_launch_or(p2, s->grid_or, s->stream)); s->stats.kernel_launches++; }
     CUDA_TRY(xgm_launch_topk(p2, s->nq, s->stream));
     s->stats.kernel_launches++;
@@ -1020,6 +1107,7 @@ extern "C" xgm_status xgm_search_submit(xgm_searcher* s, const xgm_query* querie
     /* first pass with a provisional granularity needs the driver block counts; plan twice is wasteful,
      * so use a fixed small granularity scaled by batch size */
     uint32_t bpi = nq >= 256 ? 16 : (nq >= 16 ? 4 : 1);
+    if (s->and_version == 2) bpi = nq >= 64 ? 16 : (nq >= 8 ? 8 : 4);
     s->any_sort = false;
     uint64_t alg = 0, postings = 0;
     for (uint32_t i = 0; i < nq; ++i) {
@@ -1064,6 +1152,7 @@ extern "C" xgm_status xgm_search_submit(xgm_searcher* s, const xgm_query* querie
     p.qstate = reinterpret_cast<XgmQState*>(s->d_ctrl + 32);
     p.hist = reinterpret_cast<uint32_t*>(s->d_ctrl + 32 + (size_t)s->max_batch * sizeof(XgmQState));
     p.match_cap = s->match_cap; p.keep_cap = s->keep_cap;
+    p.pool_total = s->pool_total; p.pool_w = s->d_pool_w; p.pool_d = s->d_pool_d; p.pool_k = s->d_pool_k;
     p.match_w = s->d_match_w; p.match_d = s->d_match_d; p.match_k = s->d_match_k;
     p.out_stride = s->max_topk; p.out_w = s->d_out_w; p.out_d = s->d_out_d; p.out_k = s->d_out_k; p.out_info = s->d_info;
     CUDA_TRY(cudaMemcpyAsync(s->d_queries, s->h_queries, (size_t)nq * sizeof(XgmDevQuery), cudaMemcpyHostToDevice, s->stream));
@@ -1097,11 +1186,15 @@ static void finish_info(const PlannedQuery& pq, const XgmDevResult* dr, const do
         max_w = dr->max_w;
         (void)w;
         /* ProtoMSet::finalise, protomset.h:484-612 (no collapser / decider / percent cut-off) */
-        if (size != pq.topk) lb = est = ub = size;
+        if (pq.count_only) { size = 0; lb = est = ub = dr->exact; }
+        else if (size != pq.topk) lb = est = ub = size;
         else if (known < pq.check_at_least) lb = est = ub = known;
         else { lb = std::max(lb, known); est = std::max(est, known); }
         if (dr->flags & 5u) o->status = XGM_E_UNIMPLEMENTED; /* candidates lost: pathological tie mass */
         if (dr->flags & 2u) o->flags |= XGM_MSET_BOUNDS_APPROX;
+        /* with a value-range source in the AND the reference's lower bound / estimate also fold in
+         * ValueRangePostList::get_termfreq_est (valuerangepostlist.cc:70-130), which is not restated */
+        if (pq.filter && size == pq.topk && known >= pq.check_at_least) o->flags |= XGM_MSET_BOUNDS_APPROX;
     } else if (pq.check_at_least != 0) {
         lb = est = ub = 0; /* empty result set: !full() branch */
     }
@@ -1110,7 +1203,7 @@ static void finish_info(const PlannedQuery& pq, const XgmDevResult* dr, const do
     o->matches_upper_bound = o->uncollapsed_upper_bound = ub;
     o->max_attained = max_w;
     o->n = size > pq.first ? size - pq.first : 0;
-    if (size != 0 && max_w != 0.0) {
+    if ((size != 0 || (pq.count_only && pq.on_device && dr->exact != 0)) && max_w != 0.0) {
         /* ProtoMSet::finalise_percentages protomset.h:466-471: AND → every subquery matched */
         /* AND: every leaf matches; OR sorted by relevance: leaves matching the best document */
         uint32_t subqs = dr->max_subqs;

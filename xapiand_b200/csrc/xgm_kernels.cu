@@ -248,7 +248,7 @@ __device__ __noinline__ void emit_matches_impl(const XgmKernelParams& p, const X
         if (alive >> k & 1u) {
             if (q->sort_by != 0) key[k] = doc_sort_key(p, q, c[k]);
             bkt[k] = match_bucket(q, acc[k], key[k]);
-            if (bkt[k] >= bstar) keep |= 1u << k;
+            if (bkt[k] >= bstar && q->topk != 0) keep |= 1u << k;
         }
     }
     const uint32_t n = __popc(keep);
@@ -270,17 +270,34 @@ __device__ __noinline__ void emit_matches_impl(const XgmKernelParams& p, const X
     base = __shfl_sync(FULL, base, 0);
     if (nkeep == 0) return;
     uint32_t idx = base + (incl - n);
-    const size_t qoff = (size_t)qi * p.match_cap;
+    if (p.pass == 0) {
+        const size_t qoff = (size_t)qi * p.match_cap;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (keep >> k & 1u) {
-            if (p.pass == 0) atomicAdd(&hist[bkt[k]], 1u);
-            if (idx < p.match_cap) {
-                p.match_w[qoff + idx] = acc[k];
-                p.match_d[qoff + idx] = c[k];
-                p.match_k[qoff + idx] = q->sort_by != 0 ? key[k] : (uint64_t)aux[k];
+        for (int k = 0; k < 4; ++k) {
+            if (keep >> k & 1u) {
+                atomicAdd(&hist[bkt[k]], 1u);
+                if (idx < p.match_cap) {
+                    p.match_w[qoff + idx] = acc[k];
+                    p.match_d[qoff + idx] = c[k];
+                    p.match_k[qoff + idx] = q->sort_by != 0 ? key[k] : (uint64_t)aux[k];
+                }
+                ++idx;
             }
-            ++idx;
+        }
+    } else {
+        /* second pass: every match at or above the exact b* goes to the query's slice of the pool */
+        const size_t poff = st->pool_off;
+        const uint32_t pcap = st->pool_cap;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (keep >> k & 1u) {
+                if (idx < pcap) {
+                    p.pool_w[poff + idx] = acc[k];
+                    p.pool_d[poff + idx] = c[k];
+                    p.pool_k[poff + idx] = q->sort_by != 0 ? key[k] : (uint64_t)aux[k];
+                }
+                ++idx;
+            }
         }
     }
     /* raise b* whenever the stored count crosses a multiple of 256 (and topk matches exist) */
@@ -478,23 +495,55 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 3) xgm_and_kernel(XgmKernelP
                 if (!__any_sync(FULL, alive != 0)) break;
                 const uint32_t lbegin = __shfl_sync(FULL, my_begin, j);
                 const uint32_t lnblk = __shfl_sync(FULL, my_nblk, j);
-                uint32_t cur = __shfl_sync(FULL, my_cur, j);
                 const double twj = q->terms[j].termweight;
-                cur = probe_list(
-                    p, hdr + lbegin, lnblk, cur, ws, phase, lane, c, alive,
-                    [&](int k, uint32_t pos, const XgmBlockHdr& bh) {
-                        if (j == 1) {
-                            /* first confirmation: fetch doclen and the driver's own wdf lazily */
-                            dl[k] = __ldg(&p.doclen[c[k]]);
-                            uint32_t tf0 = unpack_gl(p.tfs, dh.tf_off, 4 * lane + k, XGM_HDR_TF_BITS(dh.meta));
-                            acc[k] = bm25_sumpart(tw0, q, tf0, dl[k]);
+                auto on_hit = [&](int k, uint32_t pos, const XgmBlockHdr& bh) {
+                    if (j == 1) {
+                        /* first confirmation: fetch doclen and the driver's own wdf lazily */
+                        dl[k] = __ldg(&p.doclen[c[k]]);
+                        uint32_t tf0 = unpack_gl(p.tfs, dh.tf_off, 4 * lane + k, XGM_HDR_TF_BITS(dh.meta));
+                        acc[k] = bm25_sumpart(tw0, q, tf0, dl[k]);
+                    }
+                    uint32_t tfj = unpack_gl(p.tfs, bh.tf_off, pos, XGM_HDR_TF_BITS(bh.meta));
+                    /* MultiAndPostList::get_weight: result += plist[i]->get_weight(), in plist order */
+                    acc[k] = __dadd_rn(acc[k], bm25_sumpart(twj, q, tfj, dl[k]));
+                };
+                const uint64_t bm_off = q->terms[j].bm_off;
+                if (bm_off != XGM_NO_BITMAP) {
+                    /* membership bitmap: the skip_to/check of the leapfrog is one word load per candidate,
+                     * all four of a lane (and all 128 of the warp) in flight together */
+                    const uint32_t* __restrict__ bm = p.bitmaps + bm_off;
+                    uint32_t w[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) w[k] = (alive >> k & 1u) ? __ldg(bm + (c[k] >> 5)) : 0u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (alive >> k & 1u) {
+                            if (w[k] >> (c[k] & 31) & 1u) {
+                                /* rank of the docid = postings before its 256-docid group + set bits before it */
+                                const uint32_t d = c[k], g = d >> 8, wsel = (d >> 5) & 7u;
+                                uint32_t r = __ldg(p.ranks + q->terms[j].rk_off + g);
+                                const uint4 a = __ldg(reinterpret_cast<const uint4*>(bm + g * 8));
+                                const uint4 b2 = __ldg(reinterpret_cast<const uint4*>(bm + g * 8 + 4));
+                                const uint32_t ww[8] = {a.x, a.y, a.z, a.w, b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+                                for (uint32_t x = 0; x < 8; ++x) {
+                                    if (x < wsel) r += __popc(ww[x]);
+                                    else if (x == wsel) r += __popc(ww[x] & ((1u << (d & 31)) - 1u));
+                                }
+                                const XgmBlockHdr bh = hdr[lbegin + (r >> 7)];
+                                on_hit(k, r & 127u, bh);
+                            } else {
+                                alive &= ~(1u << k);
+                            }
                         }
-                        uint32_t tfj = unpack_gl(p.tfs, bh.tf_off, pos, XGM_HDR_TF_BITS(bh.meta));
-                        /* MultiAndPostList::get_weight: result += plist[i]->get_weight(), in plist order */
-                        acc[k] = __dadd_rn(acc[k], bm25_sumpart(twj, q, tfj, dl[k]));
-                    },
-                    [&](int k) { alive &= ~(1u << k); });
-                if (lane == j) my_cur = cur;
+                    }
+                    (void)lnblk;
+                } else {
+                    uint32_t cur = __shfl_sync(FULL, my_cur, j);
+                    cur = probe_list(p, hdr + lbegin, lnblk, cur, ws, phase, lane, c, alive, on_hit,
+                                     [&](int k) { alive &= ~(1u << k); });
+                    if (lane == j) my_cur = cur;
+                }
             }
 
             /* value-slot filter (OP_FILTER with a range source), applied to the survivors */
@@ -509,6 +558,353 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 3) xgm_and_kernel(XgmKernelP
             buf ^= 1u;
         }
     }
+}
+
+
+/* ------------------------------------------------------------------ chunked AND kernel (v2) */
+
+/* Same contract as xgm_and_kernel, organised for memory-level parallelism (the warp-autonomous kernel
+ * is bound by its chain of dependent global round trips, ~20 per driver block).  A CTA owns a chunk of
+ * up to 16 driver blocks (2048 candidate docids).  The candidates go into a shared-memory hash set; the
+ * blocks of the next list that overlap the chunk's docid span are then fetched with all their headers
+ * in one coalesced read and four bulk copies in flight per warp, decoded by all warps at once, and
+ * every decoded posting probes the hash set in O(1).  When the survivors are few compared with the
+ * blocks in the span the kernel gallops per survivor instead (the leapfrog of
+ * MultiAndPostList::find_next_match, multiandpostlist.cc:179-206).  Scoring is lazy: wdf / doc length
+ * are only fetched for documents confirmed by the second list. */
+#define A2_WARPS 8
+#define A2_THREADS (A2_WARPS * 32)
+#define A2_MAXBLK 16
+#define A2_CAND (A2_MAXBLK * XGM_BLOCK)
+#define A2_BMWORDS 1024u /* 32768-bit membership filter over (docid mod 32768) */
+#define A2_STAGES 4
+
+struct __align__(16) A2Smem {
+    uint32_t stage[A2_WARPS][A2_STAGES][STAGE_WORDS];
+    uint64_t bar[A2_WARPS][A2_STAGES];
+    double acc[A2_CAND];
+    uint32_t cand[A2_CAND];   /* ascending docids: index = blk*128 + position in driver block blk */
+    uint32_t hitpos[A2_CAND]; /* (block - lo) << 7 | position, valid where `hit` is set */
+    uint32_t bm[A2_BMWORDS];
+    uint32_t alive[A2_CAND / 32];
+    uint32_t hit[A2_CAND / 32];
+    uint32_t lo[XGM_DEV_MAX_TERMS], hi[XGM_DEV_MAX_TERMS]; /* block span of list j covering the chunk */
+    uint32_t item;
+    uint32_t n_alive;
+};
+
+/* index of docid d in the chunk's ascending candidate array (n entries, padded with the sentinel), or -1 */
+__device__ __forceinline__ int a2_find(const A2Smem& s, uint32_t d) {
+    uint32_t pos = 0;
+#pragma unroll
+    for (uint32_t step = A2_CAND / 2; step >= 1; step >>= 1)
+        if (s.cand[pos + step - 1] < d) pos += step;
+    return s.cand[pos] == d ? (int)pos : -1;
+}
+
+__global__ void __launch_bounds__(A2_THREADS, 3) xgm_and2_kernel(XgmKernelParams p) {
+    extern __shared__ __align__(16) unsigned char a2_raw[];
+    A2Smem& s = *reinterpret_cast<A2Smem*>(a2_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (lane < A2_STAGES) mbar_init(&s.bar[warp][lane], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    uint32_t phases = 0; /* bit b = parity of this warp's staging barrier b */
+    const XgmBlockHdr* __restrict__ hdr = p.hdr;
+    if (p.pass != 0 && *reinterpret_cast<volatile uint32_t*>(p.work_counter + 4) == 0) return;
+
+    auto stage_issue = [&](uint32_t b, const uint4* col, uint32_t off16, uint32_t bits) {
+        __syncwarp();
+        if (bits != 0 && lane == 0) {
+            mbar_expect_tx(&s.bar[warp][b], bits * 16u);
+            bulk_g2s(s.stage[warp][b], col + off16, bits * 16u, &s.bar[warp][b]);
+        }
+    };
+    auto stage_wait = [&](uint32_t b, uint32_t bits) {
+        if (bits == 0) return;
+        mbar_wait(&s.bar[warp][b], (phases >> b) & 1u);
+        phases ^= 1u << b;
+    };
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s.item = atomicAdd(p.work_counter + 2 * p.pass, 1u);
+        __syncthreads();
+        const uint32_t item = s.item;
+        if (item >= p.nitems) break;
+        const XgmWorkItem wi = p.items[item];
+        if (p.pass != 0 && p.qstate[wi.query].rerun == 0) continue;
+        const XgmDevQuery* q = &p.queries[wi.query];
+        const uint32_t nterms = q->nterms;
+        const uint32_t nb = wi.b1 - wi.b0;
+        const uint32_t drv_begin = q->terms[0].blk_begin;
+        const double tw0 = q->terms[0].termweight;
+
+        /* ---- driver blocks: both headers, then both bulk copies, in flight before anything waits ---- */
+        const uint32_t blk0 = warp, blk1 = warp + A2_WARPS;
+        XgmBlockHdr dh0, dh1;
+        dh0.meta = dh1.meta = 0; dh0.first = dh1.first = 0; dh0.doc_off = dh1.doc_off = 0; dh0.tf_off = dh1.tf_off = 0;
+        if (blk0 < nb) { const uint4 h = __ldg(reinterpret_cast<const uint4*>(hdr + drv_begin + wi.b0 + blk0)); dh0.first = h.x; dh0.doc_off = h.y; dh0.tf_off = h.z; dh0.meta = h.w; }
+        if (blk1 < nb) { const uint4 h = __ldg(reinterpret_cast<const uint4*>(hdr + drv_begin + wi.b0 + blk1)); dh1.first = h.x; dh1.doc_off = h.y; dh1.tf_off = h.z; dh1.meta = h.w; }
+        const uint32_t cmin = __ldg(&hdr[drv_begin + wi.b0].first);
+        const uint32_t cmax = __ldg(&hdr[drv_begin + wi.b1].first) - 1u; /* sentinel after the last block */
+        if (blk0 < nb) {
+            stage_issue(0, p.docs, dh0.doc_off, XGM_HDR_DOC_BITS(dh0.meta));
+            if (nterms == 1) stage_issue(2, p.tfs, dh0.tf_off, XGM_HDR_TF_BITS(dh0.meta));
+        }
+        if (blk1 < nb) {
+            stage_issue(1, p.docs, dh1.doc_off, XGM_HDR_DOC_BITS(dh1.meta));
+            if (nterms == 1) stage_issue(3, p.tfs, dh1.tf_off, XGM_HDR_TF_BITS(dh1.meta));
+        }
+        for (uint32_t i = tid; i < A2_BMWORDS; i += A2_THREADS) s.bm[i] = 0u;
+        for (uint32_t i = nb * XGM_BLOCK + tid; i < A2_CAND; i += A2_THREADS) s.cand[i] = XGM_SENTINEL;
+        if (tid < A2_CAND / 32) { s.alive[tid] = 0u; s.hit[tid] = 0u; }
+        __syncthreads();
+
+        /* ---- spans of the other lists while the copies fly: one seek per (list, end) ---- */
+        for (uint32_t t = warp; t < 2 * (nterms - 1); t += A2_WARPS) {
+            const uint32_t j = 1 + (t >> 1);
+            if (q->terms[j].bm_off != XGM_NO_BITMAP) continue; /* probed through its bitmap: no span needed */
+            const XgmBlockHdr* lh = hdr + q->terms[j].blk_begin;
+            const uint32_t n = q->terms[j].nblocks;
+            XgmBlockHdr tmp;
+            uint32_t nf;
+            const uint32_t r = n ? warp_seek(lh, 0, n, (t & 1u) ? cmax : cmin, lane, tmp, nf) : 0u;
+            if (lane == 0) { if (t & 1u) s.hi[j] = r; else s.lo[j] = r; }
+        }
+
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            const uint32_t blk = which ? blk1 : blk0;
+            if (blk >= nb) continue;
+            const XgmBlockHdr dh = which ? dh1 : dh0;
+            const uint32_t dbits = XGM_HDR_DOC_BITS(dh.meta), dcount = XGM_HDR_COUNT(dh.meta);
+            const uint32_t tb = XGM_HDR_TF_BITS(dh.meta);
+            stage_wait(which, dbits);
+            uint32_t c[4];
+            decode_docids(s.stage[warp][which], dbits, dh.first, lane, c);
+            if (nterms == 1) stage_wait(2 + which, tb);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool valid = 4 * lane + k < dcount;
+                const uint32_t idx = blk * XGM_BLOCK + 4 * lane + k;
+                s.cand[idx] = valid ? c[k] : XGM_SENTINEL;
+                if (valid) {
+                    if (nterms == 1) {
+                        const uint32_t tf = tb ? unpack_sm(s.stage[warp][2 + which], 4 * lane + k, tb, bitmask(tb)) : 0u;
+                        s.acc[idx] = bm25_sumpart(tw0, q, tf, __ldg(&p.doclen[c[k]]));
+                    } else {
+                        atomicOr(&s.bm[(c[k] >> 5) & (A2_BMWORDS - 1)], 1u << (c[k] & 31));
+                    }
+                }
+            }
+            if (lane < 4) {
+                const uint32_t lo_pos = 32 * lane;
+                s.alive[blk * 4 + lane] = dcount >= lo_pos + 32 ? 0xffffffffu : (dcount > lo_pos ? ((1u << (dcount - lo_pos)) - 1u) : 0u);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+
+        /* ---- the other lists, ascending termfreq ---- */
+        for (uint32_t j = 1; j < nterms; ++j) {
+            if (warp == 0) {
+                uint32_t n = 0;
+                for (uint32_t w = lane; w < nb * 4; w += 32) n += __popc(s.alive[w]);
+                n = __reduce_add_sync(FULL, n);
+                if (lane == 0) s.n_alive = n;
+            }
+            __syncthreads();
+            const uint32_t n_alive = s.n_alive;
+            if (n_alive == 0) break;
+            const uint32_t lbegin = q->terms[j].blk_begin, lnblk = q->terms[j].nblocks;
+            const XgmBlockHdr* lh = hdr + lbegin;
+            const uint32_t lo = s.lo[j], hi = s.hi[j];
+            const double twj = q->terms[j].termweight;
+            const bool has_bm = q->terms[j].bm_off != XGM_NO_BITMAP;
+            if (has_bm) {
+                /* membership bitmap: one word load per surviving candidate, all in flight together;
+                 * 32 consecutive candidates belong to one warp, so the hit word is a ballot */
+                const uint32_t* __restrict__ bm = p.bitmaps + q->terms[j].bm_off;
+                for (uint32_t base = 0; base < nb * XGM_BLOCK; base += A2_THREADS) {
+                    const uint32_t idx = base + tid;
+                    const uint32_t aw = s.alive[idx >> 5];
+                    bool h = false;
+                    if (aw >> (idx & 31) & 1u) {
+                        const uint32_t d = s.cand[idx];
+                        h = (__ldg(bm + (d >> 5)) >> (d & 31)) & 1u;
+                    }
+                    const uint32_t bal = __ballot_sync(FULL, h);
+                    if (lane == 0) s.hit[idx >> 5] = bal;
+                }
+            } else if (lnblk != 0) {
+                const uint32_t nblk = hi - lo + 1;
+                if (nblk <= n_alive + 8) {
+                    /* dense: decode every block of the span.  A posting first tests the membership filter
+                     * (one shared-memory word), the few that pass binary-search the candidate array.
+                     * Per round a warp takes 32 blocks (lane i holds the header of its i-th block),
+                     * with A2_STAGES bulk copies in flight. */
+                    for (uint32_t base = lo; base <= hi; base += A2_WARPS * 32) {
+                        const uint32_t myb = base + warp + A2_WARPS * lane;
+                        uint4 hv = make_uint4(0u, 0u, 0u, 0u);
+                        if (myb <= hi) hv = __ldg(reinterpret_cast<const uint4*>(lh + myb));
+                        uint32_t cnt_w = 0;
+                        if (base + warp <= hi) cnt_w = (hi - (base + warp)) / A2_WARPS + 1;
+                        if (cnt_w > 32) cnt_w = 32;
+                        for (uint32_t i = 0; i < cnt_w && i < A2_STAGES; ++i) {
+                            const uint32_t off = __shfl_sync(FULL, hv.y, i), meta = __shfl_sync(FULL, hv.w, i);
+                            stage_issue(i, p.docs, off, XGM_HDR_DOC_BITS(meta));
+                        }
+                        for (uint32_t i = 0; i < cnt_w; ++i) {
+                            const uint32_t first = __shfl_sync(FULL, hv.x, i), meta = __shfl_sync(FULL, hv.w, i);
+                            const uint32_t bits = XGM_HDR_DOC_BITS(meta), cnt = XGM_HDR_COUNT(meta);
+                            const uint32_t sb = i % A2_STAGES;
+                            stage_wait(sb, bits);
+                            uint32_t bd[4];
+                            decode_docids(s.stage[warp][sb], bits, first, lane, bd);
+                            if (i + A2_STAGES < cnt_w) {
+                                const uint32_t off = __shfl_sync(FULL, hv.y, i + A2_STAGES);
+                                const uint32_t m2 = __shfl_sync(FULL, hv.w, i + A2_STAGES);
+                                stage_issue(sb, p.docs, off, XGM_HDR_DOC_BITS(m2));
+                            }
+                            const uint32_t brel = (base + warp + A2_WARPS * i) - lo;
+                            uint32_t flags = 0;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint32_t d = bd[k];
+                                if (4 * lane + k < cnt && d >= cmin && d <= cmax &&
+                                    (s.bm[(d >> 5) & (A2_BMWORDS - 1)] >> (d & 31) & 1u))
+                                    flags |= 1u << k;
+                            }
+                            while (__any_sync(FULL, flags != 0)) {
+                                if (flags) {
+                                    const int k = __ffs(flags) - 1;
+                                    flags &= flags - 1;
+                                    const uint32_t d = k == 0 ? bd[0] : k == 1 ? bd[1] : k == 2 ? bd[2] : bd[3];
+                                    const int idx = a2_find(s, d);
+                                    if (idx >= 0 && (s.alive[idx >> 5] >> (idx & 31) & 1u)) {
+                                        s.hitpos[idx] = (brel << 7) | (4 * lane + k);
+                                        atomicOr(&s.hit[idx >> 5], 1u << (idx & 31));
+                                    }
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    /* sparse: gallop per surviving candidate */
+                    for (uint32_t w = warp; w < nb * 4; w += A2_WARPS) {
+                        uint32_t bits = s.alive[w];
+                        while (bits) {
+                            const uint32_t bit = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            const uint32_t idx = w * 32 + bit;
+                            const uint32_t d = s.cand[idx];
+                            XgmBlockHdr bh;
+                            uint32_t nf;
+                            const uint32_t b = warp_seek(lh, lo, lnblk, d, lane, bh, nf);
+                            if (d < bh.first) continue;
+                            const uint32_t dbits = XGM_HDR_DOC_BITS(bh.meta), cnt = XGM_HDR_COUNT(bh.meta);
+                            stage_issue(0, p.docs, bh.doc_off, dbits);
+                            stage_wait(0, dbits);
+                            uint32_t bd[4];
+                            decode_docids(s.stage[warp][0], dbits, bh.first, lane, bd);
+                            uint32_t found = 0;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (4 * lane + k < cnt && bd[k] == d) found = 4 * lane + k + 1;
+                            const uint32_t bal = __ballot_sync(FULL, found != 0);
+                            if (bal) {
+                                const uint32_t pos = __shfl_sync(FULL, found, __ffs(bal) - 1) - 1;
+                                if (lane == 0) {
+                                    s.hitpos[idx] = ((b - lo) << 7) | pos;
+                                    atomicOr(&s.hit[idx >> 5], 1u << (idx & 31));
+                                }
+                            }
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            /* resolve: survivors = alive & hit; score them (MultiAndPostList::get_weight order) */
+            for (uint32_t idx = tid; idx < nb * XGM_BLOCK; idx += A2_THREADS) {
+                const uint32_t m = 1u << (idx & 31);
+                if ((s.alive[idx >> 5] & m) && (s.hit[idx >> 5] & m)) {
+                    const uint32_t d = s.cand[idx];
+                    const uint32_t dlen = __ldg(&p.doclen[d]);
+                    if (j == 1) {
+                        const XgmBlockHdr dh = hdr[drv_begin + wi.b0 + (idx >> 7)];
+                        const uint32_t tf0 = unpack_gl(p.tfs, dh.tf_off, idx & 127u, XGM_HDR_TF_BITS(dh.meta));
+                        s.acc[idx] = bm25_sumpart(tw0, q, tf0, dlen);
+                    }
+                    uint32_t bj, pj; /* block and position of the posting in list j */
+                    if (has_bm) {
+                        /* rank of docid d = postings before its 256-docid group + set bits before it */
+                        const uint32_t* __restrict__ bm = p.bitmaps + q->terms[j].bm_off;
+                        const uint32_t g = d >> 8, wsel = (d >> 5) & 7u;
+                        uint32_t r = __ldg(p.ranks + q->terms[j].rk_off + g);
+                        const uint4 a = __ldg(reinterpret_cast<const uint4*>(bm + g * 8));
+                        const uint4 b2 = __ldg(reinterpret_cast<const uint4*>(bm + g * 8 + 4));
+                        const uint32_t ww[8] = {a.x, a.y, a.z, a.w, b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+                        for (uint32_t x = 0; x < 8; ++x) {
+                            if (x < wsel) r += __popc(ww[x]);
+                            else if (x == wsel) r += __popc(ww[x] & ((1u << (d & 31)) - 1u));
+                        }
+                        bj = r >> 7; pj = r & 127u;
+                    } else {
+                        const uint32_t hp = s.hitpos[idx];
+                        bj = lo + (hp >> 7); pj = hp & 127u;
+                    }
+                    const XgmBlockHdr bh = lh[bj];
+                    const uint32_t tfj = unpack_gl(p.tfs, bh.tf_off, pj, XGM_HDR_TF_BITS(bh.meta));
+                    s.acc[idx] = __dadd_rn(s.acc[idx], bm25_sumpart(twj, q, tfj, dlen));
+                }
+            }
+            __syncthreads();
+            if (tid < A2_CAND / 32) { s.alive[tid] &= s.hit[tid]; s.hit[tid] = 0u; }
+            __syncthreads();
+        }
+
+        /* ---- filter + emit: warp w handles driver blocks w, w+8 ---- */
+        for (uint32_t blk = warp; blk < nb; blk += A2_WARPS) {
+            uint32_t alive = 0, c[4];
+            double acc[4];
+            const uint32_t aw = s.alive[blk * 4 + (lane >> 3)];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t idx = blk * XGM_BLOCK + 4 * lane + k;
+                c[k] = s.cand[idx];
+                acc[k] = s.acc[idx];
+                if (aw >> ((4 * lane + k) & 31) & 1u) alive |= 1u << k;
+            }
+            if (q->filter) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if ((alive >> k & 1u) && !doc_passes_filter(p, q, c[k])) alive &= ~(1u << k);
+            }
+            const uint32_t aux[4] = {nterms, nterms, nterms, nterms};
+            emit_matches(p, q, wi.query, lane, alive, acc, c, aux);
+        }
+    }
+}
+
+cudaError_t xgm_launch_and2(const XgmKernelParams& p, int grid, cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(xgm_and2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A2Smem));
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    xgm_and2_kernel<<<grid, A2_THREADS, sizeof(A2Smem), s>>>(p);
+    return cudaGetLastError();
+}
+
+int xgm_and2_occupancy_blocks_per_sm() {
+    int n = 0;
+    cudaFuncSetAttribute(xgm_and2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A2Smem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, xgm_and2_kernel, A2_THREADS, sizeof(A2Smem));
+    return n;
 }
 
 /* ------------------------------------------------------------------ OR kernel */
@@ -658,72 +1054,159 @@ __device__ __forceinline__ bool ranks_before(uint32_t sort_by, uint32_t reverse,
 
 #define TOPK_THREADS 256
 
-/* One CTA per query. Survivors (bucket >= final b*) are compacted into shared memory and rank-sorted:
- * every match counts how many matches rank before it; ranks < topk are written to their final
- * position.  When nothing was pruned the same pass reproduces ProtoMSet's known_matching_docs: walking
- * the matches in docid order, a match is counted iff it is among the first max(check_at_least, topk+1)
- * or fewer than topk earlier matches have a strictly greater weight (protomset.h:340-400 with the
- * `weight < min_weight → continue` of matcher.cc:496-498). */
+/* Sort key of a match as up to five 32-bit words, most significant first, such that a larger key ranks
+ * earlier under the reference's comparators (msetcmp.cc:54-98, ascending docid order):
+ *   relevance:            weight bits, ~docid                      (3 words)
+ *   value then relevance: value', weight bits, ~docid              (5 words)   value' = reverse ? v : ~v
+ *   value:                value', ~docid                           (3 words)
+ *   relevance then value: weight bits, value', ~docid              (5 words)
+ * Weights are >= 0, so their IEEE bit patterns order like the values. */
+__device__ __forceinline__ int match_key_words(uint32_t sort_by, uint32_t reverse, double w, uint64_t k, uint32_t d,
+                                               uint32_t out[5]) {
+    const uint64_t wb = (uint64_t)__double_as_longlong(w);
+    const uint64_t kv = reverse ? k : ~k;
+    const uint32_t nd = ~d;
+    if (sort_by == 0) { out[0] = (uint32_t)(wb >> 32); out[1] = (uint32_t)wb; out[2] = nd; return 3; }
+    if (sort_by == 2) { out[0] = (uint32_t)(kv >> 32); out[1] = (uint32_t)kv; out[2] = nd; return 3; }
+    if (sort_by == 1) {
+        out[0] = (uint32_t)(kv >> 32); out[1] = (uint32_t)kv; out[2] = (uint32_t)(wb >> 32); out[3] = (uint32_t)wb; out[4] = nd;
+        return 5;
+    }
+    out[0] = (uint32_t)(wb >> 32); out[1] = (uint32_t)wb; out[2] = (uint32_t)(kv >> 32); out[3] = (uint32_t)kv; out[4] = nd;
+    return 5;
+}
+
+/* One CTA per query.
+ * First pass: survivors (bucket >= final b*) are compacted into shared memory and rank-sorted under
+ * the reference's total order; when nothing was pruned the same pass reproduces ProtoMSet's
+ * known_matching_docs (walking the matches in docid order, a match is counted iff it is among the first
+ * max(check_at_least, topk+1) or fewer than topk earlier matches have a strictly greater weight —
+ * protomset.h:340-400 with the `weight < min_weight → continue` of matcher.cc:496-498).
+ * If candidates were lost (many warps emitted before b* could rise) the completed histogram gives the
+ * exact b* and the exact number of matches at or above it; the query gets a slice of the overflow pool
+ * and is flagged for a second matching pass.
+ * Second pass: the slice holds every match at or above b*.  If a single bucket holds a mass of ties the
+ * slice can be far larger than shared memory: an MSB-first radix select over the composite sort key
+ * (8 bits per round, in global memory) finds the exact topk-th key, and only the topk winners are sorted. */
 __global__ void __launch_bounds__(TOPK_THREADS) xgm_topk_kernel(XgmKernelParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t qi = blockIdx.x;
     const XgmDevQuery* q = &p.queries[qi];
     const XgmQState st = p.qstate[qi];
     if (p.pass != 0 && st.rerun == 0) return;
-    const uint32_t stored = st.stored < p.match_cap ? st.stored : p.match_cap;
     double* sw = reinterpret_cast<double*>(smem_raw);
     uint64_t* sk = reinterpret_cast<uint64_t*>(sw + p.keep_cap);
     uint32_t* sd = reinterpret_cast<uint32_t*>(sk + p.keep_cap);
-    __shared__ uint32_t s_known, s_n;
-    const size_t qoff = (size_t)qi * p.match_cap;
+    __shared__ uint32_t s_known, s_n, s_hist[256], s_prefix[5], s_krem;
     const uint32_t sort_by = q->sort_by, reverse = q->sort_reverse;
-    const bool complete = (st.total == st.stored) && (st.stored <= p.keep_cap); /* every match is here */
-    if (threadIdx.x == 0) { s_known = 0; s_n = 0; }
+    const uint32_t topk = q->topk;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) { s_known = 0; s_n = 0; }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < stored; i += TOPK_THREADS) {
-        const double w = p.match_w[qoff + i];
-        const uint64_t k = p.match_k[qoff + i];
-        if (complete || match_bucket(q, w, k) >= st.bstar) {
-            const uint32_t pos = atomicAdd(&s_n, 1u);
-            if (pos < p.keep_cap) {
-                sw[pos] = w;
-                sd[pos] = p.match_d[qoff + i];
-                sk[pos] = k;
+    bool complete = false;
+    uint32_t lost = 0;
+
+    if (p.pass == 0) {
+        const uint32_t stored = st.stored < p.match_cap ? st.stored : p.match_cap;
+        const size_t qoff = (size_t)qi * p.match_cap;
+        complete = (st.total == st.stored) && (st.stored <= p.keep_cap); /* every match is here */
+        for (uint32_t i = tid; i < stored; i += TOPK_THREADS) {
+            const double w = p.match_w[qoff + i];
+            const uint64_t k = p.match_k[qoff + i];
+            if (complete || match_bucket(q, w, k) >= st.bstar) {
+                const uint32_t pos = atomicAdd(&s_n, 1u);
+                if (pos < p.keep_cap) { sw[pos] = w; sd[pos] = p.match_d[qoff + i]; sk[pos] = k; }
             }
         }
+        __syncthreads();
+        if (st.stored > p.match_cap || s_n > p.keep_cap) {
+            if (tid == 0) {
+                const uint32_t* hist = p.hist + (size_t)qi * XGM_NBINS;
+                uint32_t cum = 0, b = XGM_NBINS;
+                while (b > 0 && cum < topk) { --b; cum += hist[b]; }
+                if (b < st.bstar) { b = st.bstar; cum = 0; for (uint32_t i = b; i < XGM_NBINS; ++i) cum += hist[i]; }
+                XgmDevResult r;
+                r.n = 0; r.exact = st.total; r.known = 0; r.max_w = __longlong_as_double((long long)st.maxw);
+                r.max_subqs = q->nterms; r.pad = 0;
+                const uint32_t off = atomicAdd(p.work_counter + 5, cum);
+                if (cum >= topk && (uint64_t)off + cum <= (uint64_t)p.pool_total) {
+                    p.qstate[qi].bstar = b;
+                    p.qstate[qi].stored = 0;
+                    p.qstate[qi].pool_off = off;
+                    p.qstate[qi].pool_cap = cum;
+                    p.qstate[qi].rerun = 1;
+                    atomicAdd(p.work_counter + 4, 1u);
+                    r.flags = 4u; /* pending second pass */
+                } else {
+                    r.flags = 1u; /* overflow pool exhausted */
+                }
+                p.out_info[qi] = r;
+            }
+            return;
+        }
+    } else {
+        const uint32_t n_src = st.stored < st.pool_cap ? st.stored : st.pool_cap;
+        if (st.stored != st.pool_cap) lost = 1; /* cannot happen: the histogram count is exact */
+        const double* gw = p.pool_w + st.pool_off;
+        const uint32_t* gd = p.pool_d + st.pool_off;
+        const uint64_t* gk = p.pool_k + st.pool_off;
+        if (n_src <= p.keep_cap) {
+            for (uint32_t i = tid; i < n_src; i += TOPK_THREADS) { sw[i] = gw[i]; sd[i] = gd[i]; sk[i] = gk[i]; }
+            if (tid == 0) s_n = n_src;
+            __syncthreads();
+        } else {
+            /* radix select: find the exact key of the topk-th best match, 8 bits per round */
+            const int nwords = (sort_by == 0 || sort_by == 2) ? 3 : 5;
+            if (tid < 5) s_prefix[tid] = 0;
+            if (tid == 0) s_krem = topk;
+            __syncthreads();
+            for (int round = 0; round < nwords * 4; ++round) {
+                s_hist[tid] = 0; /* TOPK_THREADS == 256 */
+                __syncthreads();
+                const int wi = round >> 2, sh = 24 - 8 * (round & 3);
+                for (uint32_t i = tid; i < n_src; i += TOPK_THREADS) {
+                    uint32_t kw[5];
+                    match_key_words(sort_by, reverse, gw[i], gk[i], gd[i], kw);
+                    bool ok = true;
+                    for (int x = 0; x < wi; ++x) ok = ok && (kw[x] == s_prefix[x]);
+                    if (ok && sh < 24) ok = (kw[wi] >> (sh + 8)) == (s_prefix[wi] >> (sh + 8));
+                    if (ok) atomicAdd(&s_hist[(kw[wi] >> sh) & 255u], 1u);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    uint32_t krem = s_krem, dgt = 255;
+                    for (;; --dgt) {
+                        if (s_hist[dgt] >= krem || dgt == 0) break;
+                        krem -= s_hist[dgt];
+                    }
+                    s_krem = krem;
+                    s_prefix[wi] |= dgt << sh;
+                }
+                __syncthreads();
+            }
+            /* collect everything >= the selected key: exactly topk matches (keys are unique) */
+            for (uint32_t i = tid; i < n_src; i += TOPK_THREADS) {
+                uint32_t kw[5];
+                match_key_words(sort_by, reverse, gw[i], gk[i], gd[i], kw);
+                bool ge = true;
+                for (int x = 0; x < nwords; ++x) {
+                    if (kw[x] != s_prefix[x]) { ge = kw[x] > s_prefix[x]; break; }
+                }
+                if (ge) {
+                    const uint32_t pos = atomicAdd(&s_n, 1u);
+                    if (pos < p.keep_cap) { sw[pos] = gw[i]; sd[pos] = gd[i]; sk[pos] = gk[i]; }
+                }
+            }
+            __syncthreads();
+        }
     }
-    __syncthreads();
+
     const uint32_t kept = s_n;
     const uint32_t n = kept < p.keep_cap ? kept : p.keep_cap;
-    const uint32_t topk = q->topk;
-    if (p.pass == 0 && (st.stored > p.match_cap || kept > p.keep_cap)) {
-        /* Candidates were lost (many warps emitted before b* could rise).  The histogram is complete
-         * for every bin >= the b* in force, so the exact b* (highest bin with >= topk matches at or
-         * above it) is known now: schedule a second pass that stores only those matches. */
-        if (threadIdx.x == 0) {
-            const uint32_t* hist = p.hist + (size_t)qi * XGM_NBINS;
-            uint32_t cum = 0, b = XGM_NBINS;
-            while (b > 0 && cum < topk) { --b; cum += hist[b]; }
-            XgmDevResult r;
-            r.n = 0; r.exact = st.total; r.known = 0; r.max_w = __longlong_as_double((long long)st.maxw);
-            r.max_subqs = q->nterms; r.pad = 0;
-            if (cum >= topk && cum <= p.keep_cap && cum <= p.match_cap && b >= st.bstar) {
-                p.qstate[qi].bstar = b;
-                p.qstate[qi].stored = 0;
-                p.qstate[qi].rerun = 1;
-                atomicAdd(p.work_counter + 4, 1u);
-                r.flags = 4u; /* pending second pass */
-            } else {
-                r.flags = 1u; /* a single bucket holds more ties than the buffers: give up on this query */
-            }
-            p.out_info[qi] = r;
-        }
-        return;
-    }
     const uint32_t free_count = q->check_at_least > topk + 1 ? q->check_at_least : topk + 1;
     uint32_t known = 0;
     const size_t ooff = (size_t)qi * p.out_stride;
-    for (uint32_t i = threadIdx.x; i < n; i += TOPK_THREADS) {
+    for (uint32_t i = tid; i < n; i += TOPK_THREADS) {
         const double wi = sw[i];
         const uint32_t di = sd[i];
         const uint64_t ki = sk[i];
@@ -745,13 +1228,15 @@ __global__ void __launch_bounds__(TOPK_THREADS) xgm_topk_kernel(XgmKernelParams 
     }
     atomicAdd(&s_known, known);
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         XgmDevResult r;
         r.n = n < topk ? n : topk;
         r.exact = st.total;
         r.flags = 0;
-        if (st.stored > p.match_cap || kept > p.keep_cap) r.flags |= 1u; /* lost candidates: result unusable */
-        if (complete) {
+        if (kept > p.keep_cap || lost) r.flags |= 1u;
+        if (topk == 0) {
+            r.known = st.total; /* nothing is ever kept, so min_weight never rises: every match is counted */
+        } else if (complete) {
             r.known = s_known;
         } else {
             /* pruned run: ProtoMSet's count depends on docid-order history we did not keep; report the

@@ -44,7 +44,8 @@ class IndexInfo(C.Structure):
                 ("doclen_lower_bound", C.c_uint32), ("doclen_upper_bound", C.c_uint32),
                 ("nterms", C.c_uint32), ("npostings", C.c_uint64), ("nblocks", C.c_uint64),
                 ("bytes_docids", C.c_uint64), ("bytes_wdfs", C.c_uint64), ("bytes_headers", C.c_uint64),
-                ("bytes_doclen", C.c_uint64), ("device", C.c_int), ("revision", C.c_uint64)]
+                ("bytes_doclen", C.c_uint64), ("device", C.c_int), ("revision", C.c_uint64),
+                ("bytes_bitmaps", C.c_uint64), ("nbitmaps", C.c_uint32)]
 
 
 class TermStats(C.Structure):
