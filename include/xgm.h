@@ -207,6 +207,8 @@ typedef struct xgm_batch_stats {
     float match_kernel_ms;        /* CUDA-event time of the decode+intersect+score kernel(s) */
     float topk_kernel_ms;
     uint64_t h2d_bytes, d2h_bytes; /* bytes the batch moved over PCIe (plan in, results out) */
+    float host_plan_ms;           /* host time inside xgm_search_submit (planning + enqueue) */
+    float host_wait_ms;           /* host time inside xgm_search_wait after the stream drained (result scatter) */
 } xgm_batch_stats;
 xgm_status xgm_search_last_stats(xgm_searcher*, xgm_batch_stats* out);
 

@@ -18,6 +18,7 @@ info = ix.info()
 print(json.dumps(dict(build_s=round(t1 - t0, 2), docs=info.doccount, postings=info.npostings, blocks=info.nblocks,
                       bytes_docids=info.bytes_docids, bytes_wdfs=info.bytes_wdfs, bytes_headers=info.bytes_headers)))
 rng = random.Random(777)
+nq = max(nq, 1)
 queries = [xgm.Query(xgm.OP_AND, [f"T{r:06d}" for r in rng.sample(range(1000), 3)], maxitems=100) for _ in range(nq)]
 batch = xgm.QueryBatch(queries)
 s = xgm.Searcher(ix, max_batch=nq, max_topk=100)
@@ -31,6 +32,7 @@ for it in range(5):
     print(json.dumps(dict(iter=it, e2e_ms=round(dt * 1e3, 3), qps=round(nq / dt), match_ms=round(st.match_kernel_ms, 3),
                           topk_ms=round(st.topk_kernel_ms, 3), items=st.work_items, alg_MB=round(st.algorithmic_bytes / 1e6, 1),
                           alg_GBps=round(st.algorithmic_bytes / 1e6 / max(st.match_kernel_ms, 1e-6), 1), overflow=nover,
+                          plan_ms=round(st.host_plan_ms, 3), wait_ms=round(st.host_wait_ms, 3),
                           mean_hits=float(np.mean([inf[i].exact_matches for i in range(nq)])))))
 # OR 5-term top-1000 (config C3)
 nqo = 200

@@ -35,6 +35,12 @@ def make_edge_index(tmp, seed=3):
     d = np.concatenate([alive[:300], alive[-5:]]).astype(np.uint32)
     terms.append(("m_runs", d, np.ones(len(d), np.uint32)))
     terms.sort(key=lambda t: t[0])
+    # a document's length is the sum of its wdfs (plus terms not modelled here): the reference's
+    # get_maxpart bound (bm25weight.cc:183-207) relies on doclen >= wdf
+    total = np.zeros(lastdocid + 1, np.uint64)
+    for _, d, w in terms:
+        total[d] += w
+    doclen[alive] = (total[alive] + rng.integers(1, 400, size=len(alive)).astype(np.uint64)).astype(np.uint32)
     path = os.path.join(tmp, "edge.flat")
     write_flat(path, doclen, terms)
     return path, [t[0] for t in terms]

@@ -37,9 +37,10 @@ struct XgmKernelParams {
     const XgmDevQuery* queries;
     const XgmWorkItem* items;     /* AND kernel work list */
     const XgmWorkItem* items_or;  /* OR kernel work list */
-    uint32_t nitems, nitems_or;
+    const XgmWorkItem* items_bm;  /* bitmap AND kernel work list */
+    uint32_t nitems, nitems_or, nitems_bm;
     uint32_t nq;
-    uint32_t* work_counter;       /* [0] AND items, [1] OR items, [2],[3] same for the second pass, [4] #queries to re-run, [5] overflow-pool entries reserved */
+    uint32_t* work_counter;       /* [0] AND items, [1] OR items, [2],[3] same for the second pass, [4] #queries to re-run, [5] overflow-pool entries reserved, [6],[7] bitmap-AND items (first / second pass) */
     uint32_t pass;                /* 0 = first pass, 1 = re-run of overflowed queries with their exact b* */
     XgmQState* qstate;            /* [nq] */
     uint32_t* hist;               /* [nq][XGM_NBINS] */
@@ -65,6 +66,8 @@ struct XgmKernelParams {
 cudaError_t xgm_launch_and(const XgmKernelParams& p, int grid, cudaStream_t s);
 cudaError_t xgm_launch_and2(const XgmKernelParams& p, int grid, cudaStream_t s);
 int xgm_and2_occupancy_blocks_per_sm();
+cudaError_t xgm_launch_and_bm(const XgmKernelParams& p, int grid, cudaStream_t s);
+int xgm_and_bm_occupancy_blocks_per_sm();
 cudaError_t xgm_launch_or(const XgmKernelParams& p, int grid, cudaStream_t s);
 int xgm_or_occupancy_blocks_per_sm();
 cudaError_t xgm_launch_topk(const XgmKernelParams& p, uint32_t nq, cudaStream_t s);

@@ -47,6 +47,7 @@ struct XgmDevTerm {
     double termweight;    /* BM25Weight::init result, bm25weight.cc:46-130 (computed on the host) */
     uint64_t bm_off;      /* membership bitmap of the term (u32 words into bitmaps[]), XGM_NO_BITMAP if none */
     uint64_t rk_off;      /* its rank directory (u32 entries into ranks[]): postings before each 256-docid group */
+    double maxpart;       /* BM25Weight::get_maxpart: upper bound of the term's contribution (MaxScore pruning) */
 };
 
 struct XgmDevQuery {

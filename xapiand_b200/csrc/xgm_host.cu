@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -693,17 +694,19 @@ struct xgm_searcher {
     XgmDevQuery* h_queries = nullptr;
     XgmWorkItem* h_items = nullptr;
     XgmWorkItem* h_items_or = nullptr;
+    XgmWorkItem* h_items_bm = nullptr;
     double* h_out_w = nullptr;
     uint32_t* h_out_d = nullptr;
     uint64_t* h_out_k = nullptr;
     XgmDevResult* h_info = nullptr;
-    size_t items_cap = 0, items_or_cap = 0;
+    size_t items_cap = 0, items_or_cap = 0, items_bm_cap = 0;
     uint32_t keep_cap = 0;
     size_t ctrl_bytes = 0;
     /* device */
     XgmDevQuery* d_queries = nullptr;
     XgmWorkItem* d_items = nullptr;
     XgmWorkItem* d_items_or = nullptr;
+    XgmWorkItem* d_items_bm = nullptr;
     unsigned char* d_ctrl = nullptr; /* [16 B work counters][nq x XgmQState][nq x XGM_NBINS x u32] */
     double* d_match_w = nullptr;
     uint32_t* d_match_d = nullptr;
@@ -718,10 +721,10 @@ struct xgm_searcher {
     XgmDevResult* d_info = nullptr;
     /* last batch */
     std::vector<PlannedQuery> plan;
-    uint32_t nq = 0, nitems = 0, nitems_or = 0;
+    uint32_t nq = 0, nitems = 0, nitems_or = 0, nitems_bm = 0;
     bool pending = false, any_sort = false;
     xgm_batch_stats stats{};
-    int grid = 0, grid_or = 0, grid_and2 = 0;
+    int grid = 0, grid_or = 0, grid_and2 = 0, grid_bm = 0;
     int and_version = 1; /* 1 = warp-autonomous kernel, 2 = chunked CTA kernel (XGM_AND_KERNEL env) */
     XgmKernelParams params;
 };
@@ -730,9 +733,9 @@ extern "C" void xgm_searcher_free(xgm_searcher* s) {
     if (!s) return;
     cudaSetDevice(s->ix->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    cudaFreeHost(s->h_queries); cudaFreeHost(s->h_items); cudaFreeHost(s->h_items_or); cudaFreeHost(s->h_out_w); cudaFreeHost(s->h_out_d);
+    cudaFreeHost(s->h_queries); cudaFreeHost(s->h_items); cudaFreeHost(s->h_items_or); cudaFreeHost(s->h_items_bm); cudaFreeHost(s->h_out_w); cudaFreeHost(s->h_out_d);
     cudaFreeHost(s->h_out_k); cudaFreeHost(s->h_info);
-    cudaFree(s->d_queries); cudaFree(s->d_items); cudaFree(s->d_items_or); cudaFree(s->d_ctrl); cudaFree(s->d_match_w); cudaFree(s->d_match_d);
+    cudaFree(s->d_queries); cudaFree(s->d_items); cudaFree(s->d_items_or); cudaFree(s->d_items_bm); cudaFree(s->d_ctrl); cudaFree(s->d_match_w); cudaFree(s->d_match_d);
     cudaFree(s->d_match_k); cudaFree(s->d_pool_w); cudaFree(s->d_pool_d); cudaFree(s->d_pool_k); cudaFree(s->d_out_w); cudaFree(s->d_out_d); cudaFree(s->d_out_k); cudaFree(s->d_info);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -741,10 +744,10 @@ extern "C" void xgm_searcher_free(xgm_searcher* s) {
     delete s;
 }
 
-static xgm_status ensure_items(xgm_searcher* s, size_t need, bool is_or) {
-    size_t& have = is_or ? s->items_or_cap : s->items_cap;
-    XgmWorkItem*& h = is_or ? s->h_items_or : s->h_items;
-    XgmWorkItem*& d = is_or ? s->d_items_or : s->d_items;
+static xgm_status ensure_items(xgm_searcher* s, size_t need, int which) {
+    size_t& have = which == 1 ? s->items_or_cap : which == 2 ? s->items_bm_cap : s->items_cap;
+    XgmWorkItem*& h = which == 1 ? s->h_items_or : which == 2 ? s->h_items_bm : s->h_items;
+    XgmWorkItem*& d = which == 1 ? s->d_items_or : which == 2 ? s->d_items_bm : s->d_items;
     if (need <= have) return XGM_OK;
     size_t cap = std::max<size_t>(need * 2, 4096);
     CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -775,7 +778,7 @@ extern "C" xgm_status xgm_searcher_new(const xgm_index* ix, uint32_t max_batch, 
     CUDA_TRY(cudaMallocHost(&s->h_out_w, ns * 8)); CUDA_TRY(cudaMallocHost(&s->h_out_d, ns * 4));
     CUDA_TRY(cudaMallocHost(&s->h_out_k, ns * 8)); CUDA_TRY(cudaMallocHost(&s->h_info, nq * sizeof(XgmDevResult)));
     CUDA_TRY(cudaMalloc(&s->d_queries, nq * sizeof(XgmDevQuery)));
-    s->ctrl_bytes = 32 + nq * sizeof(XgmQState) + nq * XGM_NBINS * 4;
+    s->ctrl_bytes = 64 + nq * sizeof(XgmQState) + nq * XGM_NBINS * 4;
     CUDA_TRY(cudaMalloc(&s->d_ctrl, s->ctrl_bytes));
     CUDA_TRY(cudaMalloc(&s->d_match_w, nm * 8)); CUDA_TRY(cudaMalloc(&s->d_match_d, nm * 4)); CUDA_TRY(cudaMalloc(&s->d_match_k, nm * 8));
     CUDA_TRY(cudaMalloc(&s->d_out_w, ns * 8)); CUDA_TRY(cudaMalloc(&s->d_out_d, ns * 4)); CUDA_TRY(cudaMalloc(&s->d_out_k, ns * 8));
@@ -785,9 +788,11 @@ extern "C" xgm_status xgm_searcher_new(const xgm_index* ix, uint32_t max_batch, 
     CUDA_TRY(cudaMalloc(&s->d_pool_w, (size_t)s->pool_total * 8)); CUDA_TRY(cudaMalloc(&s->d_pool_d, (size_t)s->pool_total * 4));
     CUDA_TRY(cudaMalloc(&s->d_pool_k, (size_t)s->pool_total * 8));
     CUDA_TRY(cudaMalloc(&s->d_info, nq * sizeof(XgmDevResult)));
-    xgm_status st = ensure_items(s.get(), 4096, false);
+    xgm_status st = ensure_items(s.get(), 4096, 0);
     if (st != XGM_OK) return st;
-    st = ensure_items(s.get(), 4096, true);
+    st = ensure_items(s.get(), 4096, 1);
+    if (st != XGM_OK) return st;
+    st = ensure_items(s.get(), 4096, 2);
     if (st != XGM_OK) return st;
     int occ = xgm_and_occupancy_blocks_per_sm();
     if (occ < 1) occ = 1;
@@ -795,6 +800,9 @@ extern "C" xgm_status xgm_searcher_new(const xgm_index* ix, uint32_t max_batch, 
     occ = xgm_or_occupancy_blocks_per_sm();
     if (occ < 1) occ = 1;
     s->grid_or = ix->sm_count * occ;
+    occ = xgm_and_bm_occupancy_blocks_per_sm();
+    if (occ < 1) occ = 1;
+    s->grid_bm = ix->sm_count * occ;
     occ = xgm_and2_occupancy_blocks_per_sm();
     if (occ < 1) occ = 1;
     s->grid_and2 = ix->sm_count * occ;
@@ -884,7 +892,7 @@ static double bm25_maxpart(double termweight, double len_factor, double k1, doub
 
 static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, PlannedQuery& pq, XgmDevQuery& dq,
                              std::vector<XgmWorkItem>& items, std::vector<XgmWorkItem>& items_or,
-                             uint32_t blocks_per_item) {
+                             std::vector<XgmWorkItem>& items_bm, uint32_t blocks_per_item) {
     const xgm_index* ix = s->ix;
     pq = PlannedQuery();
     memset(&dq, 0, sizeof(dq));
@@ -969,6 +977,7 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
         for (uint32_t i = 0; i < n; ++i) {
             uint32_t j = order[i];
             dq.terms[i].termweight = tw[j];
+            dq.terms[i].maxpart = maxpart[j];
             dq.terms[i].bm_off = XGM_NO_BITMAP;
             if (ids[j] != 0xffffffffu) {
                 const TermInfo& tinf = ix->terms[ids[j]];
@@ -1020,6 +1029,7 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
         for (uint32_t i = 0; i < n; ++i) {
             uint32_t j = order[i];
             dq.terms[i].termweight = tw[j];
+            dq.terms[i].maxpart = maxpart[j];
             dq.terms[i].bm_off = XGM_NO_BITMAP;
             if (ids[j] != 0xffffffffu) {
                 const TermInfo& tinf = ix->terms[ids[j]];
@@ -1048,11 +1058,15 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
     if (dq.route == 0 && any_absent) { pq.on_device = false; return XGM_OK; } /* AND with an absent term: empty */
     pq.on_device = true;
     if (dq.route == 0) {
+        /* every list but the driver has a membership bitmap → lean bitmap kernel */
+        bool all_bm = n >= 2 && s->and_version == 1;
+        for (uint32_t i = 1; i < n; ++i) all_bm = all_bm && dq.terms[i].bm_off != XGM_NO_BITMAP;
+        std::vector<XgmWorkItem>& dst = all_bm ? items_bm : items;
         uint32_t nb = dq.terms[0].nblocks;
         for (uint32_t b0 = 0; b0 < nb; b0 += blocks_per_item) {
             XgmWorkItem wi;
             wi.query = qi; wi.b0 = b0; wi.b1 = std::min(nb, b0 + blocks_per_item); wi.pad = 0;
-            items.push_back(wi);
+            dst.push_back(wi);
         }
     } else {
         for (uint32_t leaf = 0; leaf < n; ++leaf) {
@@ -1069,7 +1083,7 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
 
 static xgm_status launch_batch(xgm_searcher* s) {
     XgmKernelParams& p = s->params;
-    CUDA_TRY(cudaMemsetAsync(s->d_ctrl, 0, 32 + (size_t)s->max_batch * sizeof(XgmQState), s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->d_ctrl, 0, 64 + (size_t)s->max_batch * sizeof(XgmQState), s->stream));
     CUDA_TRY(cudaMemsetAsync(p.hist, 0, (size_t)s->nq * XGM_NBINS * 4, s->stream));
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
     s->stats.kernel_launches = 0;
@@ -1077,6 +1091,7 @@ static xgm_status launch_batch(xgm_searcher* s) {
     auto launch_and = [&](const XgmKernelParams& pp) {
         return s->and_version == 1 ? xgm_launch_and(pp, s->grid, s->stream) : xgm_launch_and2(pp, s->grid_and2, s->stream);
     };
+    if (s->nitems_bm) { CUDA_TRY(xgm_launch_and_bm(p, s->grid_bm, s->stream)); s->stats.kernel_launches++; }
     if (s->nitems) { CUDA_TRY(launch_and(p)); s->stats.kernel_launches++; }
     if (s->nitems_or) { CUDA_TRY(xgm_launch_or(p, s->grid_or, s->stream)); s->stats.kernel_launches++; }
     CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
@@ -1085,6 +1100,7 @@ static xgm_status launch_batch(xgm_searcher* s) {
     /* second pass: only queries whose candidate buffer overflowed do any work (device-side flag) */
     XgmKernelParams p2 = p;
     p2.pass = 1;
+    if (s->nitems_bm) { CUDA_TRY(xgm_launch_and_bm(p2, s->grid_bm, s->stream)); s->stats.kernel_launches++; }
     if (s->nitems) { CUDA_TRY(launch_and(p2)); s->stats.kernel_launches++; }
     if (s->nitems_or) { CUDA_TRY(xgm_launch_or(p2, s->grid_or, s->stream)); s->stats.kernel_launches++; }
     CUDA_TRY(xgm_launch_topk(p2, s->nq, s->stream));
@@ -1097,12 +1113,13 @@ extern "C" xgm_status xgm_search_submit(xgm_searcher* s, const xgm_query* querie
     if (!s || !queries || nq == 0) return fail(XGM_E_INVALID, "bad arguments");
     if (nq > s->max_batch) return fail(XGM_E_INVALID, "batch %u > max_batch %u", nq, s->max_batch);
     if (s->pending) return fail(XGM_E_INVALID, "previous batch not waited for");
+    const auto t_submit0 = std::chrono::steady_clock::now();
     CUDA_TRY(cudaSetDevice(s->ix->device));
     s->plan.resize(nq);
     s->nq = nq;
     /* work granularity: enough items to balance ~grid*8 warps, at most 32 driver blocks per item */
     uint64_t total_drv_blocks = 0;
-    std::vector<XgmWorkItem> items, items_or;
+    std::vector<XgmWorkItem> items, items_or, items_bm;
     items.reserve(4096);
     /* first pass with a provisional granularity needs the driver block counts; plan twice is wasteful,
      * so use a fixed small granularity scaled by batch size */
@@ -1110,17 +1127,51 @@ extern "C" xgm_status xgm_search_submit(xgm_searcher* s, const xgm_query* querie
     if (s->and_version == 2) bpi = nq >= 64 ? 16 : (nq >= 8 ? 8 : 4);
     s->any_sort = false;
     uint64_t alg = 0, postings = 0;
+    /* Planning (term lookup, Weight::init_, evaluation order, work items) is independent per query:
+     * large batches are planned by a few host threads, each into its own work lists. */
+    int T = 1;
+    if (nq >= 512) {
+        T = std::min(default_threads(), 8);
+        if (const char* e = getenv("XGM_HOST_THREADS")) T = std::max(1, atoi(e));
+    }
+    if (T <= 1) {
+        for (uint32_t i = 0; i < nq; ++i) {
+            xgm_status st = plan_query(s, queries[i], i, s->plan[i], s->h_queries[i], items, items_or, items_bm, bpi);
+            if (st != XGM_OK) return st;
+        }
+    } else {
+        std::vector<std::vector<XgmWorkItem>> ti(T), tio(T), tib(T);
+        std::vector<xgm_status> tst(T, XGM_OK);
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t)
+            th.emplace_back([&, t]() {
+                uint32_t a = (uint32_t)((uint64_t)nq * t / T), b = (uint32_t)((uint64_t)nq * (t + 1) / T);
+                tib[t].reserve((size_t)(b - a) * 40);
+                for (uint32_t i = a; i < b; ++i) {
+                    xgm_status st = plan_query(s, queries[i], i, s->plan[i], s->h_queries[i], ti[t], tio[t], tib[t], bpi);
+                    if (st != XGM_OK) { tst[t] = st; return; }
+                }
+            });
+        for (auto& x : th) x.join();
+        for (int t = 0; t < T; ++t) {
+            if (tst[t] != XGM_OK) return fail(tst[t], "query planning failed");
+            items.insert(items.end(), ti[t].begin(), ti[t].end());
+            items_or.insert(items_or.end(), tio[t].begin(), tio[t].end());
+            items_bm.insert(items_bm.end(), tib[t].begin(), tib[t].end());
+        }
+    }
+    const auto t_planned = std::chrono::steady_clock::now();
     for (uint32_t i = 0; i < nq; ++i) {
-        xgm_status st = plan_query(s, queries[i], i, s->plan[i], s->h_queries[i], items, items_or, bpi);
-        if (st != XGM_OK) return st;
         if (s->plan[i].sort_by || s->h_queries[i].route == 1) s->any_sort = true; /* keys/aux needed on the host */
         alg += s->plan[i].alg_bytes;
         total_drv_blocks += s->h_queries[i].terms[0].nblocks;
     }
     (void)total_drv_blocks; (void)postings;
-    xgm_status st = ensure_items(s, items.size(), false);
+    xgm_status st = ensure_items(s, items.size(), 0);
     if (st != XGM_OK) return st;
-    st = ensure_items(s, items_or.size(), true);
+    st = ensure_items(s, items_or.size(), 1);
+    if (st != XGM_OK) return st;
+    st = ensure_items(s, items_bm.size(), 2);
     if (st != XGM_OK) return st;
     /* Interleave the work lists across queries (all queries' first item, then all second items, ...):
      * the warps in flight at any moment then belong to many queries, so each query's pruning threshold
@@ -1137,20 +1188,24 @@ extern "C" xgm_status xgm_search_submit(xgm_searcher* s, const xgm_query* querie
     };
     interleave(items, s->h_items);
     interleave(items_or, s->h_items_or);
+    interleave(items_bm, s->h_items_bm);
+    const auto t_interleaved = std::chrono::steady_clock::now();
     s->nitems = (uint32_t)items.size();
     s->nitems_or = (uint32_t)items_or.size();
+    s->nitems_bm = (uint32_t)items_bm.size();
     s->stats = xgm_batch_stats{};
     s->stats.algorithmic_bytes = alg;
-    s->stats.work_items = s->nitems + s->nitems_or;
-    s->stats.h2d_bytes = (uint64_t)nq * sizeof(XgmDevQuery) + (uint64_t)(s->nitems + s->nitems_or) * sizeof(XgmWorkItem);
+    s->stats.work_items = s->nitems + s->nitems_or + s->nitems_bm;
+    s->stats.h2d_bytes = (uint64_t)nq * sizeof(XgmDevQuery) + (uint64_t)(s->nitems + s->nitems_or + s->nitems_bm) * sizeof(XgmWorkItem);
     s->stats.d2h_bytes = (uint64_t)nq * sizeof(XgmDevResult) + (uint64_t)nq * s->max_topk * (8 + 4 + (s->any_sort ? 8 : 0));
     XgmKernelParams& p = s->params;
     fill_index_params(s->ix, p);
     p.queries = s->d_queries; p.items = s->d_items; p.nitems = s->nitems; p.nq = nq;
     p.items_or = s->d_items_or; p.nitems_or = s->nitems_or;
+    p.items_bm = s->d_items_bm; p.nitems_bm = s->nitems_bm;
     p.work_counter = reinterpret_cast<uint32_t*>(s->d_ctrl);
-    p.qstate = reinterpret_cast<XgmQState*>(s->d_ctrl + 32);
-    p.hist = reinterpret_cast<uint32_t*>(s->d_ctrl + 32 + (size_t)s->max_batch * sizeof(XgmQState));
+    p.qstate = reinterpret_cast<XgmQState*>(s->d_ctrl + 64);
+    p.hist = reinterpret_cast<uint32_t*>(s->d_ctrl + 64 + (size_t)s->max_batch * sizeof(XgmQState));
     p.match_cap = s->match_cap; p.keep_cap = s->keep_cap;
     p.pool_total = s->pool_total; p.pool_w = s->d_pool_w; p.pool_d = s->d_pool_d; p.pool_k = s->d_pool_k;
     p.match_w = s->d_match_w; p.match_d = s->d_match_d; p.match_k = s->d_match_k;
@@ -1160,6 +1215,8 @@ extern "C" xgm_status xgm_search_submit(xgm_searcher* s, const xgm_query* querie
         CUDA_TRY(cudaMemcpyAsync(s->d_items, s->h_items, (size_t)s->nitems * sizeof(XgmWorkItem), cudaMemcpyHostToDevice, s->stream));
     if (s->nitems_or)
         CUDA_TRY(cudaMemcpyAsync(s->d_items_or, s->h_items_or, (size_t)s->nitems_or * sizeof(XgmWorkItem), cudaMemcpyHostToDevice, s->stream));
+    if (s->nitems_bm)
+        CUDA_TRY(cudaMemcpyAsync(s->d_items_bm, s->h_items_bm, (size_t)s->nitems_bm * sizeof(XgmWorkItem), cudaMemcpyHostToDevice, s->stream));
     st = launch_batch(s);
     if (st != XGM_OK) return st;
     size_t ns = (size_t)nq * s->max_topk;
@@ -1168,6 +1225,13 @@ extern "C" xgm_status xgm_search_submit(xgm_searcher* s, const xgm_query* querie
     CUDA_TRY(cudaMemcpyAsync(s->h_out_d, s->d_out_d, ns * 4, cudaMemcpyDeviceToHost, s->stream));
     if (s->any_sort) CUDA_TRY(cudaMemcpyAsync(s->h_out_k, s->d_out_k, ns * 8, cudaMemcpyDeviceToHost, s->stream));
     s->pending = true;
+    s->stats.host_plan_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_submit0).count();
+    if (getenv("XGM_DEBUG_TIMING"))
+        fprintf(stderr, "xgm submit: plan %.3f ms, interleave %.3f ms, enqueue %.3f ms (T=%d, items %zu)\n",
+                std::chrono::duration<float, std::milli>(t_planned - t_submit0).count(),
+                std::chrono::duration<float, std::milli>(t_interleaved - t_planned).count(),
+                std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_interleaved).count(), T,
+                items.size() + items_or.size() + items_bm.size());
     return XGM_OK;
 }
 
@@ -1224,6 +1288,7 @@ extern "C" xgm_status xgm_search_wait(xgm_searcher* s, uint32_t* docids, double*
     if (e != cudaSuccess) return fail(XGM_E_CUDA, "batch failed: %s", cudaGetErrorString(e));
     cudaEventElapsedTime(&s->stats.match_kernel_ms, s->ev0, s->ev1);
     cudaEventElapsedTime(&s->stats.topk_kernel_ms, s->ev1, s->ev2);
+    const auto t_wait0 = std::chrono::steady_clock::now();
     for (uint32_t i = 0; i < s->nq; ++i) {
         const PlannedQuery& pq = s->plan[i];
         const size_t off = (size_t)i * s->max_topk;
@@ -1238,6 +1303,7 @@ extern "C" xgm_status xgm_search_wait(xgm_searcher* s, uint32_t* docids, double*
             if (sort_keys && pq.sort_by) memcpy(sort_keys + (size_t)i * stride, s->h_out_k + off + pq.first, (size_t)n * 8);
         }
     }
+    s->stats.host_wait_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_wait0).count();
     return XGM_OK;
 }
 

@@ -221,7 +221,7 @@ __device__ __forceinline__ uint32_t match_bucket(const XgmDevQuery* q, double w,
 __device__ __noinline__ void emit_matches_impl(const XgmKernelParams& p, const XgmDevQuery* q, uint32_t qi, uint32_t lane,
                                               uint32_t alive, double a0, double a1, double a2, double a3, uint32_t c0,
                                               uint32_t c1, uint32_t c2, uint32_t c3, uint32_t x0, uint32_t x1,
-                                              uint32_t x2, uint32_t x3) {
+                                              uint32_t x2, uint32_t x3, uint32_t count_only) {
     const double acc[4] = {a0, a1, a2, a3};
     const uint32_t c[4] = {c0, c1, c2, c3};
     const uint32_t aux[4] = {x0, x1, x2, x3};
@@ -248,7 +248,7 @@ __device__ __noinline__ void emit_matches_impl(const XgmKernelParams& p, const X
         if (alive >> k & 1u) {
             if (q->sort_by != 0) key[k] = doc_sort_key(p, q, c[k]);
             bkt[k] = match_bucket(q, acc[k], key[k]);
-            if (bkt[k] >= bstar && q->topk != 0) keep |= 1u << k;
+            if (bkt[k] >= bstar && q->topk != 0 && !(count_only >> k & 1u)) keep |= 1u << k;
         }
     }
     const uint32_t n = __popc(keep);
@@ -302,7 +302,9 @@ __device__ __noinline__ void emit_matches_impl(const XgmKernelParams& p, const X
     }
     /* raise b* whenever the stored count crosses a multiple of 256 (and topk matches exist) */
     const uint32_t after = base + nkeep;
-    if (p.pass == 0 && (base >> 8) != (after >> 8) && after >= q->topk) {
+    /* (not before half of what the top-k kernel can rank is in use: small match sets stay unpruned, so
+     * their known_matching_docs is reproduced exactly) */
+    if (p.pass == 0 && (base >> 8) != (after >> 8) && after >= q->topk && after >= p.keep_cap / 2) {
         __threadfence();
         const volatile uint32_t* vh = hist;
         uint32_t mine = 0;
@@ -330,12 +332,14 @@ __device__ __noinline__ void emit_matches_impl(const XgmKernelParams& p, const X
     }
 }
 
+/* count_only: matches already proven unable to reach the top-k (MaxScore bound below b*): they are
+ * counted in the exact match total but neither scored nor stored */
 __device__ __forceinline__ void emit_matches(const XgmKernelParams& p, const XgmDevQuery* q, uint32_t qi, uint32_t lane,
                                              uint32_t alive, const double acc[4], const uint32_t c[4],
-                                             const uint32_t aux[4]) {
+                                             const uint32_t aux[4], uint32_t count_only = 0) {
     if (!__any_sync(FULL, alive != 0)) return;
     emit_matches_impl(p, q, qi, lane, alive, acc[0], acc[1], acc[2], acc[3], c[0], c[1], c[2], c[3], aux[0], aux[1],
-                      aux[2], aux[3]);
+                      aux[2], aux[3], count_only);
 }
 
 /* ------------------------------------------------------------------ shared per-warp scratch */
@@ -346,6 +350,8 @@ struct __align__(16) WarpScratch {
     uint32_t stage[STAGE_WORDS];      /* packed words of the block being probed */
     uint32_t dstage[2][STAGE_WORDS];  /* double-buffered packed docids of the driver list */
     uint32_t dbuf[XGM_BLOCK];         /* decoded docids of the probed block */
+    uint32_t qdid[160];               /* bitmap fast path: queue of candidates confirmed by the second list */
+    uint32_t qsrc[160];               /*   (driver block - b0) << 7 | position, for the lazy wdf fetch */
     uint64_t bar;                     /* completion barrier of `stage` */
     uint64_t dbar[2];                 /* completion barriers of `dstage` */
     uint64_t pad;
@@ -417,6 +423,23 @@ __device__ __forceinline__ uint32_t probe_list(const XgmKernelParams& p, const X
     return cur;
 }
 
+/* Index of docid d in the posting list of a term that has a membership bitmap (d must be a member):
+ * postings before its 256-docid group (rank directory) + set bits before it inside the group. */
+__device__ __forceinline__ uint32_t bitmap_rank(const XgmKernelParams& p, const XgmDevTerm& t, uint32_t d) {
+    const uint32_t* __restrict__ bm = p.bitmaps + t.bm_off;
+    const uint32_t g = d >> 8, wsel = (d >> 5) & 7u;
+    uint32_t r = __ldg(p.ranks + t.rk_off + g);
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(bm + g * 8));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(bm + g * 8 + 4));
+    const uint32_t ww[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (uint32_t x = 0; x < 8; ++x) {
+        if (x < wsel) r += __popc(ww[x]);
+        else if (x == wsel) r += __popc(ww[x] & ((1u << (d & 31)) - 1u));
+    }
+    return r;
+}
+
 /* ------------------------------------------------------------------ sparse AND kernel */
 
 __global__ void __launch_bounds__(MATCH_WARPS * 32, 3) xgm_and_kernel(XgmKernelParams p) {
@@ -448,6 +471,41 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 3) xgm_and_kernel(XgmKernelP
         const uint32_t drv_begin = __shfl_sync(FULL, my_begin, 0);
         const double tw0 = q->terms[0].termweight;
 
+        /* Fast path when every other list has a membership bitmap: the intersection is a word load per
+         * candidate; candidates confirmed by the second list are queued and finished 32 at a time (one
+         * per lane) so that the rank / wdf / BM25 work of the few survivors runs on full warps. */
+        bool fast = nterms >= 2;
+        for (uint32_t j = 1; j < nterms; ++j) fast = fast && (q->terms[j].bm_off != XGM_NO_BITMAP);
+        uint32_t qn = 0;
+        auto flush = [&](uint32_t from, uint32_t count) {
+            uint32_t alive = lane < count ? 1u : 0u;
+            const uint32_t d = alive ? ws.qdid[from + lane] : 0u;
+            const uint32_t src = alive ? ws.qsrc[from + lane] : 0u;
+            for (uint32_t j = 2; j < nterms && __any_sync(FULL, alive); ++j) {
+                if (alive) {
+                    const uint32_t w = __ldg(p.bitmaps + q->terms[j].bm_off + (d >> 5));
+                    if (!(w >> (d & 31) & 1u)) alive = 0u;
+                }
+            }
+            if (alive && q->filter && !doc_passes_filter(p, q, d)) alive = 0u;
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            if (alive) {
+                const uint32_t dlen = __ldg(&p.doclen[d]);
+                const XgmBlockHdr h0 = hdr[drv_begin + wi.b0 + (src >> 7)];
+                acc[0] = bm25_sumpart(tw0, q, unpack_gl(p.tfs, h0.tf_off, src & 127u, XGM_HDR_TF_BITS(h0.meta)), dlen);
+                for (uint32_t j = 1; j < nterms; ++j) {
+                    const uint32_t r = bitmap_rank(p, q->terms[j], d);
+                    const XgmBlockHdr bh = hdr[q->terms[j].blk_begin + (r >> 7)];
+                    const uint32_t tfj = unpack_gl(p.tfs, bh.tf_off, r & 127u, XGM_HDR_TF_BITS(bh.meta));
+                    /* MultiAndPostList::get_weight: result += plist[i]->get_weight(), in plist order */
+                    acc[0] = __dadd_rn(acc[0], bm25_sumpart(q->terms[j].termweight, q, tfj, dlen));
+                }
+            }
+            const uint32_t cc[4] = {d, 0u, 0u, 0u};
+            const uint32_t aux[4] = {nterms, nterms, nterms, nterms};
+            emit_matches(p, q, wi.query, lane, alive, acc, cc, aux);
+        };
+
         /* software pipeline over the driver list: block db+1 is in flight while db is intersected */
         XgmBlockHdr dh = hdr[drv_begin + wi.b0];
         __syncwarp();
@@ -472,6 +530,45 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 3) xgm_and_kernel(XgmKernelP
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 if (4 * lane + k < dcount) alive |= 1u << k;
+
+            if (fast) {
+                const uint32_t* __restrict__ bm1 = p.bitmaps + q->terms[1].bm_off;
+                uint32_t w[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) w[k] = (alive >> k & 1u) ? __ldg(bm1 + (c[k] >> 5)) : 0u;
+                uint32_t surv = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if ((alive >> k & 1u) && (w[k] >> (c[k] & 31) & 1u)) surv |= 1u << k;
+                if (__any_sync(FULL, surv != 0)) {
+                    const uint32_t n = __popc(surv);
+                    uint32_t incl = n;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(FULL, incl, o);
+                        if ((int)lane >= o) incl += t;
+                    }
+                    uint32_t slot = qn + incl - n;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (surv >> k & 1u) {
+                            ws.qdid[slot] = c[k];
+                            ws.qsrc[slot] = ((db - wi.b0) << 7) | (4 * lane + k);
+                            ++slot;
+                        }
+                    qn += __shfl_sync(FULL, incl, 31);
+                    __syncwarp();
+                    while (qn >= 32) {
+                        qn -= 32;
+                        flush(qn, 32);
+                        __syncwarp();
+                    }
+                }
+                dh = nh;
+                buf ^= 1u;
+                continue;
+            }
+
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
             uint32_t dl[4] = {0, 0, 0, 0};
 
@@ -557,9 +654,180 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 3) xgm_and_kernel(XgmKernelP
             dh = nh;
             buf ^= 1u;
         }
+        if (fast && qn) {
+            flush(0, qn);
+            __syncwarp();
+        }
     }
 }
 
+
+/* ------------------------------------------------------------------ bitmap AND kernel */
+
+/* AND of a driver list with lists that all have membership bitmaps — the common case once HBM is used
+ * for bitmaps of the frequent terms.  Warp-autonomous like xgm_and_kernel, but stripped to the fast
+ * path so that more warps fit an SM (the kernel is bound by DRAM latency of the bitmap probes): per
+ * iteration a warp decodes TWO driver blocks (bulk copies of the next pair already in flight), issues
+ * the 8 bitmap word loads of every lane together, queues the candidates confirmed by the second list
+ * and finishes them 32 at a time, one per lane (remaining bitmaps, rank → wdf, doc length, BM25 in
+ * MultiAndPostList order, emission). */
+#define BM_WARPS 8
+#define BM_QCAP 288
+
+struct __align__(16) BmScratch {
+    uint32_t dstage[4][STAGE_WORDS];
+    uint32_t qdid[BM_QCAP];
+    uint32_t qsrc[BM_QCAP];
+    uint64_t dbar[4];
+};
+
+__global__ void __launch_bounds__(BM_WARPS * 32, 4) xgm_and_bm_kernel(XgmKernelParams p) {
+    __shared__ BmScratch scratch[BM_WARPS];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    BmScratch& ws = scratch[warp];
+    if (lane < 4) mbar_init(&ws.dbar[lane], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    uint32_t phases = 0;
+    const XgmBlockHdr* __restrict__ hdr = p.hdr;
+    if (p.pass != 0 && *reinterpret_cast<volatile uint32_t*>(p.work_counter + 4) == 0) return;
+
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(p.work_counter + 6 + p.pass, 1u);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= p.nitems_bm) break;
+        const XgmWorkItem wi = p.items_bm[item];
+        if (p.pass != 0 && p.qstate[wi.query].rerun == 0) continue;
+        const XgmDevQuery* q = &p.queries[wi.query];
+        const uint32_t nterms = q->nterms;
+        const uint32_t drv_begin = q->terms[0].blk_begin;
+        const uint32_t* __restrict__ bm1 = p.bitmaps + q->terms[1].bm_off;
+        uint32_t qn = 0;
+
+        auto flush = [&](uint32_t from, uint32_t count) {
+            uint32_t alive = lane < count ? 1u : 0u;
+            const uint32_t d = alive ? ws.qdid[from + lane] : 0u;
+            const uint32_t src = alive ? ws.qsrc[from + lane] : 0u;
+            for (uint32_t j = 2; j < nterms && __any_sync(FULL, alive); ++j) {
+                if (alive) {
+                    const uint32_t w = __ldg(p.bitmaps + q->terms[j].bm_off + (d >> 5));
+                    if (!(w >> (d & 31) & 1u)) alive = 0u;
+                }
+            }
+            if (alive && q->filter && !doc_passes_filter(p, q, d)) alive = 0u;
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            if (alive) {
+                const uint32_t dlen = __ldg(&p.doclen[d]);
+                const XgmBlockHdr h0 = hdr[drv_begin + wi.b0 + (src >> 7)];
+                acc[0] = bm25_sumpart(q->terms[0].termweight, q,
+                                      unpack_gl(p.tfs, h0.tf_off, src & 127u, XGM_HDR_TF_BITS(h0.meta)), dlen);
+                for (uint32_t j = 1; j < nterms; ++j) {
+                    const uint32_t r = bitmap_rank(p, q->terms[j], d);
+                    const XgmBlockHdr bh = hdr[q->terms[j].blk_begin + (r >> 7)];
+                    const uint32_t tfj = unpack_gl(p.tfs, bh.tf_off, r & 127u, XGM_HDR_TF_BITS(bh.meta));
+                    /* MultiAndPostList::get_weight: result += plist[i]->get_weight(), in plist order */
+                    acc[0] = __dadd_rn(acc[0], bm25_sumpart(q->terms[j].termweight, q, tfj, dlen));
+                }
+            }
+            const uint32_t cc[4] = {d, 0u, 0u, 0u};
+            const uint32_t aux[4] = {nterms, nterms, nterms, nterms};
+            emit_matches(p, q, wi.query, lane, alive, acc, cc, aux);
+        };
+        auto issue = [&](uint32_t b, uint32_t blk) { /* stage driver block blk into buffer b */
+            const XgmBlockHdr h = hdr[drv_begin + blk];
+            const uint32_t bits = XGM_HDR_DOC_BITS(h.meta);
+            __syncwarp();
+            if (bits != 0 && lane == 0) {
+                mbar_expect_tx(&ws.dbar[b], bits * 16u);
+                bulk_g2s(ws.dstage[b], p.docs + h.doc_off, bits * 16u, &ws.dbar[b]);
+            }
+            return h;
+        };
+
+        XgmBlockHdr h0 = issue(0, wi.b0), h1 = h0;
+        if (wi.b0 + 1 < wi.b1) h1 = issue(1, wi.b0 + 1);
+        uint32_t cur = 0; /* buffers cur, cur+1 hold the current pair; (cur^2), (cur^2)+1 the next */
+        for (uint32_t db = wi.b0; db < wi.b1; db += 2) {
+            const bool two = db + 1 < wi.b1;
+            XgmBlockHdr n0 = h0, n1 = h1;
+            if (db + 2 < wi.b1) n0 = issue(cur ^ 2, db + 2);
+            if (db + 3 < wi.b1) n1 = issue((cur ^ 2) + 1, db + 3);
+            uint32_t c[8];
+            uint32_t alive = 0;
+            {
+                const uint32_t bits = XGM_HDR_DOC_BITS(h0.meta);
+                if (bits) { mbar_wait(&ws.dbar[cur], (phases >> cur) & 1u); phases ^= 1u << cur; }
+                decode_docids(ws.dstage[cur], bits, h0.first, lane, c);
+                const uint32_t cnt = XGM_HDR_COUNT(h0.meta);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (4 * lane + k < cnt) alive |= 1u << k;
+            }
+            if (two) {
+                const uint32_t bits = XGM_HDR_DOC_BITS(h1.meta);
+                if (bits) { mbar_wait(&ws.dbar[cur + 1], (phases >> (cur + 1)) & 1u); phases ^= 1u << (cur + 1); }
+                decode_docids(ws.dstage[cur + 1], bits, h1.first, lane, c + 4);
+                const uint32_t cnt = XGM_HDR_COUNT(h1.meta);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (4 * lane + k < cnt) alive |= 16u << k;
+            } else {
+                c[4] = c[5] = c[6] = c[7] = 0u;
+            }
+            /* the skip_to/check of the leapfrog: one bitmap word per candidate, all loads issued together */
+            uint32_t w[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[k] = (alive >> k & 1u) ? __ldg(bm1 + (c[k] >> 5)) : 0u;
+            uint32_t surv = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if ((alive >> k & 1u) && (w[k] >> (c[k] & 31) & 1u)) surv |= 1u << k;
+            if (__any_sync(FULL, surv != 0)) {
+                const uint32_t n = __popc(surv);
+                uint32_t incl = n;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(FULL, incl, o);
+                    if ((int)lane >= o) incl += t;
+                }
+                uint32_t slot = qn + incl - n;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (surv >> k & 1u) {
+                        ws.qdid[slot] = c[k];
+                        ws.qsrc[slot] = ((db - wi.b0 + (k >> 2)) << 7) | (4 * lane + (k & 3));
+                        ++slot;
+                    }
+                qn += __shfl_sync(FULL, incl, 31);
+                __syncwarp();
+                while (qn >= 32) {
+                    qn -= 32;
+                    flush(qn, 32);
+                    __syncwarp();
+                }
+            }
+            h0 = n0;
+            h1 = n1;
+            cur ^= 2u;
+        }
+        if (qn) {
+            flush(0, qn);
+            __syncwarp();
+        }
+    }
+}
+
+cudaError_t xgm_launch_and_bm(const XgmKernelParams& p, int grid, cudaStream_t s) {
+    xgm_and_bm_kernel<<<grid, BM_WARPS * 32, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+int xgm_and_bm_occupancy_blocks_per_sm() {
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, xgm_and_bm_kernel, BM_WARPS * 32, 0);
+    return n;
+}
 
 /* ------------------------------------------------------------------ chunked AND kernel (v2) */
 
@@ -913,13 +1181,17 @@ int xgm_and2_occupancy_blocks_per_sm() {
 
 struct __align__(16) OrScratch {
     WarpScratch w;
-    uint32_t tft[XGM_DEV_MAX_TERMS][XGM_BLOCK]; /* wdf of candidate x in leaf i (valid where present) */
+    uint32_t tft[XGM_DEV_MAX_TERMS][XGM_BLOCK]; /* wdf of candidate x in leaf i, for leaves probed by decoding */
 };
 
 /* OR of leaves (OrPostList tree, orpostlist.cc:93-204).  Each document of the union is produced exactly
- * once, by the rarest leaf that contains it ("owner"): work items walk one leaf's blocks, probe the
- * other leaves for the same 128 docids, drop documents owned by a rarer leaf, and evaluate the
- * reference's tree-shaped sum (l, r or l+r per node, queryinternal.cc:440-489) for the rest. */
+ * once, by the rarest leaf that contains it ("owner"): work items walk one leaf's blocks, test the other
+ * leaves for the same 128 docids (membership bitmap when the leaf has one, galloping block decode
+ * otherwise), drop documents owned by a rarer leaf, and evaluate the reference's tree-shaped sum (l, r
+ * or l+r per node, queryinternal.cc:440-489) for the rest.
+ * MaxScore pruning, the parallel form of OrPostList's w_min checks (orpostlist.cc:113-155): a document
+ * whose present leaves cannot add up to the current top-k threshold (sum of their get_maxpart bounds
+ * falls in a bucket below b*) is counted as a match but neither scored nor stored. */
 __global__ void __launch_bounds__(OR_WARPS * 32) xgm_or_kernel(XgmKernelParams p) {
     __shared__ OrScratch scratch[OR_WARPS];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -948,6 +1220,7 @@ __global__ void __launch_bounds__(OR_WARPS * 32) xgm_or_kernel(XgmKernelParams p
             my_nblk = q->terms[lane].nblocks;
         }
         const uint32_t drv_begin = __shfl_sync(FULL, my_begin, drv);
+        const bool can_prune = (q->sort_by == 0) && (q->topk != 0);
 
         for (uint32_t db = wi.b0; db < wi.b1; ++db) {
             const XgmBlockHdr dh = hdr[drv_begin + db];
@@ -955,53 +1228,78 @@ __global__ void __launch_bounds__(OR_WARPS * 32) xgm_or_kernel(XgmKernelParams p
             uint32_t c[4];
             stage_block(p.docs, dh.doc_off, XGM_HDR_DOC_BITS(dh.meta), ws.stage, &ws.bar, phase, lane);
             decode_docids(ws.stage, XGM_HDR_DOC_BITS(dh.meta), dh.first, lane, c);
-            stage_block(p.tfs, dh.tf_off, XGM_HDR_TF_BITS(dh.meta), ws.stage, &ws.bar, phase, lane);
             uint32_t owned = 0;
             uint32_t present[4];
-            {
-                const uint32_t tb = XGM_HDR_TF_BITS(dh.meta);
-                const uint32_t tmask = bitmask(tb);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    present[k] = 1u << drv;
-                    if (4 * lane + k < dcount) {
-                        owned |= 1u << k;
-                        os.tft[drv][4 * lane + k] = tb ? unpack_sm(ws.stage, 4 * lane + k, tb, tmask) : 0u;
-                    }
-                }
+            for (int k = 0; k < 4; ++k) {
+                present[k] = 1u << drv;
+                if (4 * lane + k < dcount) owned |= 1u << k;
             }
             __syncwarp();
             for (uint32_t j = 0; j < nterms; ++j) {
                 if (j == drv) continue;
                 if (!__any_sync(FULL, owned != 0)) break;
-                const uint32_t lbegin = __shfl_sync(FULL, my_begin, j);
-                const uint32_t lnblk = __shfl_sync(FULL, my_nblk, j);
-                uint32_t cur = __shfl_sync(FULL, my_cur, j);
-                cur = probe_list(
-                    p, hdr + lbegin, lnblk, cur, ws, phase, lane, c, owned,
-                    [&](int k, uint32_t pos, const XgmBlockHdr& bh) {
-                        if (j < drv) {
-                            owned &= ~(1u << k); /* a rarer leaf owns this document */
-                        } else {
-                            os.tft[j][4 * lane + k] = unpack_gl(p.tfs, bh.tf_off, pos, XGM_HDR_TF_BITS(bh.meta));
-                            present[k] |= 1u << j;
+                const uint64_t bm_off = q->terms[j].bm_off;
+                if (bm_off != XGM_NO_BITMAP) {
+                    const uint32_t* __restrict__ bm = p.bitmaps + bm_off;
+                    uint32_t w[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) w[k] = (owned >> k & 1u) ? __ldg(bm + (c[k] >> 5)) : 0u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if ((owned >> k & 1u) && (w[k] >> (c[k] & 31) & 1u)) {
+                            if (j < drv) owned &= ~(1u << k); /* a rarer leaf owns this document */
+                            else present[k] |= 1u << j;
                         }
-                    },
-                    [&](int) {});
-                if (lane == j) my_cur = cur;
+                    }
+                } else {
+                    const uint32_t lbegin = __shfl_sync(FULL, my_begin, j);
+                    const uint32_t lnblk = __shfl_sync(FULL, my_nblk, j);
+                    uint32_t cur = __shfl_sync(FULL, my_cur, j);
+                    cur = probe_list(
+                        p, hdr + lbegin, lnblk, cur, ws, phase, lane, c, owned,
+                        [&](int k, uint32_t pos, const XgmBlockHdr& bh) {
+                            if (j < drv) {
+                                owned &= ~(1u << k);
+                            } else {
+                                os.tft[j][4 * lane + k] = unpack_gl(p.tfs, bh.tf_off, pos, XGM_HDR_TF_BITS(bh.meta));
+                                present[k] |= 1u << j;
+                            }
+                        },
+                        [&](int) {});
+                    if (lane == j) my_cur = cur;
+                }
             }
             if (q->filter) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if ((owned >> k & 1u) && !doc_passes_filter(p, q, c[k])) owned &= ~(1u << k);
             }
+            /* MaxScore: can the leaves present reach the current threshold at all? */
+            uint32_t skip = 0;
+            if (can_prune) {
+                const uint32_t bstar = *reinterpret_cast<volatile uint32_t*>(&p.qstate[wi.query].bstar);
+                if (bstar != 0) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (owned >> k & 1u) {
+                            double ub = 0.0;
+                            for (uint32_t i = 0; i < nterms; ++i)
+                                if (present[k] >> i & 1u) ub += q->terms[i].maxpart;
+                            ub *= 1.0 + 1e-12; /* the bound and the tree-order sum round differently */
+                            if (match_bucket(q, ub, 0) < bstar) skip |= 1u << k;
+                        }
+                    }
+                }
+            }
             /* weight = fold of the tree over the leaves present (OrPostList::get_weight, orpostlist.cc:93-103) */
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
             uint32_t aux[4] = {0, 0, 0, 0};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (owned >> k & 1u) {
-                    const uint32_t dlen = __ldg(&p.doclen[c[k]]);
+                if ((owned & ~skip) >> k & 1u) {
+                    const uint32_t d = c[k];
+                    const uint32_t dlen = __ldg(&p.doclen[d]);
                     double stk[XGM_DEV_MAX_TERMS];
                     uint32_t has = 0; /* bit s: stack slot s holds a value */
                     int sp = 0;
@@ -1009,7 +1307,17 @@ __global__ void __launch_bounds__(OR_WARPS * 32) xgm_or_kernel(XgmKernelParams p
                         const int op = q->prog[i];
                         if (op >= 0) {
                             if (present[k] >> op & 1u) {
-                                stk[sp] = bm25_sumpart(q->terms[op].termweight, q, os.tft[op][4 * lane + k], dlen);
+                                uint32_t tf;
+                                if ((uint32_t)op == drv) {
+                                    tf = unpack_gl(p.tfs, dh.tf_off, 4 * lane + k, XGM_HDR_TF_BITS(dh.meta));
+                                } else if (q->terms[op].bm_off != XGM_NO_BITMAP) {
+                                    const uint32_t r = bitmap_rank(p, q->terms[op], d);
+                                    const XgmBlockHdr bh = hdr[q->terms[op].blk_begin + (r >> 7)];
+                                    tf = unpack_gl(p.tfs, bh.tf_off, r & 127u, XGM_HDR_TF_BITS(bh.meta));
+                                } else {
+                                    tf = os.tft[op][4 * lane + k];
+                                }
+                                stk[sp] = bm25_sumpart(q->terms[op].termweight, q, tf, dlen);
                                 has |= 1u << sp;
                             } else {
                                 has &= ~(1u << sp);
@@ -1026,7 +1334,7 @@ __global__ void __launch_bounds__(OR_WARPS * 32) xgm_or_kernel(XgmKernelParams p
                     aux[k] = __popc(present[k]);
                 }
             }
-            emit_matches(p, q, wi.query, lane, owned, acc, c, aux);
+            emit_matches(p, q, wi.query, lane, owned, acc, c, aux, skip);
             __syncwarp();
         }
     }
