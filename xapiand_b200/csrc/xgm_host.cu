@@ -707,6 +707,9 @@ struct xgm_searcher {
     XgmWorkItem* d_items = nullptr;
     XgmWorkItem* d_items_or = nullptr;
     XgmWorkItem* d_items_bm = nullptr;
+    XgmWorkItem* d_exp[3] = {nullptr, nullptr, nullptr}; /* expanded + interleaved work lists (device only) */
+    size_t exp_cap[3] = {0, 0, 0};
+    uint32_t nseg[3] = {0, 0, 0}, stride[3] = {1, 1, 1}, bpi = 16;
     unsigned char* d_ctrl = nullptr; /* [16 B work counters][nq x XgmQState][nq x XGM_NBINS x u32] */
     double* d_match_w = nullptr;
     uint32_t* d_match_d = nullptr;
@@ -735,7 +738,7 @@ extern "C" void xgm_searcher_free(xgm_searcher* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFreeHost(s->h_queries); cudaFreeHost(s->h_items); cudaFreeHost(s->h_items_or); cudaFreeHost(s->h_items_bm); cudaFreeHost(s->h_out_w); cudaFreeHost(s->h_out_d);
     cudaFreeHost(s->h_out_k); cudaFreeHost(s->h_info);
-    cudaFree(s->d_queries); cudaFree(s->d_items); cudaFree(s->d_items_or); cudaFree(s->d_items_bm); cudaFree(s->d_ctrl); cudaFree(s->d_match_w); cudaFree(s->d_match_d);
+    cudaFree(s->d_queries); cudaFree(s->d_items); cudaFree(s->d_items_or); cudaFree(s->d_items_bm); cudaFree(s->d_exp[0]); cudaFree(s->d_exp[1]); cudaFree(s->d_exp[2]); cudaFree(s->d_ctrl); cudaFree(s->d_match_w); cudaFree(s->d_match_d);
     cudaFree(s->d_match_k); cudaFree(s->d_pool_w); cudaFree(s->d_pool_d); cudaFree(s->d_pool_k); cudaFree(s->d_out_w); cudaFree(s->d_out_d); cudaFree(s->d_out_k); cudaFree(s->d_info);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -759,6 +762,17 @@ static xgm_status ensure_items(xgm_searcher* s, size_t need, int which) {
     d = nullptr;
     CUDA_TRY(cudaMalloc(&d, cap * sizeof(XgmWorkItem)));
     have = cap;
+    return XGM_OK;
+}
+
+static xgm_status ensure_expanded(xgm_searcher* s, size_t need, int which) {
+    if (need <= s->exp_cap[which]) return XGM_OK;
+    size_t cap = std::max<size_t>(need * 2, 65536);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    cudaFree(s->d_exp[which]);
+    s->d_exp[which] = nullptr;
+    CUDA_TRY(cudaMalloc(&s->d_exp[which], cap * sizeof(XgmWorkItem)));
+    s->exp_cap[which] = cap;
     return XGM_OK;
 }
 
@@ -1057,25 +1071,21 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
     if (cal == 0) { pq.on_device = false; return XGM_OK; } /* bounds only, matcher.cc:437-461 */
     if (dq.route == 0 && any_absent) { pq.on_device = false; return XGM_OK; } /* AND with an absent term: empty */
     pq.on_device = true;
+    /* one segment per (query[, leaf]); the device expands segments into work items (xgm_expand_items_kernel) */
+    (void)blocks_per_item;
     if (dq.route == 0) {
         /* every list but the driver has a membership bitmap → lean bitmap kernel */
         bool all_bm = n >= 2 && s->and_version == 1;
         for (uint32_t i = 1; i < n; ++i) all_bm = all_bm && dq.terms[i].bm_off != XGM_NO_BITMAP;
         std::vector<XgmWorkItem>& dst = all_bm ? items_bm : items;
-        uint32_t nb = dq.terms[0].nblocks;
-        for (uint32_t b0 = 0; b0 < nb; b0 += blocks_per_item) {
-            XgmWorkItem wi;
-            wi.query = qi; wi.b0 = b0; wi.b1 = std::min(nb, b0 + blocks_per_item); wi.pad = 0;
-            dst.push_back(wi);
-        }
+        XgmWorkItem wi;
+        wi.query = qi; wi.b0 = dq.terms[0].nblocks; wi.b1 = 0; wi.pad = 0;
+        if (wi.b0) dst.push_back(wi);
     } else {
         for (uint32_t leaf = 0; leaf < n; ++leaf) {
-            uint32_t nb = dq.terms[leaf].nblocks;
-            for (uint32_t b0 = 0; b0 < nb; b0 += blocks_per_item) {
-                XgmWorkItem wi;
-                wi.query = qi; wi.b0 = b0; wi.b1 = std::min(nb, b0 + blocks_per_item); wi.pad = leaf;
-                items_or.push_back(wi);
-            }
+            XgmWorkItem wi;
+            wi.query = qi; wi.b0 = dq.terms[leaf].nblocks; wi.b1 = 0; wi.pad = leaf;
+            if (wi.b0) items_or.push_back(wi);
         }
     }
     return XGM_OK;
@@ -1085,9 +1095,18 @@ static xgm_status launch_batch(xgm_searcher* s) {
     XgmKernelParams& p = s->params;
     CUDA_TRY(cudaMemsetAsync(s->d_ctrl, 0, 64 + (size_t)s->max_batch * sizeof(XgmQState), s->stream));
     CUDA_TRY(cudaMemsetAsync(p.hist, 0, (size_t)s->nq * XGM_NBINS * 4, s->stream));
-    CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
     s->stats.kernel_launches = 0;
     p.pass = 0;
+    {
+        const XgmWorkItem* segs[3] = {s->d_items, s->d_items_or, s->d_items_bm};
+        const uint32_t totals[3] = {s->nitems, s->nitems_or, s->nitems_bm};
+        for (int w = 0; w < 3; ++w)
+            if (totals[w]) {
+                CUDA_TRY(xgm_launch_expand(segs[w], s->nseg[w], totals[w], s->stride[w], s->bpi, s->d_exp[w], s->stream));
+                s->stats.kernel_launches++;
+            }
+    }
+    CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
     auto launch_and = [&](const XgmKernelParams& pp) {
         return s->and_version == 1 ? xgm_launch_and(pp, s->grid, s->stream) : xgm_launch_and2(pp, s->grid_and2, s->stream);
     };
@@ -1146,7 +1165,7 @@ extern "C" xgm_status xgm_search_submit(xgm_searcher* s, const xgm_query* querie
         for (int t = 0; t < T; ++t)
             th.emplace_back([&, t]() {
                 uint32_t a = (uint32_t)((uint64_t)nq * t / T), b = (uint32_t)((uint64_t)nq * (t + 1) / T);
-                tib[t].reserve((size_t)(b - a) * 40);
+                tib[t].reserve((size_t)(b - a));
                 for (uint32_t i = a; i < b; ++i) {
                     xgm_status st = plan_query(s, queries[i], i, s->plan[i], s->h_queries[i], ti[t], tio[t], tib[t], bpi);
                     if (st != XGM_OK) { tst[t] = st; return; }
@@ -1167,42 +1186,51 @@ extern "C" xgm_status xgm_search_submit(xgm_searcher* s, const xgm_query* querie
         total_drv_blocks += s->h_queries[i].terms[0].nblocks;
     }
     (void)total_drv_blocks; (void)postings;
-    xgm_status st = ensure_items(s, items.size(), 0);
-    if (st != XGM_OK) return st;
-    st = ensure_items(s, items_or.size(), 1);
-    if (st != XGM_OK) return st;
-    st = ensure_items(s, items_bm.size(), 2);
-    if (st != XGM_OK) return st;
-    /* Interleave the work lists across queries (all queries' first item, then all second items, ...):
-     * the warps in flight at any moment then belong to many queries, so each query's pruning threshold
-     * has risen before most of its matches are produced, and long queries do not form a tail. */
-    auto interleave = [nq](const std::vector<XgmWorkItem>& in, XgmWorkItem* out) {
-        if (in.empty()) return;
-        std::vector<uint32_t> seq(in.size()), per_q(nq, 0);
-        uint32_t maxseq = 0;
-        for (size_t i = 0; i < in.size(); ++i) { seq[i] = per_q[in[i].query]++; maxseq = std::max(maxseq, seq[i]); }
-        std::vector<size_t> start((size_t)maxseq + 2, 0);
-        for (size_t i = 0; i < in.size(); ++i) start[seq[i] + 1]++;
-        for (size_t k = 1; k < start.size(); ++k) start[k] += start[k - 1];
-        for (size_t i = 0; i < in.size(); ++i) out[start[seq[i]]++] = in[i];
-    };
-    interleave(items, s->h_items);
-    interleave(items_or, s->h_items_or);
-    interleave(items_bm, s->h_items_bm);
+    /* segments → pinned staging with the running item index; totals and permutation strides */
+    xgm_status st = XGM_OK;
+    s->bpi = bpi;
+    {
+        std::vector<XgmWorkItem>* lists[3] = {&items, &items_or, &items_bm};
+        XgmWorkItem** hbuf[3] = {&s->h_items, &s->h_items_or, &s->h_items_bm};
+        uint32_t* totals[3] = {&s->nitems, &s->nitems_or, &s->nitems_bm};
+        for (int w = 0; w < 3; ++w) {
+            std::vector<XgmWorkItem>& v = *lists[w];
+            st = ensure_items(s, v.size(), w);
+            if (st != XGM_OK) return st;
+            uint64_t run = 0;
+            XgmWorkItem* h = *hbuf[w];
+            for (size_t i = 0; i < v.size(); ++i) {
+                h[i] = v[i];
+                h[i].b1 = (uint32_t)run;
+                run += (v[i].b0 + bpi - 1) / bpi;
+            }
+            if (run >= 0xffffffffull) return fail(XGM_E_INVALID, "too many work items in one batch");
+            *totals[w] = (uint32_t)run;
+            s->nseg[w] = (uint32_t)v.size();
+            uint32_t stride = 1;
+            if (run > 2) {
+                stride = (uint32_t)((double)run * 0.6180339887498949) | 1u;
+                auto gcd = [](uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; };
+                while (gcd(stride, run) != 1) stride += 2;
+                stride %= (uint32_t)run;
+                if (stride == 0) stride = 1;
+            }
+            s->stride[w] = stride;
+            st = ensure_expanded(s, run, w);
+            if (st != XGM_OK) return st;
+        }
+    }
     const auto t_interleaved = std::chrono::steady_clock::now();
-    s->nitems = (uint32_t)items.size();
-    s->nitems_or = (uint32_t)items_or.size();
-    s->nitems_bm = (uint32_t)items_bm.size();
     s->stats = xgm_batch_stats{};
     s->stats.algorithmic_bytes = alg;
     s->stats.work_items = s->nitems + s->nitems_or + s->nitems_bm;
-    s->stats.h2d_bytes = (uint64_t)nq * sizeof(XgmDevQuery) + (uint64_t)(s->nitems + s->nitems_or + s->nitems_bm) * sizeof(XgmWorkItem);
+    s->stats.h2d_bytes = (uint64_t)nq * sizeof(XgmDevQuery) + (uint64_t)(s->nseg[0] + s->nseg[1] + s->nseg[2]) * sizeof(XgmWorkItem);
     s->stats.d2h_bytes = (uint64_t)nq * sizeof(XgmDevResult) + (uint64_t)nq * s->max_topk * (8 + 4 + (s->any_sort ? 8 : 0));
     XgmKernelParams& p = s->params;
     fill_index_params(s->ix, p);
-    p.queries = s->d_queries; p.items = s->d_items; p.nitems = s->nitems; p.nq = nq;
-    p.items_or = s->d_items_or; p.nitems_or = s->nitems_or;
-    p.items_bm = s->d_items_bm; p.nitems_bm = s->nitems_bm;
+    p.queries = s->d_queries; p.items = s->d_exp[0]; p.nitems = s->nitems; p.nq = nq;
+    p.items_or = s->d_exp[1]; p.nitems_or = s->nitems_or;
+    p.items_bm = s->d_exp[2]; p.nitems_bm = s->nitems_bm;
     p.work_counter = reinterpret_cast<uint32_t*>(s->d_ctrl);
     p.qstate = reinterpret_cast<XgmQState*>(s->d_ctrl + 64);
     p.hist = reinterpret_cast<uint32_t*>(s->d_ctrl + 64 + (size_t)s->max_batch * sizeof(XgmQState));
@@ -1211,12 +1239,12 @@ extern "C" xgm_status xgm_search_submit(xgm_searcher* s, const xgm_query* querie
     p.match_w = s->d_match_w; p.match_d = s->d_match_d; p.match_k = s->d_match_k;
     p.out_stride = s->max_topk; p.out_w = s->d_out_w; p.out_d = s->d_out_d; p.out_k = s->d_out_k; p.out_info = s->d_info;
     CUDA_TRY(cudaMemcpyAsync(s->d_queries, s->h_queries, (size_t)nq * sizeof(XgmDevQuery), cudaMemcpyHostToDevice, s->stream));
-    if (s->nitems)
-        CUDA_TRY(cudaMemcpyAsync(s->d_items, s->h_items, (size_t)s->nitems * sizeof(XgmWorkItem), cudaMemcpyHostToDevice, s->stream));
-    if (s->nitems_or)
-        CUDA_TRY(cudaMemcpyAsync(s->d_items_or, s->h_items_or, (size_t)s->nitems_or * sizeof(XgmWorkItem), cudaMemcpyHostToDevice, s->stream));
-    if (s->nitems_bm)
-        CUDA_TRY(cudaMemcpyAsync(s->d_items_bm, s->h_items_bm, (size_t)s->nitems_bm * sizeof(XgmWorkItem), cudaMemcpyHostToDevice, s->stream));
+    if (s->nseg[0])
+        CUDA_TRY(cudaMemcpyAsync(s->d_items, s->h_items, (size_t)s->nseg[0] * sizeof(XgmWorkItem), cudaMemcpyHostToDevice, s->stream));
+    if (s->nseg[1])
+        CUDA_TRY(cudaMemcpyAsync(s->d_items_or, s->h_items_or, (size_t)s->nseg[1] * sizeof(XgmWorkItem), cudaMemcpyHostToDevice, s->stream));
+    if (s->nseg[2])
+        CUDA_TRY(cudaMemcpyAsync(s->d_items_bm, s->h_items_bm, (size_t)s->nseg[2] * sizeof(XgmWorkItem), cudaMemcpyHostToDevice, s->stream));
     st = launch_batch(s);
     if (st != XGM_OK) return st;
     size_t ns = (size_t)nq * s->max_topk;
@@ -1231,7 +1259,7 @@ extern "C" xgm_status xgm_search_submit(xgm_searcher* s, const xgm_query* querie
                 std::chrono::duration<float, std::milli>(t_planned - t_submit0).count(),
                 std::chrono::duration<float, std::milli>(t_interleaved - t_planned).count(),
                 std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_interleaved).count(), T,
-                items.size() + items_or.size() + items_bm.size());
+                (size_t)s->nitems + s->nitems_or + s->nitems_bm);
     return XGM_OK;
 }
 

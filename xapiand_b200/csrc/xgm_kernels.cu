@@ -1361,6 +1361,8 @@ __device__ __forceinline__ bool ranks_before(uint32_t sort_by, uint32_t reverse,
 }
 
 #define TOPK_THREADS 256
+#define XGM_EXACT_COUNT_MAX 1024u /* largest match set whose ProtoMSet count is reproduced exactly */
+#define XGM_KEEP_PER_THREAD 32   /* keep_cap <= 8192 = 32 * TOPK_THREADS */
 
 /* Sort key of a match as up to five 32-bit words, most significant first, such that a larger key ranks
  * earlier under the reference's comparators (msetcmp.cc:54-98, ascending docid order):
@@ -1510,29 +1512,87 @@ __global__ void __launch_bounds__(TOPK_THREADS) xgm_topk_kernel(XgmKernelParams 
     }
 
     const uint32_t kept = s_n;
-    const uint32_t n = kept < p.keep_cap ? kept : p.keep_cap;
+    uint32_t n = kept < p.keep_cap ? kept : p.keep_cap;
+    /* The exact ProtoMSet count needs all n^2 pairs; beyond XGM_EXACT_COUNT_MAX matches only the top-k is
+     * produced: a shared-memory histogram of the same monotone buckets gives a threshold bucket, entries
+     * below it are dropped before ranking (the bounds are then flagged approximate). */
+    if (n > XGM_EXACT_COUNT_MAX && topk != 0 && topk < n) {
+        complete = false;
+        uint32_t* lh = reinterpret_cast<uint32_t*>(sd + p.keep_cap); /* XGM_NBINS words after the arrays */
+        for (uint32_t i = tid; i < XGM_NBINS; i += TOPK_THREADS) lh[i] = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < n; i += TOPK_THREADS) atomicAdd(&lh[match_bucket(q, sw[i], sk[i])], 1u);
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t cum = 0, b = XGM_NBINS;
+            while (b > 0 && cum < topk) { --b; cum += lh[b]; }
+            s_prefix[0] = b;
+            s_n = 0;
+        }
+        __syncthreads();
+        const uint32_t bsel = s_prefix[0];
+        /* in-place compaction: read everything into registers first (n <= keep_cap <= 32 per thread) */
+        double rw[XGM_KEEP_PER_THREAD]; uint64_t rk[XGM_KEEP_PER_THREAD]; uint32_t rd[XGM_KEEP_PER_THREAD];
+        uint32_t cnt = 0;
+        for (uint32_t i = tid, x = 0; i < n; i += TOPK_THREADS, ++x) {
+            rw[x] = sw[i]; rk[x] = sk[i]; rd[x] = sd[i];
+            cnt = x + 1;
+        }
+        __syncthreads();
+        for (uint32_t x = 0; x < cnt; ++x) {
+            if (match_bucket(q, rw[x], rk[x]) >= bsel) {
+                const uint32_t pos = atomicAdd(&s_n, 1u);
+                sw[pos] = rw[x]; sk[pos] = rk[x]; sd[pos] = rd[x];
+            }
+        }
+        __syncthreads();
+        n = s_n;
+    }
     const uint32_t free_count = q->check_at_least > topk + 1 ? q->check_at_least : topk + 1;
     uint32_t known = 0;
     const size_t ooff = (size_t)qi * p.out_stride;
-    for (uint32_t i = tid; i < n; i += TOPK_THREADS) {
-        const double wi = sw[i];
-        const uint32_t di = sd[i];
-        const uint64_t ki = sk[i];
-        uint32_t rank = 0, before = 0, greater_before = 0;
-        for (uint32_t j = 0; j < n; ++j) {
-            const double wj = sw[j];
-            const uint32_t dj = sd[j];
-            rank += ranks_before(sort_by, reverse, wj, dj, sk[j], wi, di, ki) ? 1u : 0u;
-            const bool earlier = dj < di;
-            before += earlier ? 1u : 0u;
-            greater_before += (earlier && wj > wi) ? 1u : 0u;
+    if (sort_by == 0) {
+        /* relevance order: weight desc, docid asc — no sort keys to compare */
+        for (uint32_t i = tid; i < n; i += TOPK_THREADS) {
+            const double wi = sw[i];
+            const uint32_t di = sd[i];
+            uint32_t rank = 0, before = 0, greater_before = 0;
+            for (uint32_t j = 0; j < n; ++j) {
+                const double wj = sw[j];
+                const uint32_t dj = sd[j];
+                const bool earlier = dj < di, greater = wj > wi;
+                rank += (greater || (wj == wi && earlier)) ? 1u : 0u;
+                before += earlier ? 1u : 0u;
+                greater_before += (earlier && greater) ? 1u : 0u;
+            }
+            if (rank < topk) {
+                p.out_w[ooff + rank] = wi;
+                p.out_d[ooff + rank] = di;
+                p.out_k[ooff + rank] = sk[i];
+            }
+            if (before < free_count || greater_before < topk) ++known;
         }
-        if (rank < topk) {
-            p.out_w[ooff + rank] = wi;
-            p.out_d[ooff + rank] = di;
-            p.out_k[ooff + rank] = ki;
+    } else {
+        for (uint32_t i = tid; i < n; i += TOPK_THREADS) {
+            const double wi = sw[i];
+            const uint32_t di = sd[i];
+            const uint64_t ki = sk[i];
+            uint32_t rank = 0, before = 0, greater_before = 0;
+            for (uint32_t j = 0; j < n; ++j) {
+                const double wj = sw[j];
+                const uint32_t dj = sd[j];
+                rank += ranks_before(sort_by, reverse, wj, dj, sk[j], wi, di, ki) ? 1u : 0u;
+                const bool earlier = dj < di;
+                before += earlier ? 1u : 0u;
+                greater_before += (earlier && wj > wi) ? 1u : 0u;
+            }
+            if (rank < topk) {
+                p.out_w[ooff + rank] = wi;
+                p.out_d[ooff + rank] = di;
+                p.out_k[ooff + rank] = ki;
+            }
+            if (sort_by == 1 || sort_by == 2 || before < free_count || greater_before < topk) ++known;
         }
-        if (sort_by == 1 || sort_by == 2 || before < free_count || greater_before < topk) ++known;
     }
     atomicAdd(&s_known, known);
     __syncthreads();
@@ -1645,6 +1705,39 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) xgm_decode_kernel(XgmKernelP
     }
 }
 
+/* ------------------------------------------------------------------ work-list expansion */
+
+/* The host only sends one segment per (query[, leaf]): {query, #blocks, first item index, leaf}.  This
+ * kernel expands them into work items of `bpi` blocks and, at the same time, interleaves the items of
+ * different queries with a multiplicative permutation (slot s takes item s*stride mod total, stride
+ * coprime with total): the warps in flight at any moment then belong to many queries, so every
+ * query's pruning threshold rises early and long queries do not form a tail. */
+__global__ void xgm_expand_items_kernel(const XgmWorkItem* __restrict__ seg, uint32_t nseg, uint32_t total,
+                                        uint32_t stride, uint32_t bpi, XgmWorkItem* __restrict__ out) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= total) return;
+    const uint32_t i = (uint32_t)(((uint64_t)s * stride) % total);
+    uint32_t lo = 0, hi = nseg; /* last segment whose first item index (field b1) is <= i */
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (seg[mid].b1 <= i) lo = mid; else hi = mid;
+    }
+    const XgmWorkItem sg = seg[lo]; /* query, b0 = #blocks, b1 = first item index, pad = leaf */
+    XgmWorkItem w;
+    w.query = sg.query;
+    w.b0 = (i - sg.b1) * bpi;
+    w.b1 = min(sg.b0, w.b0 + bpi);
+    w.pad = sg.pad;
+    out[s] = w;
+}
+
+cudaError_t xgm_launch_expand(const XgmWorkItem* seg, uint32_t nseg, uint32_t total, uint32_t stride, uint32_t bpi,
+                              XgmWorkItem* out, cudaStream_t s) {
+    if (total == 0) return cudaSuccess;
+    xgm_expand_items_kernel<<<(total + 255) / 256, 256, 0, s>>>(seg, nseg, total, stride, bpi, out);
+    return cudaGetLastError();
+}
+
 /* ------------------------------------------------------------------ launchers */
 
 cudaError_t xgm_launch_and(const XgmKernelParams& p, int grid, cudaStream_t s) {
@@ -1657,7 +1750,7 @@ cudaError_t xgm_launch_or(const XgmKernelParams& p, int grid, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-size_t xgm_topk_smem_bytes(uint32_t keep_cap) { return (size_t)keep_cap * (8 + 8 + 4); }
+size_t xgm_topk_smem_bytes(uint32_t keep_cap) { return (size_t)keep_cap * (8 + 8 + 4) + XGM_NBINS * 4; }
 
 cudaError_t xgm_launch_topk(const XgmKernelParams& p, uint32_t nq, cudaStream_t s) {
     size_t smem = xgm_topk_smem_bytes(p.keep_cap);
