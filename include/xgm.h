@@ -168,6 +168,10 @@ typedef struct xgm_mset_info {
  * conservative (still valid bounds) and this flag is set.  Docids, weights, max_possible,
  * max_attained, the upper bound and exact_matches are always exact. */
 #define XGM_MSET_BOUNDS_APPROX 1u
+/* OR queries only: MaxScore skipped whole posting-list segments that cannot reach the top-k (what
+ * OrPostList's w_min pruning does in the reference, orpostlist.cc:113-155), so exact_matches counts only
+ * the documents actually visited.  Never set when check_at_least covers the match set. */
+#define XGM_MSET_COUNT_LOWER_BOUND 2u
 
 /* ---- searching ---------------------------------------------------------------------------- */
 /* A searcher owns a CUDA stream and pinned/device staging for batches of up to max_batch queries

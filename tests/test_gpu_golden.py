@@ -125,3 +125,55 @@ def test_multi_range_filter_and_sort_variants_against_oracle():
         assert bits(m.max_attained) == bits(ref.max_attained), ctx
         if q.sort_by != O.SORT_REL:
             assert list(m.sort_keys) == list(ref.sortvals), ctx
+
+
+class _CudaArray:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def test_device_merge_matches_reference_twophase():
+    """The multi-GPU data path on one GPU: per-shard device results are concatenated exactly as an
+    all-gather would lay them out ([part][query][rank]) and merged by xgm_merge_topk_device (unshard +
+    Matcher::merge_mset order); checked against the reference's own two-phase run over 4 shards."""
+    import torch
+    fx = load("shard4_20k")
+    n = fx["nshards"]
+    qs = [q for q in fx["queries"] if q["first"] == 0]  # the device merge keeps ranks [0, k)
+    K = 128
+    shards = [xgm.Index.synthetic(fx["ndocs"], fx["vocab"], fx["seed"], nshards=n, shard=s) for s in range(n)]
+    infos = [ix.info() for ix in shards]
+    coll = sum(i.doccount for i in infos)
+    tlen = sum(i.total_length for i in infos)
+    nq = len(qs)
+    gw, gd, gc = [], [], []
+    searchers = []
+    for si, ix in enumerate(shards):
+        s = xgm.Searcher(ix, max_batch=nq, max_topk=K)
+        searchers.append(s)
+        batch = []
+        for q in qs:
+            gtf = [sum(x.term_stats(f"T{t:06d}").termfreq for x in shards) for t in q["terms"]]
+            batch.append(x_query(q, stats=(coll, tlen, gtf), first=0, maxitems=q["maxitems"]))
+        s.search(batch)
+        wptr, dptr, cptr, stride = s.device_results()
+        assert stride == K
+        gw.append(torch.as_tensor(_CudaArray(wptr, (nq * K,), "<f8"), device="cuda").clone())
+        gd.append(torch.as_tensor(_CudaArray(dptr, (nq * K,), "<u4"), device="cuda").view(torch.int32).clone())
+        gc.append(torch.as_tensor(_CudaArray(cptr, (nq * 8,), "<u4"), device="cuda").view(torch.int32).clone())
+    W, D, Cn = torch.cat(gw), torch.cat(gd), torch.cat(gc)
+    ow = torch.zeros(nq * K, dtype=torch.float64, device="cuda")
+    od = torch.zeros(nq * K, dtype=torch.int32, device="cuda")
+    on = torch.zeros(nq, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    st = xgm.lib().xgm_merge_topk_device(W.data_ptr(), D.data_ptr(), Cn.data_ptr(), n, nq, K, K, ow.data_ptr(),
+                                         od.data_ptr(), on.data_ptr(), None)
+    assert st == 0, xgm.lib().xgm_last_error()
+    torch.cuda.synchronize()
+    ow, od, on = ow.cpu().numpy().reshape(nq, K), od.cpu().numpy().view(np.uint32).reshape(nq, K), on.cpu().numpy()
+    for i, q in enumerate(qs):
+        m = q["maxitems"]
+        got_n = min(int(on[i]), m)
+        assert got_n == len(q["docids"]), f"merge[{i}]"
+        assert list(od[i, :got_n]) == q["docids"], f"merge[{i}] docids"
+        assert all(bits(a) == bits(b) for a, b in zip(ow[i, :got_n], q["weights"])), f"merge[{i}] weights"

@@ -68,8 +68,8 @@ cudaError_t xgm_launch_and2(const XgmKernelParams& p, int grid, cudaStream_t s);
 int xgm_and2_occupancy_blocks_per_sm();
 cudaError_t xgm_launch_and_bm(const XgmKernelParams& p, int grid, cudaStream_t s);
 int xgm_and_bm_occupancy_blocks_per_sm();
-cudaError_t xgm_launch_expand(const XgmWorkItem* seg, uint32_t nseg, uint32_t total, uint32_t stride, uint32_t bpi,
-                              XgmWorkItem* out, cudaStream_t s);
+cudaError_t xgm_launch_expand(const XgmWorkItem* seg, uint32_t nseg, uint32_t total, const uint32_t* level_start,
+                              uint32_t nlevels, uint32_t bpi, XgmWorkItem* out, cudaStream_t s);
 cudaError_t xgm_launch_or(const XgmKernelParams& p, int grid, cudaStream_t s);
 int xgm_or_occupancy_blocks_per_sm();
 cudaError_t xgm_launch_topk(const XgmKernelParams& p, uint32_t nq, cudaStream_t s);

@@ -79,6 +79,8 @@ struct XgmQState {
     unsigned long long maxw;   /* bit pattern of the best weight over all matches */
     uint32_t pool_off;         /* second pass: this query's slice of the overflow pool (entries) */
     uint32_t pool_cap;         /* exact number of matches at or above b* (from the completed histogram) */
+    uint32_t skipped;          /* OR: whole work items were skipped by MaxScore (match count is a lower bound) */
+    uint32_t pad;
 };
 
 #endif

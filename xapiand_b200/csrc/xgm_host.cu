@@ -709,7 +709,10 @@ struct xgm_searcher {
     XgmWorkItem* d_items_bm = nullptr;
     XgmWorkItem* d_exp[3] = {nullptr, nullptr, nullptr}; /* expanded + interleaved work lists (device only) */
     size_t exp_cap[3] = {0, 0, 0};
-    uint32_t nseg[3] = {0, 0, 0}, stride[3] = {1, 1, 1}, bpi = 16;
+    uint32_t nseg[3] = {0, 0, 0}, nlevels[3] = {0, 0, 0}, bpi = 16;
+    uint32_t* h_levels[3] = {nullptr, nullptr, nullptr}; /* pinned: level_start arrays of the AND lists */
+    uint32_t* d_levels[3] = {nullptr, nullptr, nullptr};
+    size_t levels_cap[3] = {0, 0, 0};
     unsigned char* d_ctrl = nullptr; /* [16 B work counters][nq x XgmQState][nq x XGM_NBINS x u32] */
     double* d_match_w = nullptr;
     uint32_t* d_match_d = nullptr;
@@ -738,7 +741,8 @@ extern "C" void xgm_searcher_free(xgm_searcher* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFreeHost(s->h_queries); cudaFreeHost(s->h_items); cudaFreeHost(s->h_items_or); cudaFreeHost(s->h_items_bm); cudaFreeHost(s->h_out_w); cudaFreeHost(s->h_out_d);
     cudaFreeHost(s->h_out_k); cudaFreeHost(s->h_info);
-    cudaFree(s->d_queries); cudaFree(s->d_items); cudaFree(s->d_items_or); cudaFree(s->d_items_bm); cudaFree(s->d_exp[0]); cudaFree(s->d_exp[1]); cudaFree(s->d_exp[2]); cudaFree(s->d_ctrl); cudaFree(s->d_match_w); cudaFree(s->d_match_d);
+    cudaFree(s->d_queries); cudaFree(s->d_items); cudaFree(s->d_items_or); cudaFree(s->d_items_bm); cudaFree(s->d_exp[0]); cudaFree(s->d_exp[1]); cudaFree(s->d_exp[2]);
+    for (int w = 0; w < 3; ++w) { if (s->h_levels[w]) cudaFreeHost(s->h_levels[w]); cudaFree(s->d_levels[w]); } cudaFree(s->d_ctrl); cudaFree(s->d_match_w); cudaFree(s->d_match_d);
     cudaFree(s->d_match_k); cudaFree(s->d_pool_w); cudaFree(s->d_pool_d); cudaFree(s->d_pool_k); cudaFree(s->d_out_w); cudaFree(s->d_out_d); cudaFree(s->d_out_k); cudaFree(s->d_info);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -765,6 +769,19 @@ static xgm_status ensure_items(xgm_searcher* s, size_t need, int which) {
     return XGM_OK;
 }
 
+static xgm_status ensure_levels(xgm_searcher* s, size_t need, int which) {
+    if (need <= s->levels_cap[which]) return XGM_OK;
+    size_t cap = std::max<size_t>(need * 2, 1024);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (s->h_levels[which]) cudaFreeHost(s->h_levels[which]);
+    cudaFree(s->d_levels[which]);
+    s->h_levels[which] = nullptr; s->d_levels[which] = nullptr;
+    CUDA_TRY(cudaMallocHost(&s->h_levels[which], cap * 4));
+    CUDA_TRY(cudaMalloc(&s->d_levels[which], cap * 4));
+    s->levels_cap[which] = cap;
+    return XGM_OK;
+}
+
 static xgm_status ensure_expanded(xgm_searcher* s, size_t need, int which) {
     if (need <= s->exp_cap[which]) return XGM_OK;
     size_t cap = std::max<size_t>(need * 2, 65536);
@@ -782,8 +799,10 @@ extern "C" xgm_status xgm_searcher_new(const xgm_index* ix, uint32_t max_batch, 
     CUDA_TRY(cudaSetDevice(ix->device));
     std::unique_ptr<xgm_searcher, void (*)(xgm_searcher*)> s(new xgm_searcher(), xgm_searcher_free);
     s->ix = ix; s->max_batch = max_batch; s->max_topk = max_topk;
-    s->match_cap = std::max<uint32_t>(8192, 8 * max_topk);
-    s->keep_cap = std::max<uint32_t>(2048, std::min<uint32_t>(8192, 2 * max_topk + 1024));
+    /* candidates a query may buffer before its pruning threshold settles (~k(1+ln(M/k)) arrive above
+     * a rising threshold) and how many of them the top-k kernel can hold in shared memory */
+    s->match_cap = std::max<uint32_t>(8192, 16 * max_topk);
+    s->keep_cap = std::max<uint32_t>(2048, std::min<uint32_t>(8192, 8 * max_topk));
     if (s->keep_cap > s->match_cap) s->keep_cap = s->match_cap;
     CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&s->ev0)); CUDA_TRY(cudaEventCreate(&s->ev1)); CUDA_TRY(cudaEventCreate(&s->ev2));
@@ -1102,7 +1121,7 @@ static xgm_status launch_batch(xgm_searcher* s) {
         const uint32_t totals[3] = {s->nitems, s->nitems_or, s->nitems_bm};
         for (int w = 0; w < 3; ++w)
             if (totals[w]) {
-                CUDA_TRY(xgm_launch_expand(segs[w], s->nseg[w], totals[w], s->stride[w], s->bpi, s->d_exp[w], s->stream));
+                CUDA_TRY(xgm_launch_expand(segs[w], s->nseg[w], totals[w], s->d_levels[w], s->nlevels[w], s->bpi, s->d_exp[w], s->stream));
                 s->stats.kernel_launches++;
             }
     }
@@ -1186,6 +1205,10 @@ extern "C" xgm_status xgm_search_submit(xgm_searcher* s, const xgm_query* querie
         total_drv_blocks += s->h_queries[i].terms[0].nblocks;
     }
     (void)total_drv_blocks; (void)postings;
+    /* OR work is ordered leaf-major (all queries' rarest leaves first): by the time the frequent, low-weight
+     * leaves come up the thresholds have risen and MaxScore skips them wholesale */
+    std::stable_sort(items_or.begin(), items_or.end(),
+                     [](const XgmWorkItem& a, const XgmWorkItem& b) { return a.pad < b.pad; });
     /* segments → pinned staging with the running item index; totals and permutation strides */
     xgm_status st = XGM_OK;
     s->bpi = bpi;
@@ -1199,23 +1222,34 @@ extern "C" xgm_status xgm_search_submit(xgm_searcher* s, const xgm_query* querie
             if (st != XGM_OK) return st;
             uint64_t run = 0;
             XgmWorkItem* h = *hbuf[w];
-            for (size_t i = 0; i < v.size(); ++i) {
-                h[i] = v[i];
-                h[i].b1 = (uint32_t)run;
-                run += (v[i].b0 + bpi - 1) / bpi;
+            s->nlevels[w] = 0;
+            if (w != 1 && !v.empty()) {
+                /* AND lists: level order — sort segments by descending length, level k holds the k-th item of
+                 * every segment that has one, i.e. a prefix of the sorted segments */
+                std::sort(v.begin(), v.end(), [](const XgmWorkItem& a, const XgmWorkItem& b) { return a.b0 > b.b0; });
+                const uint32_t maxlev = (v[0].b0 + bpi - 1) / bpi;
+                st = ensure_levels(s, (size_t)maxlev + 1, w);
+                if (st != XGM_OK) return st;
+                uint32_t* lv = s->h_levels[w];
+                size_t alive = v.size();
+                for (uint32_t k = 0; k < maxlev; ++k) {
+                    while (alive > 0 && (v[alive - 1].b0 + bpi - 1) / bpi <= k) --alive;
+                    lv[k] = (uint32_t)run;
+                    run += alive;
+                }
+                lv[maxlev] = (uint32_t)run;
+                s->nlevels[w] = maxlev;
+                for (size_t i = 0; i < v.size(); ++i) h[i] = v[i];
+            } else {
+                for (size_t i = 0; i < v.size(); ++i) {
+                    h[i] = v[i];
+                    h[i].b1 = (uint32_t)run;
+                    run += (v[i].b0 + bpi - 1) / bpi;
+                }
             }
             if (run >= 0xffffffffull) return fail(XGM_E_INVALID, "too many work items in one batch");
             *totals[w] = (uint32_t)run;
             s->nseg[w] = (uint32_t)v.size();
-            uint32_t stride = 1;
-            if (run > 2) {
-                stride = (uint32_t)((double)run * 0.6180339887498949) | 1u;
-                auto gcd = [](uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; };
-                while (gcd(stride, run) != 1) stride += 2;
-                stride %= (uint32_t)run;
-                if (stride == 0) stride = 1;
-            }
-            s->stride[w] = stride;
             st = ensure_expanded(s, run, w);
             if (st != XGM_OK) return st;
         }
@@ -1245,6 +1279,9 @@ extern "C" xgm_status xgm_search_submit(xgm_searcher* s, const xgm_query* querie
         CUDA_TRY(cudaMemcpyAsync(s->d_items_or, s->h_items_or, (size_t)s->nseg[1] * sizeof(XgmWorkItem), cudaMemcpyHostToDevice, s->stream));
     if (s->nseg[2])
         CUDA_TRY(cudaMemcpyAsync(s->d_items_bm, s->h_items_bm, (size_t)s->nseg[2] * sizeof(XgmWorkItem), cudaMemcpyHostToDevice, s->stream));
+    for (int w = 0; w < 3; ++w)
+        if (s->nlevels[w])
+            CUDA_TRY(cudaMemcpyAsync(s->d_levels[w], s->h_levels[w], ((size_t)s->nlevels[w] + 1) * 4, cudaMemcpyHostToDevice, s->stream));
     st = launch_batch(s);
     if (st != XGM_OK) return st;
     size_t ns = (size_t)nq * s->max_topk;
@@ -1284,6 +1321,7 @@ static void finish_info(const PlannedQuery& pq, const XgmDevResult* dr, const do
         else { lb = std::max(lb, known); est = std::max(est, known); }
         if (dr->flags & 5u) o->status = XGM_E_UNIMPLEMENTED; /* candidates lost: pathological tie mass */
         if (dr->flags & 2u) o->flags |= XGM_MSET_BOUNDS_APPROX;
+        if (dr->flags & 8u) o->flags |= XGM_MSET_BOUNDS_APPROX | XGM_MSET_COUNT_LOWER_BOUND;
         /* with a value-range source in the AND the reference's lower bound / estimate also fold in
          * ValueRangePostList::get_termfreq_est (valuerangepostlist.cc:70-130), which is not restated */
         if (pq.filter && size == pq.topk && known >= pq.check_at_least) o->flags |= XGM_MSET_BOUNDS_APPROX;

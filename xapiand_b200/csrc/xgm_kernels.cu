@@ -1222,6 +1222,26 @@ __global__ void __launch_bounds__(OR_WARPS * 32) xgm_or_kernel(XgmKernelParams p
         const uint32_t drv_begin = __shfl_sync(FULL, my_begin, drv);
         const bool can_prune = (q->sort_by == 0) && (q->topk != 0);
 
+        /* MaxScore at work-item granularity: a document owned by leaf `drv` contains no rarer leaf, so its
+         * weight is bounded by the get_maxpart sum of leaves drv..n-1.  Once the top-k threshold b* is above
+         * that bound — and at least check_at_least matches have been counted, as ProtoMSet requires before
+         * min_weight may rise (protomset.h:185-194) — nothing this item owns can enter the MSet: skip it
+         * without decoding a block.  Work items are ordered rarest leaf first, so the frequent (low-weight)
+         * leaves, which hold most of the union, are usually skipped wholesale. */
+        if (can_prune) {
+            const XgmQState* st = &p.qstate[wi.query];
+            const uint32_t bstar = *reinterpret_cast<const volatile uint32_t*>(&st->bstar);
+            if (bstar != 0 && *reinterpret_cast<const volatile uint32_t*>(&st->total) >= q->check_at_least) {
+                double ub = 0.0;
+                for (uint32_t i = drv; i < nterms; ++i) ub += q->terms[i].maxpart;
+                ub *= 1.0 + 1e-12;
+                if (match_bucket(q, ub, 0) < bstar) {
+                    if (lane == 0) p.qstate[wi.query].skipped = 1u;
+                    continue;
+                }
+            }
+        }
+
         for (uint32_t db = wi.b0; db < wi.b1; ++db) {
             const XgmBlockHdr dh = hdr[drv_begin + db];
             const uint32_t dcount = XGM_HDR_COUNT(dh.meta);
@@ -1604,7 +1624,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) xgm_topk_kernel(XgmKernelParams 
         if (kept > p.keep_cap || lost) r.flags |= 1u;
         if (topk == 0) {
             r.known = st.total; /* nothing is ever kept, so min_weight never rises: every match is counted */
-        } else if (complete) {
+        } else if (complete && !st.skipped) {
             r.known = s_known;
         } else {
             /* pruned run: ProtoMSet's count depends on docid-order history we did not keep; report the
@@ -1612,6 +1632,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) xgm_topk_kernel(XgmKernelParams 
             r.known = st.total < free_count ? st.total : free_count;
             r.flags |= 2u;
         }
+        if (st.skipped) r.flags |= 8u; /* whole work items were pruned: the match count is a lower bound */
         r.max_w = __longlong_as_double((long long)st.maxw);
         r.max_subqs = q->nterms;
         r.pad = 0;
@@ -1707,34 +1728,49 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) xgm_decode_kernel(XgmKernelP
 
 /* ------------------------------------------------------------------ work-list expansion */
 
-/* The host only sends one segment per (query[, leaf]): {query, #blocks, first item index, leaf}.  This
- * kernel expands them into work items of `bpi` blocks and, at the same time, interleaves the items of
- * different queries with a multiplicative permutation (slot s takes item s*stride mod total, stride
- * coprime with total): the warps in flight at any moment then belong to many queries, so every
- * query's pruning threshold rises early and long queries do not form a tail. */
+/* The host only sends one segment per (query[, leaf]): {query, #blocks, first item index, leaf}, and
+ * this kernel expands them into work items of `bpi` blocks, in one of two orders:
+ *  - level order (AND lists; segments sorted by descending length, level_start[k] = number of items in
+ *    levels < k): all queries' first items, then all second items, ...  The warps in flight at any
+ *    moment belong to many queries, so every query's pruning threshold rises early, long queries do not
+ *    form a tail, and concurrently running items of one query stay far apart;
+ *  - segment order (OR list, nlevels == 0): rarest leaves of all queries first, for MaxScore. */
 __global__ void xgm_expand_items_kernel(const XgmWorkItem* __restrict__ seg, uint32_t nseg, uint32_t total,
-                                        uint32_t stride, uint32_t bpi, XgmWorkItem* __restrict__ out) {
+                                        const uint32_t* __restrict__ level_start, uint32_t nlevels, uint32_t bpi,
+                                        XgmWorkItem* __restrict__ out) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= total) return;
-    const uint32_t i = (uint32_t)(((uint64_t)s * stride) % total);
-    uint32_t lo = 0, hi = nseg; /* last segment whose first item index (field b1) is <= i */
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (seg[mid].b1 <= i) lo = mid; else hi = mid;
-    }
-    const XgmWorkItem sg = seg[lo]; /* query, b0 = #blocks, b1 = first item index, pad = leaf */
     XgmWorkItem w;
-    w.query = sg.query;
-    w.b0 = (i - sg.b1) * bpi;
-    w.b1 = min(sg.b0, w.b0 + bpi);
-    w.pad = sg.pad;
+    if (nlevels != 0) {
+        uint32_t lo = 0, hi = nlevels; /* last level whose start is <= s */
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (level_start[mid] <= s) lo = mid; else hi = mid;
+        }
+        const XgmWorkItem sg = seg[s - level_start[lo]]; /* segments sorted by descending #blocks */
+        w.query = sg.query;
+        w.b0 = lo * bpi;
+        w.b1 = min(sg.b0, w.b0 + bpi);
+        w.pad = sg.pad;
+    } else {
+        uint32_t lo = 0, hi = nseg; /* last segment whose first item index (field b1) is <= s */
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (seg[mid].b1 <= s) lo = mid; else hi = mid;
+        }
+        const XgmWorkItem sg = seg[lo]; /* query, b0 = #blocks, b1 = first item index, pad = leaf */
+        w.query = sg.query;
+        w.b0 = (s - sg.b1) * bpi;
+        w.b1 = min(sg.b0, w.b0 + bpi);
+        w.pad = sg.pad;
+    }
     out[s] = w;
 }
 
-cudaError_t xgm_launch_expand(const XgmWorkItem* seg, uint32_t nseg, uint32_t total, uint32_t stride, uint32_t bpi,
-                              XgmWorkItem* out, cudaStream_t s) {
+cudaError_t xgm_launch_expand(const XgmWorkItem* seg, uint32_t nseg, uint32_t total, const uint32_t* level_start,
+                              uint32_t nlevels, uint32_t bpi, XgmWorkItem* out, cudaStream_t s) {
     if (total == 0) return cudaSuccess;
-    xgm_expand_items_kernel<<<(total + 255) / 256, 256, 0, s>>>(seg, nseg, total, stride, bpi, out);
+    xgm_expand_items_kernel<<<(total + 255) / 256, 256, 0, s>>>(seg, nseg, total, level_start, nlevels, bpi, out);
     return cudaGetLastError();
 }
 
