@@ -232,7 +232,8 @@ def ours(args):
                         stats=None if stats_list is None else stats_list[i]) for i, q in enumerate(terms)]
         return xgm.QueryBatch(qs)
 
-    searchers = [xgm.Searcher(ix, max_batch=BATCH, max_topk=TOPK) for _ in range(2)]
+    NSEARCH = 3  # batches in flight in the end-to-end loop (host planning / GPU / result scatter overlap)
+    searchers = [xgm.Searcher(ix, max_batch=BATCH, max_topk=TOPK) for _ in range(NSEARCH)]
     streams = [torch.cuda.ExternalStream(s.stream(), device=torch.device("cuda", local_rank)) for s in searchers]
     L = xgm.lib()
 
@@ -314,21 +315,22 @@ def ours(args):
     dev_ms = float(t.item())
     value = BATCH * args.steps / (dev_ms / 1e3)
 
-    # ---- end-to-end timed region: K steps through submit/wait with host buffers, two searchers ----
+    # ---- end-to-end timed region: K steps through submit/wait with host buffers, NSEARCH searchers ----
     barrier()
     t0 = time.perf_counter()
-    pending = None
+    inflight = []
     h2d = d2h = 0
     for k in range(args.steps):
-        si = k & 1
+        si = k % NSEARCH
+        if len(inflight) == NSEARCH:
+            searchers[inflight.pop(0)].wait_raw()
         searchers[si].submit(batches[1 + k])
         if world > 1:
             merge_step(si, True)
-        if pending is not None:
-            searchers[pending].wait_raw()
-        pending = si
-        bs = searchers[si].last_stats() if False else None
-    searchers[pending].wait_raw()
+        inflight.append(si)
+    pending = inflight[-1]
+    for si in inflight:
+        searchers[si].wait_raw()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     e2e_s = t1 - t0
