@@ -213,6 +213,8 @@ typedef struct xgm_batch_stats {
     uint64_t h2d_bytes, d2h_bytes; /* bytes the batch moved over PCIe (plan in, results out) */
     float host_plan_ms;           /* host time inside xgm_search_submit (planning + enqueue) */
     float host_wait_ms;           /* host time inside xgm_search_wait after the stream drained (result scatter) */
+    uint32_t second_pass_queries; /* queries whose candidate buffer overflowed and were matched a second time */
+    uint32_t reserved;
 } xgm_batch_stats;
 xgm_status xgm_search_last_stats(xgm_searcher*, xgm_batch_stats* out);
 

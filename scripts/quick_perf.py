@@ -47,7 +47,7 @@ for it in range(3):
     st = so.last_stats()
     print(json.dumps(dict(or_iter=it, e2e_ms=round(dt * 1e3, 3), qps=round(nqo / dt), match_ms=round(st.match_kernel_ms, 3),
                           topk_ms=round(st.topk_kernel_ms, 3), items=st.work_items, bad=sum(1 for i in range(nqo) if inf2[i].status != 0),
-                          approx=sum(1 for i in range(nqo) if inf2[i].flags & 1),
+                          approx=sum(1 for i in range(nqo) if inf2[i].flags & 1), second_pass=st.second_pass_queries,
                           mean_hits=float(np.mean([inf2[i].exact_matches for i in range(nqo)])))))
 # replay timing (device only)
 import ctypes

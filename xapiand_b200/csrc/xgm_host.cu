@@ -713,6 +713,8 @@ struct xgm_searcher {
     uint32_t* h_levels[3] = {nullptr, nullptr, nullptr}; /* pinned: level_start arrays of the AND lists */
     uint32_t* d_levels[3] = {nullptr, nullptr, nullptr};
     size_t levels_cap[3] = {0, 0, 0};
+    struct OrGroup { uint32_t seg_off, nseg, level_off, nlevels, out_off, total; };
+    std::vector<OrGroup> or_groups; /* OR list: one level-ordered expansion per leaf position */
     unsigned char* d_ctrl = nullptr; /* [16 B work counters][nq x XgmQState][nq x XGM_NBINS x u32] */
     double* d_match_w = nullptr;
     uint32_t* d_match_d = nullptr;
@@ -1119,11 +1121,19 @@ static xgm_status launch_batch(xgm_searcher* s) {
     {
         const XgmWorkItem* segs[3] = {s->d_items, s->d_items_or, s->d_items_bm};
         const uint32_t totals[3] = {s->nitems, s->nitems_or, s->nitems_bm};
-        for (int w = 0; w < 3; ++w)
-            if (totals[w]) {
+        for (int w = 0; w < 3; ++w) {
+            if (!totals[w]) continue;
+            if (w == 1) {
+                for (const auto& g : s->or_groups) {
+                    CUDA_TRY(xgm_launch_expand(segs[1] + g.seg_off, g.nseg, g.total, s->d_levels[1] + g.level_off, g.nlevels,
+                                               s->bpi, s->d_exp[1] + g.out_off, s->stream));
+                    s->stats.kernel_launches++;
+                }
+            } else {
                 CUDA_TRY(xgm_launch_expand(segs[w], s->nseg[w], totals[w], s->d_levels[w], s->nlevels[w], s->bpi, s->d_exp[w], s->stream));
                 s->stats.kernel_launches++;
             }
+        }
     }
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
     auto launch_and = [&](const XgmKernelParams& pp) {
@@ -1240,12 +1250,45 @@ extern "C" xgm_status xgm_search_submit(xgm_searcher* s, const xgm_query* querie
                 lv[maxlev] = (uint32_t)run;
                 s->nlevels[w] = maxlev;
                 for (size_t i = 0; i < v.size(); ++i) h[i] = v[i];
-            } else {
-                for (size_t i = 0; i < v.size(); ++i) {
-                    h[i] = v[i];
-                    h[i].b1 = (uint32_t)run;
-                    run += (v[i].b0 + bpi - 1) / bpi;
+            } else if (w == 1) {
+                /* OR: leaf-major groups (rarest leaves of all queries first, for MaxScore), level order inside
+                 * each group so that one query's items are spread in time and its threshold settles early */
+                s->or_groups.clear();
+                size_t nlev_total = 0;
+                for (size_t a = 0; a < v.size();) {
+                    size_t b = a;
+                    while (b < v.size() && v[b].pad == v[a].pad) ++b;
+                    std::sort(v.begin() + a, v.begin() + b, [](const XgmWorkItem& x, const XgmWorkItem& y) { return x.b0 > y.b0; });
+                    nlev_total += (v[a].b0 + bpi - 1) / bpi + 1;
+                    a = b;
                 }
+                st = ensure_levels(s, nlev_total + 1, 1);
+                if (st != XGM_OK) return st;
+                uint32_t* lv = s->h_levels[1];
+                size_t lvpos = 0;
+                for (size_t a = 0; a < v.size();) {
+                    size_t b = a;
+                    while (b < v.size() && v[b].pad == v[a].pad) ++b;
+                    const uint32_t maxlev = (v[a].b0 + bpi - 1) / bpi;
+                    xgm_searcher::OrGroup g;
+                    g.seg_off = (uint32_t)a; g.nseg = (uint32_t)(b - a); g.level_off = (uint32_t)lvpos; g.nlevels = maxlev;
+                    g.out_off = (uint32_t)run;
+                    uint64_t grun = 0;
+                    size_t alive = b - a;
+                    for (uint32_t k = 0; k < maxlev; ++k) {
+                        while (alive > 0 && (v[a + alive - 1].b0 + bpi - 1) / bpi <= k) --alive;
+                        lv[lvpos + k] = (uint32_t)grun;
+                        grun += alive;
+                    }
+                    lv[lvpos + maxlev] = (uint32_t)grun;
+                    lvpos += (size_t)maxlev + 1;
+                    g.total = (uint32_t)grun;
+                    run += grun;
+                    s->or_groups.push_back(g);
+                    a = b;
+                }
+                s->nlevels[1] = (uint32_t)lvpos; /* total entries to copy */
+                for (size_t i = 0; i < v.size(); ++i) h[i] = v[i];
             }
             if (run >= 0xffffffffull) return fail(XGM_E_INVALID, "too many work items in one batch");
             *totals[w] = (uint32_t)run;
@@ -1355,9 +1398,11 @@ extern "C" xgm_status xgm_search_wait(xgm_searcher* s, uint32_t* docids, double*
     cudaEventElapsedTime(&s->stats.match_kernel_ms, s->ev0, s->ev1);
     cudaEventElapsedTime(&s->stats.topk_kernel_ms, s->ev1, s->ev2);
     const auto t_wait0 = std::chrono::steady_clock::now();
+    s->stats.second_pass_queries = 0;
     for (uint32_t i = 0; i < s->nq; ++i) {
         const PlannedQuery& pq = s->plan[i];
         const size_t off = (size_t)i * s->max_topk;
+        if (pq.status == XGM_OK && pq.on_device && (s->h_info[i].flags & 16u)) s->stats.second_pass_queries++;
         finish_info(pq, &s->h_info[i], s->h_out_w + off, s->any_sort ? s->h_out_k + off : nullptr,
                     s->h_queries[i].route == 1, &info[i]);
         if (pq.status == XGM_OK && pq.on_device) s->stats.algorithmic_bytes += 4ull * s->h_info[i].exact;

@@ -1633,6 +1633,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) xgm_topk_kernel(XgmKernelParams 
             r.flags |= 2u;
         }
         if (st.skipped) r.flags |= 8u; /* whole work items were pruned: the match count is a lower bound */
+        if (p.pass != 0) r.flags |= 16u; /* produced by the second pass */
         r.max_w = __longlong_as_double((long long)st.maxw);
         r.max_subqs = q->nterms;
         r.pad = 0;

@@ -82,7 +82,8 @@ class BatchStats(C.Structure):
     _fields_ = [("algorithmic_bytes", C.c_uint64), ("postings", C.c_uint64), ("work_items", C.c_uint32),
                 ("kernel_launches", C.c_uint32), ("match_kernel_ms", C.c_float), ("topk_kernel_ms", C.c_float),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("host_plan_ms", C.c_float), ("host_wait_ms", C.c_float)]
+                ("host_plan_ms", C.c_float), ("host_wait_ms", C.c_float),
+                ("second_pass_queries", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 _lib = None
