@@ -58,51 +58,126 @@ def term_name(r: int) -> str:
 # ---------------------------------------------------------------------------------------------
 
 class ClockSampler:
+    """SM clock / throttle-reason samples taken DURING the timed regions.  NVML is polled from a thread every
+    few milliseconds (the regions last tens of milliseconds; polling faster contends with the CUDA driver
+    and slows the host side of the end-to-end loop), plus one sample taken by the main thread while the
+    device-resident region's work is queued; `nvidia-smi -lms` is the fallback."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+               (0x4, "sw_power_cap"), (0x80, "hw_power_brake_slowdown"))
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, uuid: str | None = None):
         self.gpu = gpu_index
-        self.rows = []
+        self.uuid = uuid
+        self.samples = []      # (perf_counter, sm_mhz, reason_bits)
+        self.windows = []      # [t0, t1] of the timed regions
+        self.max_mhz = None
         self.proc = None
+        self.rows = []
+        self.handle = None
+        self.stop_flag = False
+        self.thread = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(self.uuid)
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.handle = h
+            self.nvml = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.handle = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
                                           "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            time.sleep(0.3)
         except Exception:
             self.proc = None
 
+    def sample_now(self):
+        if self.handle is None:
+            return
+        n = self.nvml
+        try:
+            mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            try:
+                bits = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:
+                bits = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            self.samples.append((time.perf_counter(), mhz, bits))
+        except Exception:
+            pass
+
+    def _poll(self):
+        while not self.stop_flag:
+            self.sample_now()
+            time.sleep(0.004)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def begin(self):
+        self.windows.append([time.perf_counter(), None])
+
+    def end(self):
+        self.windows[-1][1] = time.perf_counter()
+
+    def _inside(self, t):
+        return any(w[0] <= t <= (w[1] if w[1] is not None else t) for w in self.windows)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            p = [x.strip() for x in r.split(",")]
-            if len(p) < 9:
-                continue
+        self.stop_flag = True
+        if self.handle is None and not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml and nvidia-smi unavailable"]}
+        if self.proc:
+            self.proc.terminate()
             try:
-                sm.append(float(p[1]))
-                mx.append(float(p[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+            mx = []
+            for t, r in self.rows:
+                p = [x.strip() for x in r.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    mhz = float(p[1]); mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                bits = 0
+                for (bit, _), v in zip(self.REASONS[:4], p[5:9]):
+                    if v.lower().startswith("active"):
+                        bits |= bit
+                self.samples.append((t, mhz, bits))
+            self.max_mhz = max(mx) if mx else None
+        elif self.thread:
+            self.thread.join(timeout=1)
+        inside = [s for s in self.samples if self._inside(s[0])]
+        # the regions are short; if the poller never fell inside one, use the samples bracketing them
+        use = inside or self.samples
+        bits = 0
+        for s in use:
+            bits |= s[2]
+        reasons = sorted(name for bit, name in self.REASONS if bits & bit)
+        return {"sm_mhz": statistics.median(s[1] for s in use) if use else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(use), "samples_in_timed_regions": len(inside), "reasons": reasons,
+                "source": "nvml" if self.handle is not None else "nvidia-smi"}
 
 
 def measured_peak_gbs():
@@ -237,34 +312,29 @@ def ours(args):
     streams = [torch.cuda.ExternalStream(s.stream(), device=torch.device("cuda", local_rank)) for s in searchers]
     L = xgm.lib()
 
-    # merge buffers for N > 1 (one all-gather of per-GPU top-k records, then the merge kernel)
+    # merge buffers for N > 1: ONE all-gather of each GPU's result slab (weights | docids | counts of its
+    # per-query top-k), then the merge kernel (Matcher::merge_mset) on every rank
     if world > 1:
         gathered = []
         for s in searchers:
-            wptr, dptr, cptr, stride = s.device_results()
-            w_local = torch.as_tensor(CudaArray(wptr, (BATCH * stride,), "<f8"), device="cuda")
-            d_local = torch.as_tensor(CudaArray(dptr, (BATCH * stride,), "<u4"), device="cuda").view(torch.int32)
-            c_local = torch.as_tensor(CudaArray(cptr, (BATCH * 8,), "<u4"), device="cuda").view(torch.int32)
-            gw = torch.empty(world * BATCH * stride, dtype=torch.float64, device="cuda")
-            gd = torch.empty(world * BATCH * stride, dtype=torch.int32, device="cuda")
-            gc = torch.empty(world * BATCH * 8, dtype=torch.int32, device="cuda")
+            base, nbytes, off_d, off_c, stride = s.device_slab()
+            local = torch.as_tensor(CudaArray(base, (nbytes,), "|u1"), device="cuda")
+            g = torch.empty(world * nbytes, dtype=torch.uint8, device="cuda")
             ow = torch.empty(BATCH * TOPK, dtype=torch.float64, device="cuda")
             od = torch.empty(BATCH * TOPK, dtype=torch.int32, device="cuda")
             on = torch.empty(BATCH, dtype=torch.int32, device="cuda")
-            gathered.append((w_local, d_local, c_local, gw, gd, gc, ow, od, on, stride))
+            gathered.append((local, g, nbytes, off_d, off_c, ow, od, on, stride))
         host_out = [(torch.empty(BATCH * TOPK, dtype=torch.float64).pin_memory(),
                      torch.empty(BATCH * TOPK, dtype=torch.int32).pin_memory(),
                      torch.empty(BATCH, dtype=torch.int32).pin_memory()) for _ in searchers]
 
     def merge_step(si: int, to_host: bool):
         """all-gather + merge on the searcher's stream; optionally copy the merged MSets to the host."""
-        w_local, d_local, c_local, gw, gd, gc, ow, od, on, stride = gathered[si]
+        local, g, nbytes, off_d, off_c, ow, od, on, stride = gathered[si]
         with torch.cuda.stream(streams[si]):
-            dist.all_gather_into_tensor(gw, w_local)
-            dist.all_gather_into_tensor(gd, d_local)
-            dist.all_gather_into_tensor(gc, c_local)
-            st = L.xgm_merge_topk_device(gw.data_ptr(), gd.data_ptr(), gc.data_ptr(), world, BATCH, stride, TOPK,
-                                         ow.data_ptr(), od.data_ptr(), on.data_ptr(), searchers[si].stream())
+            dist.all_gather_into_tensor(g, local)
+            st = L.xgm_merge_topk_device_slab(g.data_ptr(), nbytes, off_d, off_c, world, BATCH, stride, TOPK,
+                                              ow.data_ptr(), od.data_ptr(), on.data_ptr(), searchers[si].stream())
             if st != 0:
                 raise RuntimeError(L.xgm_last_error().decode())
             if to_host:
@@ -276,10 +346,12 @@ def ours(args):
     # ---- warm-up: W steps through the full API (also makes the plan of batch 0 resident) ----
     batches = [make_batch(i) for i in range(max(args.warmup, 1) + args.steps + 1)]
     for w in range(max(args.warmup, 3)):
-        searchers[0].submit(batches[w % len(batches)])
-        searchers[0].wait_raw()
-        if world > 1:
-            merge_step(0, True)
+        for si, srch in enumerate(searchers):  # every searcher (staging buffers, worker thread) is warmed up
+            srch.submit(batches[w % len(batches)], background=True)
+            if world > 1:
+                srch.launched()
+                merge_step(si, True)
+            srch.wait_raw()
     searchers[0].submit(batches[0])
     _, _, _, inf0 = searchers[0].wait_raw()
     bad = sum(1 for i in range(BATCH) if inf0[i].status != 0)
@@ -289,20 +361,26 @@ def ours(args):
     barrier()
 
     # ---- device-resident timed region: K replays of the resident plan ----
-    sampler = ClockSampler(local_rank)
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local_rank, uuid)
     sampler.start()
-    time.sleep(0.15)  # let nvidia-smi start sampling before the timed regions
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
     match_ms = []
     barrier()
+    sampler.begin()
     ev0.record(streams[0])
     for k in range(args.steps):
         searchers[0].replay()
         if world > 1:
             merge_step(0, False)
     ev1.record(streams[0])
+    sampler.sample_now()  # the K replays are queued and running
     barrier()
+    sampler.end()
     dev_ms = ev0.elapsed_time(ev1)
     # per-launch time of the dominant kernel: K more replays, reading each launch's own events
     for k in range(args.steps):
@@ -317,6 +395,7 @@ def ours(args):
 
     # ---- end-to-end timed region: K steps through submit/wait with host buffers, NSEARCH searchers ----
     barrier()
+    sampler.begin()
     t0 = time.perf_counter()
     inflight = []
     h2d = d2h = 0
@@ -324,8 +403,12 @@ def ours(args):
         si = k % NSEARCH
         if len(inflight) == NSEARCH:
             searchers[inflight.pop(0)].wait_raw()
-        searchers[si].submit(batches[1 + k])
+        # the searcher's worker thread plans + enqueues batch k while this thread scatters an earlier one
+        searchers[si].submit(batches[1 + k], background=True)
         if world > 1:
+            if inflight:
+                searchers[inflight.pop(0)].wait_raw()
+            searchers[si].launched()
             merge_step(si, True)
         inflight.append(si)
     pending = inflight[-1]
@@ -333,6 +416,7 @@ def ours(args):
         searchers[si].wait_raw()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
+    sampler.end()
     e2e_s = t1 - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:

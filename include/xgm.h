@@ -182,6 +182,14 @@ void xgm_searcher_free(xgm_searcher*);
 /* Asynchronous batch: plan on the host, copy the plan to the device, launch the kernels, start the
  * device→host copy of the results.  Returns as soon as the work is enqueued. */
 xgm_status xgm_search_submit(xgm_searcher*, const xgm_query* queries, uint32_t nq);
+/* Same, but the host half (planning = the host part of LocalSubMatch::open_post_list + Weight::init_,
+ * matcher/localsubmatch.cc:164-309, and the launches) runs on the searcher's worker thread, so the caller
+ * can scatter an earlier batch of another searcher meanwhile.  `queries` (and the term strings they point
+ * to) must stay valid until xgm_search_launched or xgm_search_wait returns; planning errors are reported
+ * there.  xgm_search_launched blocks until everything is enqueued on the searcher's stream — needed
+ * before enqueuing dependent work (the all-gather + merge of the multi-GPU path) on that stream. */
+xgm_status xgm_search_submit_async(xgm_searcher*, const xgm_query* queries, uint32_t nq);
+xgm_status xgm_search_launched(xgm_searcher*);
 /* Wait for the submitted batch and scatter results: docids/weights hold `stride` entries per query
  * (query i at [i*stride, i*stride + info[i].n)); sort_keys may be NULL. */
 xgm_status xgm_search_wait(xgm_searcher*, uint32_t* docids, double* weights, uint64_t* sort_keys,
@@ -201,6 +209,12 @@ xgm_status xgm_search_replay(xgm_searcher*);
  * weights f64[nq*max_topk], docids u32[nq*max_topk], counts u32[nq] */
 xgm_status xgm_search_device_results(xgm_searcher*, void** weights, void** docids, void** counts,
                                      uint32_t* stride);
+/* The same three arrays live in ONE device allocation ("result slab": weights at offset 0, docids at
+ * *off_docids, counts at *off_counts, *bytes in total), so that a shard's MSets travel in a single
+ * all-gather (north_star: "a single NCCL all-gather of per-GPU top-k"; the exchange that replaces
+ * handler.cc:1540-1556's per-shard prepared MSets). */
+xgm_status xgm_search_device_slab(xgm_searcher*, void** base, uint64_t* bytes, uint64_t* off_docids,
+                                  uint64_t* off_counts, uint32_t* stride);
 /* CUDA stream of the searcher (cudaStream_t as void*) and timing/roofline counters of the last batch. */
 void* xgm_searcher_stream(xgm_searcher*);
 typedef struct xgm_batch_stats {
@@ -236,6 +250,12 @@ xgm_status xgm_merge_topk_device(const void* gathered_weights, const void* gathe
                                  const void* gathered_counts, uint32_t nparts, uint32_t nq, uint32_t stride,
                                  uint32_t k, void* out_weights, void* out_docids, void* out_counts,
                                  void* cuda_stream);
+/* Same merge over nparts gathered result slabs (xgm_search_device_slab layout, slab p at
+ * gathered + p*slab_bytes). */
+xgm_status xgm_merge_topk_device_slab(const void* gathered, uint64_t slab_bytes, uint64_t off_docids,
+                                      uint64_t off_counts, uint32_t nparts, uint32_t nq, uint32_t stride,
+                                      uint32_t k, void* out_weights, void* out_docids, void* out_counts,
+                                      void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -169,3 +169,38 @@ def test_glass_db_through_public_iterators_matches_reference():
                 assert (m.matches_lower_bound, m.get_matches_estimated()) == (r.lb, r.est), f"glass[{i}] {lines[i]}"
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+def test_background_submit_matches_synchronous(edge):
+    """xgm_search_submit_async: planning + launches on the searcher's worker thread; same MSets, two
+    searchers in flight, and a second submit before wait is refused."""
+    ix, orc, names = edge
+    rng = random.Random(8)
+    batches = []
+    for b in range(4):
+        qs = []
+        for _ in range(600):  # >= 512 queries: the threaded planner runs inside the worker
+            ts = rng.sample(range(len(names)), rng.choice([1, 2, 3]))
+            qs.append(xgm.Query(rng.choice([xgm.OP_AND, xgm.OP_OR]), [names[t] for t in ts], maxitems=rng.choice([5, 40])))
+        batches.append(xgm.QueryBatch(qs))
+    s0 = xgm.Searcher(ix, max_batch=600, max_topk=64)
+    s1 = xgm.Searcher(ix, max_batch=600, max_topk=64)
+    sync = [s0.search(b) for b in batches]
+    got = [None] * 4
+    s0.submit(batches[0], background=True)
+    s1.submit(batches[1], background=True)
+    with pytest.raises(xgm.XgmError):
+        s0.submit(batches[2], background=True)
+    s0.launched()
+    got[0] = s0.wait()
+    s0.submit(batches[2], background=True)
+    got[1] = s1.wait()
+    s1.submit(batches[3], background=True)
+    got[2] = s0.wait()
+    got[3] = s1.wait()
+    for b in range(4):
+        for i, (a, m) in enumerate(zip(sync[b], got[b])):
+            assert a.status == m.status and list(a.docids) == list(m.docids), (b, i)
+            assert [float(x).hex() for x in a.weights] == [float(x).hex() for x in m.weights], (b, i)
+            assert (a.matches_lower_bound, a.matches_estimated_raw, a.matches_upper_bound) == \
+                   (m.matches_lower_bound, m.matches_estimated_raw, m.matches_upper_bound), (b, i)

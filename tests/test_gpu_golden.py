@@ -146,7 +146,7 @@ def test_device_merge_matches_reference_twophase():
     coll = sum(i.doccount for i in infos)
     tlen = sum(i.total_length for i in infos)
     nq = len(qs)
-    gw, gd, gc = [], [], []
+    gw, gd, gc, slabs = [], [], [], []
     searchers = []
     for si, ix in enumerate(shards):
         s = xgm.Searcher(ix, max_batch=nq, max_topk=K)
@@ -161,6 +161,9 @@ def test_device_merge_matches_reference_twophase():
         gw.append(torch.as_tensor(_CudaArray(wptr, (nq * K,), "<f8"), device="cuda").clone())
         gd.append(torch.as_tensor(_CudaArray(dptr, (nq * K,), "<u4"), device="cuda").view(torch.int32).clone())
         gc.append(torch.as_tensor(_CudaArray(cptr, (nq * 8,), "<u4"), device="cuda").view(torch.int32).clone())
+        base, nbytes, off_d, off_c, sstride = s.device_slab()
+        assert sstride == K and base == wptr and base + off_d == dptr and base + off_c == cptr
+        slabs.append(torch.as_tensor(_CudaArray(base, (nbytes,), "|u1"), device="cuda").clone())
     W, D, Cn = torch.cat(gw), torch.cat(gd), torch.cat(gc)
     ow = torch.zeros(nq * K, dtype=torch.float64, device="cuda")
     od = torch.zeros(nq * K, dtype=torch.int32, device="cuda")
@@ -170,6 +173,17 @@ def test_device_merge_matches_reference_twophase():
                                          od.data_ptr(), on.data_ptr(), None)
     assert st == 0, xgm.lib().xgm_last_error()
     torch.cuda.synchronize()
+    # the same merge over whole result slabs, as one all-gather lays them out
+    G = torch.cat(slabs)
+    ow2, od2, on2 = torch.zeros_like(ow), torch.zeros_like(od), torch.zeros_like(on)
+    st = xgm.lib().xgm_merge_topk_device_slab(G.data_ptr(), nbytes, off_d, off_c, n, nq, K, K, ow2.data_ptr(),
+                                              od2.data_ptr(), on2.data_ptr(), None)
+    assert st == 0, xgm.lib().xgm_last_error()
+    torch.cuda.synchronize()
+    assert torch.equal(on, on2)
+    for i in range(nq):
+        c = int(on[i])
+        assert torch.equal(od[i * K:i * K + c], od2[i * K:i * K + c]) and torch.equal(ow[i * K:i * K + c], ow2[i * K:i * K + c])
     ow, od, on = ow.cpu().numpy().reshape(nq, K), od.cpu().numpy().view(np.uint32).reshape(nq, K), on.cpu().numpy()
     for i, q in enumerate(qs):
         m = q["maxitems"]

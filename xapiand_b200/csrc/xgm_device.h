@@ -76,8 +76,8 @@ cudaError_t xgm_launch_topk(const XgmKernelParams& p, uint32_t nq, cudaStream_t 
 cudaError_t xgm_launch_decode(const XgmKernelParams& p, uint32_t blk_begin, uint32_t nblocks, uint32_t* out_d,
                               uint32_t* out_w, cudaStream_t s);
 size_t xgm_topk_smem_bytes(uint32_t keep_cap);
-cudaError_t xgm_launch_merge(const double* gw, const uint32_t* gd, const XgmDevResult* ginfo, uint32_t nparts, uint32_t nq,
-                             uint32_t stride, uint32_t k, double* out_w, uint32_t* out_d, uint32_t* out_n,
+cudaError_t xgm_launch_merge(const double* gw, const uint32_t* gd, const XgmDevResult* ginfo, size_t part_w, size_t part_d,
+                             size_t part_info, uint32_t nparts, uint32_t nq, uint32_t stride, uint32_t k, double* out_w, uint32_t* out_d, uint32_t* out_n,
                              cudaStream_t s);
 int xgm_and_occupancy_blocks_per_sm();
 

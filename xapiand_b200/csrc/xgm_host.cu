@@ -12,7 +12,9 @@
 #include <cstdlib>
 #include <chrono>
 #include <cstring>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -116,6 +118,11 @@ struct xgm_index {
     uint64_t* d_vals[XGM_MAX_SLOTS] = {};
     uint64_t slot_max[XGM_MAX_SLOTS] = {};
     int sm_count = 148;
+    /* Large batches fill the GPU on their own: the kernels of all searchers of this index go through one
+     * FIFO compute stream (copies stay on the searchers' streams), so that batch k's results are not
+     * delayed by batch k+1's kernels sharing the SMs with them. */
+    mutable cudaStream_t compute_stream = nullptr;
+    mutable std::mutex launch_mu;
 };
 
 /* Compressed form of a contiguous range of terms, produced by one builder thread. */
@@ -397,6 +404,7 @@ extern "C" void xgm_index_close(xgm_index* ix) {
     cudaFree(ix->d_hdr); cudaFree(ix->d_docs); cudaFree(ix->d_tfs); cudaFree(ix->d_doclen);
     cudaFree(ix->d_bitmaps); cudaFree(ix->d_ranks);
     for (int s = 0; s < XGM_MAX_SLOTS; ++s) { cudaFree(ix->d_voff[s]); cudaFree(ix->d_vals[s]); }
+    if (ix->compute_stream) cudaStreamDestroy(ix->compute_stream);
     delete ix;
 }
 
@@ -690,6 +698,8 @@ struct xgm_searcher {
     uint32_t max_batch = 0, max_topk = 0, match_cap = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_done = nullptr; /* hand-over between the copy stream and the shared compute stream */
+    bool shared_compute = true;
     /* pinned host staging */
     XgmDevQuery* h_queries = nullptr;
     XgmWorkItem* h_items = nullptr;
@@ -727,6 +737,8 @@ struct xgm_searcher {
     uint32_t* d_out_d = nullptr;
     uint64_t* d_out_k = nullptr;
     XgmDevResult* d_info = nullptr;
+    unsigned char* d_slab = nullptr; /* d_out_w | d_out_d | d_info in one allocation: one all-gather moves a shard's MSets */
+    size_t slab_bytes = 0, slab_off_d = 0, slab_off_info = 0;
     /* last batch */
     std::vector<PlannedQuery> plan;
     uint32_t nq = 0, nitems = 0, nitems_or = 0, nitems_bm = 0;
@@ -735,20 +747,56 @@ struct xgm_searcher {
     int grid = 0, grid_or = 0, grid_and2 = 0, grid_bm = 0;
     int and_version = 1; /* 1 = warp-autonomous kernel, 2 = chunked CTA kernel (XGM_AND_KERNEL env) */
     XgmKernelParams params;
+    /* xgm_search_submit_async: a worker thread plans and enqueues the batch while the caller scatters the
+     * results of an earlier one */
+    std::thread worker;
+    std::mutex mu;
+    std::condition_variable cv;
+    enum { JOB_NONE = 0, JOB_QUEUED, JOB_RUNNING, JOB_DONE } job = JOB_NONE;
+    bool worker_exit = false;
+    const xgm_query* job_queries = nullptr;
+    uint32_t job_nq = 0;
+    xgm_status job_status = XGM_OK;
+    char job_err[512] = "";
 };
+
+/* Block until the worker (if any) has planned and enqueued the batch handed to xgm_search_submit_async;
+ * its status and error text become the caller's. */
+static xgm_status join_async(xgm_searcher* s) {
+    std::unique_lock<std::mutex> lk(s->mu);
+    if (s->job == xgm_searcher::JOB_NONE) return XGM_OK;
+    s->cv.wait(lk, [&] { return s->job == xgm_searcher::JOB_DONE; });
+    s->job = xgm_searcher::JOB_NONE;
+    if (s->job_status != XGM_OK) {
+        s->pending = false;
+        return fail(s->job_status, "%s", s->job_err);
+    }
+    return XGM_OK;
+}
 
 extern "C" void xgm_searcher_free(xgm_searcher* s) {
     if (!s) return;
+    if (s->worker.joinable()) {
+        {
+            std::unique_lock<std::mutex> lk(s->mu);
+            s->cv.wait(lk, [&] { return s->job == xgm_searcher::JOB_NONE || s->job == xgm_searcher::JOB_DONE; });
+            s->worker_exit = true;
+        }
+        s->cv.notify_all();
+        s->worker.join();
+    }
     cudaSetDevice(s->ix->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFreeHost(s->h_queries); cudaFreeHost(s->h_items); cudaFreeHost(s->h_items_or); cudaFreeHost(s->h_items_bm); cudaFreeHost(s->h_out_w); cudaFreeHost(s->h_out_d);
     cudaFreeHost(s->h_out_k); cudaFreeHost(s->h_info);
     cudaFree(s->d_queries); cudaFree(s->d_items); cudaFree(s->d_items_or); cudaFree(s->d_items_bm); cudaFree(s->d_exp[0]); cudaFree(s->d_exp[1]); cudaFree(s->d_exp[2]);
     for (int w = 0; w < 3; ++w) { if (s->h_levels[w]) cudaFreeHost(s->h_levels[w]); cudaFree(s->d_levels[w]); } cudaFree(s->d_ctrl); cudaFree(s->d_match_w); cudaFree(s->d_match_d);
-    cudaFree(s->d_match_k); cudaFree(s->d_pool_w); cudaFree(s->d_pool_d); cudaFree(s->d_pool_k); cudaFree(s->d_out_w); cudaFree(s->d_out_d); cudaFree(s->d_out_k); cudaFree(s->d_info);
+    cudaFree(s->d_match_k); cudaFree(s->d_pool_w); cudaFree(s->d_pool_d); cudaFree(s->d_pool_k); cudaFree(s->d_slab); cudaFree(s->d_out_k);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->ev2) cudaEventDestroy(s->ev2);
+    if (s->ev_in) cudaEventDestroy(s->ev_in);
+    if (s->ev_done) cudaEventDestroy(s->ev_done);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -808,6 +856,13 @@ extern "C" xgm_status xgm_searcher_new(const xgm_index* ix, uint32_t max_batch, 
     if (s->keep_cap > s->match_cap) s->keep_cap = s->match_cap;
     CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&s->ev0)); CUDA_TRY(cudaEventCreate(&s->ev1)); CUDA_TRY(cudaEventCreate(&s->ev2));
+    CUDA_TRY(cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming));
+    if (const char* e = getenv("XGM_SHARED_COMPUTE")) s->shared_compute = atoi(e) != 0;
+    {
+        std::lock_guard<std::mutex> lk(ix->launch_mu);
+        if (!ix->compute_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ix->compute_stream, cudaStreamNonBlocking));
+    }
     size_t nq = max_batch, ns = (size_t)max_batch * max_topk, nm = (size_t)max_batch * s->match_cap;
     CUDA_TRY(cudaMallocHost(&s->h_queries, nq * sizeof(XgmDevQuery)));
     CUDA_TRY(cudaMallocHost(&s->h_out_w, ns * 8)); CUDA_TRY(cudaMallocHost(&s->h_out_d, ns * 4));
@@ -816,13 +871,22 @@ extern "C" xgm_status xgm_searcher_new(const xgm_index* ix, uint32_t max_batch, 
     s->ctrl_bytes = 64 + nq * sizeof(XgmQState) + nq * XGM_NBINS * 4;
     CUDA_TRY(cudaMalloc(&s->d_ctrl, s->ctrl_bytes));
     CUDA_TRY(cudaMalloc(&s->d_match_w, nm * 8)); CUDA_TRY(cudaMalloc(&s->d_match_d, nm * 4)); CUDA_TRY(cudaMalloc(&s->d_match_k, nm * 8));
-    CUDA_TRY(cudaMalloc(&s->d_out_w, ns * 8)); CUDA_TRY(cudaMalloc(&s->d_out_d, ns * 4)); CUDA_TRY(cudaMalloc(&s->d_out_k, ns * 8));
+    {
+        auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        s->slab_off_d = up(ns * 8);
+        s->slab_off_info = s->slab_off_d + up(ns * 4);
+        s->slab_bytes = s->slab_off_info + up(nq * sizeof(XgmDevResult));
+        CUDA_TRY(cudaMalloc(&s->d_slab, s->slab_bytes));
+        s->d_out_w = reinterpret_cast<double*>(s->d_slab);
+        s->d_out_d = reinterpret_cast<uint32_t*>(s->d_slab + s->slab_off_d);
+        s->d_info = reinterpret_cast<XgmDevResult*>(s->d_slab + s->slab_off_info);
+    }
+    CUDA_TRY(cudaMalloc(&s->d_out_k, ns * 8));
     /* overflow pool: room for the tie mass of a few pathological queries per batch (doccount entries at least) */
     s->pool_total = std::max<uint32_t>(1u << 20, std::min<uint32_t>(1u << 25, 2 * ix->doccount + (1u << 16)));
     if (const char* e = getenv("XGM_POOL_ENTRIES")) s->pool_total = (uint32_t)strtoul(e, nullptr, 10);
     CUDA_TRY(cudaMalloc(&s->d_pool_w, (size_t)s->pool_total * 8)); CUDA_TRY(cudaMalloc(&s->d_pool_d, (size_t)s->pool_total * 4));
     CUDA_TRY(cudaMalloc(&s->d_pool_k, (size_t)s->pool_total * 8));
-    CUDA_TRY(cudaMalloc(&s->d_info, nq * sizeof(XgmDevResult)));
     xgm_status st = ensure_items(s.get(), 4096, 0);
     if (st != XGM_OK) return st;
     st = ensure_items(s.get(), 4096, 1);
@@ -1114,8 +1178,18 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
 
 static xgm_status launch_batch(xgm_searcher* s) {
     XgmKernelParams& p = s->params;
-    CUDA_TRY(cudaMemsetAsync(s->d_ctrl, 0, 64 + (size_t)s->max_batch * sizeof(XgmQState), s->stream));
-    CUDA_TRY(cudaMemsetAsync(p.hist, 0, (size_t)s->nq * XGM_NBINS * 4, s->stream));
+    /* batches that fill the GPU on their own run their kernels on the index's FIFO compute stream; small
+     * ones (concurrent single queries of many host threads) stay on the searcher's stream and share the SMs */
+    const bool shared = s->shared_compute && s->nq >= 256;
+    cudaStream_t cs = shared ? s->ix->compute_stream : s->stream;
+    std::unique_lock<std::mutex> lk(s->ix->launch_mu, std::defer_lock);
+    if (shared) {
+        CUDA_TRY(cudaEventRecord(s->ev_in, s->stream));
+        lk.lock(); /* one batch's launches stay contiguous in the shared stream */
+        CUDA_TRY(cudaStreamWaitEvent(cs, s->ev_in, 0));
+    }
+    CUDA_TRY(cudaMemsetAsync(s->d_ctrl, 0, 64 + (size_t)s->max_batch * sizeof(XgmQState), cs));
+    CUDA_TRY(cudaMemsetAsync(p.hist, 0, (size_t)s->nq * XGM_NBINS * 4, cs));
     s->stats.kernel_launches = 0;
     p.pass = 0;
     {
@@ -1126,41 +1200,43 @@ static xgm_status launch_batch(xgm_searcher* s) {
             if (w == 1) {
                 for (const auto& g : s->or_groups) {
                     CUDA_TRY(xgm_launch_expand(segs[1] + g.seg_off, g.nseg, g.total, s->d_levels[1] + g.level_off, g.nlevels,
-                                               s->bpi, s->d_exp[1] + g.out_off, s->stream));
+                                               s->bpi, s->d_exp[1] + g.out_off, cs));
                     s->stats.kernel_launches++;
                 }
             } else {
-                CUDA_TRY(xgm_launch_expand(segs[w], s->nseg[w], totals[w], s->d_levels[w], s->nlevels[w], s->bpi, s->d_exp[w], s->stream));
+                CUDA_TRY(xgm_launch_expand(segs[w], s->nseg[w], totals[w], s->d_levels[w], s->nlevels[w], s->bpi, s->d_exp[w], cs));
                 s->stats.kernel_launches++;
             }
         }
     }
-    CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+    CUDA_TRY(cudaEventRecord(s->ev0, cs));
     auto launch_and = [&](const XgmKernelParams& pp) {
-        return s->and_version == 1 ? xgm_launch_and(pp, s->grid, s->stream) : xgm_launch_and2(pp, s->grid_and2, s->stream);
+        return s->and_version == 1 ? xgm_launch_and(pp, s->grid, cs) : xgm_launch_and2(pp, s->grid_and2, cs);
     };
-    if (s->nitems_bm) { CUDA_TRY(xgm_launch_and_bm(p, s->grid_bm, s->stream)); s->stats.kernel_launches++; }
+    if (s->nitems_bm) { CUDA_TRY(xgm_launch_and_bm(p, s->grid_bm, cs)); s->stats.kernel_launches++; }
     if (s->nitems) { CUDA_TRY(launch_and(p)); s->stats.kernel_launches++; }
-    if (s->nitems_or) { CUDA_TRY(xgm_launch_or(p, s->grid_or, s->stream)); s->stats.kernel_launches++; }
-    CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
-    CUDA_TRY(xgm_launch_topk(p, s->nq, s->stream));
+    if (s->nitems_or) { CUDA_TRY(xgm_launch_or(p, s->grid_or, cs)); s->stats.kernel_launches++; }
+    CUDA_TRY(cudaEventRecord(s->ev1, cs));
+    CUDA_TRY(xgm_launch_topk(p, s->nq, cs));
     s->stats.kernel_launches++;
     /* second pass: only queries whose candidate buffer overflowed do any work (device-side flag) */
     XgmKernelParams p2 = p;
     p2.pass = 1;
-    if (s->nitems_bm) { CUDA_TRY(xgm_launch_and_bm(p2, s->grid_bm, s->stream)); s->stats.kernel_launches++; }
+    if (s->nitems_bm) { CUDA_TRY(xgm_launch_and_bm(p2, s->grid_bm, cs)); s->stats.kernel_launches++; }
     if (s->nitems) { CUDA_TRY(launch_and(p2)); s->stats.kernel_launches++; }
-    if (s->nitems_or) { CUDA_TRY(xgm_launch_or(p2, s->grid_or, s->stream)); s->stats.kernel_launches++; }
-    CUDA_TRY(xgm_launch_topk(p2, s->nq, s->stream));
+    if (s->nitems_or) { CUDA_TRY(xgm_launch_or(p2, s->grid_or, cs)); s->stats.kernel_launches++; }
+    CUDA_TRY(xgm_launch_topk(p2, s->nq, cs));
     s->stats.kernel_launches++;
-    CUDA_TRY(cudaEventRecord(s->ev2, s->stream));
+    CUDA_TRY(cudaEventRecord(s->ev2, cs));
+    if (shared) {
+        CUDA_TRY(cudaEventRecord(s->ev_done, cs));
+        lk.unlock();
+        CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_done, 0));
+    }
     return XGM_OK;
 }
 
-extern "C" xgm_status xgm_search_submit(xgm_searcher* s, const xgm_query* queries, uint32_t nq) {
-    if (!s || !queries || nq == 0) return fail(XGM_E_INVALID, "bad arguments");
-    if (nq > s->max_batch) return fail(XGM_E_INVALID, "batch %u > max_batch %u", nq, s->max_batch);
-    if (s->pending) return fail(XGM_E_INVALID, "previous batch not waited for");
+static xgm_status submit_impl(xgm_searcher* s, const xgm_query* queries, uint32_t nq) {
     const auto t_submit0 = std::chrono::steady_clock::now();
     CUDA_TRY(cudaSetDevice(s->ix->device));
     s->plan.resize(nq);
@@ -1387,10 +1463,68 @@ static void finish_info(const PlannedQuery& pq, const XgmDevResult* dr, const do
     }
 }
 
+extern "C" xgm_status xgm_search_submit(xgm_searcher* s, const xgm_query* queries, uint32_t nq) {
+    if (!s || !queries || nq == 0) return fail(XGM_E_INVALID, "bad arguments");
+    if (nq > s->max_batch) return fail(XGM_E_INVALID, "batch %u > max_batch %u", nq, s->max_batch);
+    if (s->pending) return fail(XGM_E_INVALID, "previous batch not waited for");
+    return submit_impl(s, queries, nq);
+}
+
+static void worker_main(xgm_searcher* s) {
+    for (;;) {
+        const xgm_query* queries;
+        uint32_t nq;
+        {
+            std::unique_lock<std::mutex> lk(s->mu);
+            s->cv.wait(lk, [&] { return s->worker_exit || s->job == xgm_searcher::JOB_QUEUED; });
+            if (s->worker_exit) return;
+            s->job = xgm_searcher::JOB_RUNNING;
+            queries = s->job_queries;
+            nq = s->job_nq;
+        }
+        g_err[0] = 0;
+        const xgm_status st = submit_impl(s, queries, nq);
+        {
+            std::lock_guard<std::mutex> lk(s->mu);
+            s->job_status = st;
+            snprintf(s->job_err, sizeof(s->job_err), "%s", g_err);
+            s->job = xgm_searcher::JOB_DONE;
+        }
+        s->cv.notify_all();
+    }
+}
+
+extern "C" xgm_status xgm_search_submit_async(xgm_searcher* s, const xgm_query* queries, uint32_t nq) {
+    if (!s || !queries || nq == 0) return fail(XGM_E_INVALID, "bad arguments");
+    if (nq > s->max_batch) return fail(XGM_E_INVALID, "batch %u > max_batch %u", nq, s->max_batch);
+    if (s->pending) return fail(XGM_E_INVALID, "previous batch not waited for");
+    if (!s->worker.joinable()) s->worker = std::thread(worker_main, s);
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        s->job_queries = queries;
+        s->job_nq = nq;
+        s->job_status = XGM_OK;
+        s->job = xgm_searcher::JOB_QUEUED;
+        s->pending = true;
+    }
+    s->cv.notify_all();
+    return XGM_OK;
+}
+
+extern "C" xgm_status xgm_search_launched(xgm_searcher* s) {
+    if (!s) return fail(XGM_E_INVALID, "null argument");
+    if (!s->pending) return fail(XGM_E_INVALID, "no batch submitted");
+    return join_async(s);
+}
+
 extern "C" xgm_status xgm_search_wait(xgm_searcher* s, uint32_t* docids, double* weights, uint64_t* sort_keys,
                                       uint32_t stride, xgm_mset_info* info) {
     if (!s || !info) return fail(XGM_E_INVALID, "null argument");
     if (!s->pending) return fail(XGM_E_INVALID, "no batch submitted");
+    {
+        xgm_status jst = join_async(s);
+        if (jst != XGM_OK) return jst;
+    }
     CUDA_TRY(cudaSetDevice(s->ix->device));
     cudaError_t e = cudaStreamSynchronize(s->stream);
     s->pending = false;
@@ -1442,6 +1576,17 @@ extern "C" xgm_status xgm_search_device_results(xgm_searcher* s, void** weights,
     if (weights) *weights = s->d_out_w;
     if (docids) *docids = s->d_out_d;
     if (counts) *counts = s->d_info;
+    if (stride) *stride = s->max_topk;
+    return XGM_OK;
+}
+
+extern "C" xgm_status xgm_search_device_slab(xgm_searcher* s, void** base, uint64_t* bytes, uint64_t* off_docids,
+                                             uint64_t* off_counts, uint32_t* stride) {
+    if (!s) return fail(XGM_E_INVALID, "null argument");
+    if (base) *base = s->d_slab;
+    if (bytes) *bytes = s->slab_bytes;
+    if (off_docids) *off_docids = s->slab_off_d;
+    if (off_counts) *off_counts = s->slab_off_info;
     if (stride) *stride = s->max_topk;
     return XGM_OK;
 }
@@ -1532,10 +1677,29 @@ extern "C" xgm_status xgm_merge_topk_device(const void* gw, const void* gd, cons
                                             void* cuda_stream) {
     if (!gw || !gd || !ginfo || !out_w || !out_d || !out_n || nparts == 0 || nq == 0 || k == 0 || k > stride)
         return fail(XGM_E_INVALID, "bad arguments");
-    if ((size_t)nparts * k * 12 > 200 * 1024) return fail(XGM_E_INVALID, "nparts*k too large for the merge kernel");
+    if ((size_t)nparts * k * 12 > 200 * 1024 || nparts > 64) return fail(XGM_E_INVALID, "nparts*k too large for the merge kernel");
     CUDA_TRY(xgm_launch_merge(static_cast<const double*>(gw), static_cast<const uint32_t*>(gd),
-                              static_cast<const XgmDevResult*>(ginfo), nparts, nq, stride, k, static_cast<double*>(out_w),
+                              static_cast<const XgmDevResult*>(ginfo), (size_t)nq * stride * 8, (size_t)nq * stride * 4,
+                              (size_t)nq * sizeof(XgmDevResult), nparts, nq, stride, k, static_cast<double*>(out_w),
                               static_cast<uint32_t*>(out_d), static_cast<uint32_t*>(out_n),
                               static_cast<cudaStream_t>(cuda_stream)));
+    return XGM_OK;
+}
+
+extern "C" xgm_status xgm_merge_topk_device_slab(const void* gathered, uint64_t slab_bytes, uint64_t off_docids,
+                                                 uint64_t off_counts, uint32_t nparts, uint32_t nq, uint32_t stride,
+                                                 uint32_t k, void* out_w, void* out_d, void* out_n, void* cuda_stream) {
+    if (!gathered || !out_w || !out_d || !out_n || nparts == 0 || nq == 0 || k == 0 || k > stride)
+        return fail(XGM_E_INVALID, "bad arguments");
+    if ((slab_bytes | off_docids | off_counts) & 7) return fail(XGM_E_INVALID, "slab offsets must be 8-byte aligned");
+    if (off_docids < (uint64_t)nq * stride * 8 || off_counts < off_docids + (uint64_t)nq * stride * 4 ||
+        slab_bytes < off_counts + (uint64_t)nq * sizeof(XgmDevResult))
+        return fail(XGM_E_INVALID, "slab layout too small for nq*stride records");
+    if ((size_t)nparts * k * 12 > 200 * 1024 || nparts > 64) return fail(XGM_E_INVALID, "nparts*k too large for the merge kernel");
+    const unsigned char* g = static_cast<const unsigned char*>(gathered);
+    CUDA_TRY(xgm_launch_merge(reinterpret_cast<const double*>(g), reinterpret_cast<const uint32_t*>(g + off_docids),
+                              reinterpret_cast<const XgmDevResult*>(g + off_counts), slab_bytes, slab_bytes, slab_bytes,
+                              nparts, nq, stride, k, static_cast<double*>(out_w), static_cast<uint32_t*>(out_d),
+                              static_cast<uint32_t*>(out_n), static_cast<cudaStream_t>(cuda_stream)));
     return XGM_OK;
 }

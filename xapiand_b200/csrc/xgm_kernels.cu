@@ -1644,46 +1644,70 @@ __global__ void __launch_bounds__(TOPK_THREADS) xgm_topk_kernel(XgmKernelParams 
 /* ------------------------------------------------------------------ multi-shard merge */
 
 /* Matcher::merge_mset (matcher.cc:653-782) on the device, after an all-gather of the per-GPU top-k
- * records: one CTA per query rank-sorts the nparts*k candidates under (weight desc, docid asc) with
- * docids mapped through unshard() (backends/multi.h:66-70). */
+ * records: one CTA per query merges the nparts sorted lists under (weight desc, docid asc) with docids
+ * mapped through unshard() (backends/multi.h:66-70).  Every part arrives sorted in that very order
+ * (unshard is monotone within a part), so the rank of a record is its index in its own part plus, for
+ * every other part, the number of records there that rank before it — a binary search each. */
+#define XGM_MERGE_MAX_PARTS 64
 __global__ void __launch_bounds__(256) xgm_merge_kernel(const double* __restrict__ gw, const uint32_t* __restrict__ gd,
-                                                        const XgmDevResult* __restrict__ ginfo, uint32_t nparts,
+                                                        const XgmDevResult* __restrict__ ginfo, size_t part_w,
+                                                        size_t part_d, size_t part_info, uint32_t nparts,
                                                         uint32_t nq, uint32_t stride, uint32_t k, double* out_w,
                                                         uint32_t* out_d, uint32_t* out_n) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sw = reinterpret_cast<double*>(smem_raw);
     uint32_t* sd = reinterpret_cast<uint32_t*>(sw + (size_t)nparts * k);
-    __shared__ uint32_t s_n;
+    __shared__ uint32_t s_cnt[XGM_MERGE_MAX_PARTS];
     const uint32_t qi = blockIdx.x;
-    if (threadIdx.x == 0) s_n = 0;
+    /* part strides are in bytes: the parts are either three gathered arrays or whole result slabs */
+    for (uint32_t part = threadIdx.x; part < nparts; part += blockDim.x) {
+        const XgmDevResult* pi = reinterpret_cast<const XgmDevResult*>(reinterpret_cast<const unsigned char*>(ginfo) + part * part_info);
+        s_cnt[part] = min(pi[qi].n, k);
+    }
     __syncthreads();
-    for (uint32_t part = 0; part < nparts; ++part) {
-        const uint32_t n = min(ginfo[(size_t)part * nq + qi].n, k);
-        const size_t off = ((size_t)part * nq + qi) * stride;
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-            const uint32_t pos = atomicAdd(&s_n, 1u);
-            sw[pos] = gw[off + i];
-            sd[pos] = (gd[off + i] - 1u) * nparts + part + 1u;
+    const size_t off = (size_t)qi * stride;
+    for (uint32_t x = threadIdx.x; x < nparts * k; x += blockDim.x) {
+        const uint32_t part = x / k, i = x - part * k;
+        if (i < s_cnt[part]) {
+            const double* pw = reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(gw) + part * part_w);
+            const uint32_t* pd = reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(gd) + part * part_d);
+            sw[x] = pw[off + i];
+            sd[x] = (pd[off + i] - 1u) * nparts + part + 1u;
         }
     }
     __syncthreads();
-    const uint32_t n = s_n;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const double wi = sw[i];
-        const uint32_t di = sd[i];
-        uint32_t rank = 0;
-        for (uint32_t j = 0; j < n; ++j) rank += (sw[j] > wi || (sw[j] == wi && sd[j] < di)) ? 1u : 0u;
+    uint32_t total = 0;
+    for (uint32_t part = 0; part < nparts; ++part) total += s_cnt[part];
+    for (uint32_t x = threadIdx.x; x < nparts * k; x += blockDim.x) {
+        const uint32_t part = x / k, i = x - part * k;
+        if (i >= s_cnt[part]) continue;
+        const double wi = sw[x];
+        const uint32_t di = sd[x];
+        uint32_t rank = i;
+        for (uint32_t o = 0; o < nparts && rank < k; ++o) {
+            if (o == part) continue;
+            const double* ow = sw + (size_t)o * k;
+            const uint32_t* od = sd + (size_t)o * k;
+            uint32_t lo = 0, hi = s_cnt[o]; /* first record of part o that does not rank before (wi, di) */
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                const double wm = ow[mid];
+                if (wm > wi || (wm == wi && od[mid] < di)) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
         if (rank < k) {
             out_w[(size_t)qi * k + rank] = wi;
             out_d[(size_t)qi * k + rank] = di;
         }
     }
-    if (threadIdx.x == 0) out_n[qi] = n < k ? n : k;
+    if (threadIdx.x == 0) out_n[qi] = total < k ? total : k;
 }
 
-cudaError_t xgm_launch_merge(const double* gw, const uint32_t* gd, const XgmDevResult* ginfo, uint32_t nparts, uint32_t nq,
-                             uint32_t stride, uint32_t k, double* out_w, uint32_t* out_d, uint32_t* out_n,
+cudaError_t xgm_launch_merge(const double* gw, const uint32_t* gd, const XgmDevResult* ginfo, size_t part_w, size_t part_d,
+                             size_t part_info, uint32_t nparts, uint32_t nq, uint32_t stride, uint32_t k, double* out_w, uint32_t* out_d, uint32_t* out_n,
                              cudaStream_t s) {
+    if (nparts > XGM_MERGE_MAX_PARTS) return cudaErrorInvalidValue;
     size_t smem = (size_t)nparts * k * 12;
     static size_t attr_bytes = 48 * 1024;
     if (smem > attr_bytes) {
@@ -1691,7 +1715,7 @@ cudaError_t xgm_launch_merge(const double* gw, const uint32_t* gd, const XgmDevR
         if (e != cudaSuccess) return e;
         attr_bytes = smem;
     }
-    xgm_merge_kernel<<<nq, 256, smem, s>>>(gw, gd, ginfo, nparts, nq, stride, k, out_w, out_d, out_n);
+    xgm_merge_kernel<<<nq, 256, smem, s>>>(gw, gd, ginfo, part_w, part_d, part_info, nparts, nq, stride, k, out_w, out_d, out_n);
     return cudaGetLastError();
 }
 

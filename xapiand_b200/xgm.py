@@ -28,8 +28,10 @@ EXPORTS = [
     "xgm_builder_add_value_slot", "xgm_builder_finish", "xgm_builder_free", "xgm_index_build_synthetic",
     "xgm_index_load_flat", "xgm_index_close", "xgm_index_info_get", "xgm_term_stats_get",
     "xgm_index_decode_term", "xgm_searcher_new", "xgm_searcher_free", "xgm_search_submit", "xgm_search_wait",
-    "xgm_search_batch", "xgm_search", "xgm_search_replay", "xgm_search_device_results", "xgm_searcher_stream",
-    "xgm_search_last_stats", "xgm_unshard", "xgm_merge_msets", "xgm_merge_topk_device",
+    "xgm_search_submit_async", "xgm_search_launched", "xgm_search_batch", "xgm_search", "xgm_search_replay",
+    "xgm_search_device_results", "xgm_search_device_slab",
+    "xgm_searcher_stream", "xgm_search_last_stats", "xgm_unshard", "xgm_merge_msets", "xgm_merge_topk_device",
+    "xgm_merge_topk_device_slab",
 ]
 
 
@@ -121,6 +123,8 @@ def lib():
     L.xgm_searcher_free.argtypes = [C.c_void_p]
     L.xgm_searcher_free.restype = None
     L.xgm_search_submit.argtypes = [C.c_void_p, C.POINTER(CQuery), C.c_uint32]
+    L.xgm_search_submit_async.argtypes = [C.c_void_p, C.POINTER(CQuery), C.c_uint32]
+    L.xgm_search_launched.argtypes = [C.c_void_p]
     L.xgm_search_wait.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(MSetInfo)]
     L.xgm_search_batch.argtypes = [C.c_void_p, C.POINTER(CQuery), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_uint32, C.POINTER(MSetInfo)]
@@ -129,6 +133,10 @@ def lib():
     L.xgm_search_replay.argtypes = [C.c_void_p]
     L.xgm_search_device_results.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                             C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]
+    L.xgm_search_device_slab.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+    L.xgm_merge_topk_device_slab.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32,
+                                             C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.xgm_searcher_stream.argtypes = [C.c_void_p]
     L.xgm_searcher_stream.restype = C.c_void_p
     L.xgm_search_last_stats.argtypes = [C.c_void_p, C.POINTER(BatchStats)]
@@ -379,10 +387,18 @@ class Searcher:
         except Exception:
             pass
 
-    def submit(self, batch: QueryBatch):
-        self._batch = batch
+    def submit(self, batch: QueryBatch, background: bool = False):
+        """Plan + enqueue a batch.  background=True hands the host half to the searcher's worker thread
+        (xgm_search_submit_async); call launched() before enqueuing dependent work on stream()."""
+        if background:
+            _check(lib().xgm_search_submit_async(self._h, batch.arr, batch.n))
+        else:
+            _check(lib().xgm_search_submit(self._h, batch.arr, batch.n))
+        self._batch = batch  # keeps the query array and term strings alive until wait
         self._nq = batch.n
-        _check(lib().xgm_search_submit(self._h, batch.arr, batch.n))
+
+    def launched(self):
+        _check(lib().xgm_search_launched(self._h))
 
     def wait_raw(self):
         """Results left in the searcher's flat host buffers (stride = max_topk)."""
@@ -425,6 +441,12 @@ class Searcher:
         w, d, c, s = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint32()
         _check(lib().xgm_search_device_results(self._h, C.byref(w), C.byref(d), C.byref(c), C.byref(s)))
         return w.value, d.value, c.value, s.value
+
+    def device_slab(self):
+        """(base pointer, bytes, docids offset, counts offset, stride) of the one-allocation result slab."""
+        b, n, od, oc, s = C.c_void_p(), C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint32()
+        _check(lib().xgm_search_device_slab(self._h, C.byref(b), C.byref(n), C.byref(od), C.byref(oc), C.byref(s)))
+        return b.value, n.value, od.value, oc.value, s.value
 
 
 def unshard(docids: np.ndarray, shard: int, nshards: int) -> np.ndarray:
