@@ -115,6 +115,9 @@ xgm_status xgm_term_stats_get(const xgm_index*, const char* term, uint32_t term_
 /* Round-trip check: decode a term's posting list on the device back into flat arrays (capacity n). */
 xgm_status xgm_index_decode_term(const xgm_index*, uint32_t term_id, uint32_t* docids, uint32_t* wdfs,
                                  uint32_t capacity, uint32_t* n);
+/* Document lengths of docids [first_docid, first_docid + n) copied from the dense HBM column (0 for unused
+ * docids) — Database::get_doclength (api/database.cc:347), for tests and tools; not on the query path. */
+xgm_status xgm_index_copy_doclengths(const xgm_index*, uint32_t first_docid, uint32_t n, uint32_t* out);
 
 /* ---- queries ------------------------------------------------------------------------------ */
 enum { XGM_OP_AND = 0, XGM_OP_OR = 1 };                      /* Query::OP_AND / OP_OR of LEAF_TERMs */

@@ -1602,6 +1602,14 @@ extern "C" xgm_status xgm_search_last_stats(xgm_searcher* s, xgm_batch_stats* ou
     return XGM_OK;
 }
 
+extern "C" xgm_status xgm_index_copy_doclengths(const xgm_index* ix, uint32_t first_docid, uint32_t n, uint32_t* out) {
+    if (!ix || (n && !out)) return fail(XGM_E_INVALID, "null argument");
+    if ((uint64_t)first_docid + n > (uint64_t)ix->lastdocid + 1) return fail(XGM_E_INVALID, "docid range beyond lastdocid");
+    CUDA_TRY(cudaSetDevice(ix->device));
+    if (n) CUDA_TRY(cudaMemcpy(out, ix->d_doclen + first_docid, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return XGM_OK;
+}
+
 /* ------------------------------------------------------------------ multi-shard merge */
 
 extern "C" void xgm_unshard(uint32_t* docids, uint32_t n, uint32_t shard, uint32_t nshards) {

@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(HERE, "libxgm.so")
 
 OP_AND, OP_OR = 0, 1
 SORT_REL, SORT_VAL_REL, SORT_VAL, SORT_REL_VAL = 0, 1, 2, 3
+MSET_BOUNDS_APPROX, MSET_COUNT_LOWER_BOUND = 1, 2  # xgm_mset_info.flags (include/xgm.h)
 FILTER_NONE, FILTER_VALUE_RANGE, FILTER_MULTI_RANGE = 0, 1, 2
 OK, E_INVALID, E_UNIMPLEMENTED, E_CUDA, E_NOMEM, E_IO, E_STALE, E_NODEVICE = range(8)
 MAX_TERMS = 16
@@ -27,7 +28,7 @@ EXPORTS = [
     "xgm_last_error", "xgm_abi_version", "xgm_builder_new", "xgm_builder_set_docs", "xgm_builder_add_term",
     "xgm_builder_add_value_slot", "xgm_builder_finish", "xgm_builder_free", "xgm_index_build_synthetic",
     "xgm_index_load_flat", "xgm_index_close", "xgm_index_info_get", "xgm_term_stats_get",
-    "xgm_index_decode_term", "xgm_searcher_new", "xgm_searcher_free", "xgm_search_submit", "xgm_search_wait",
+    "xgm_index_decode_term", "xgm_index_copy_doclengths", "xgm_searcher_new", "xgm_searcher_free", "xgm_search_submit", "xgm_search_wait",
     "xgm_search_submit_async", "xgm_search_launched", "xgm_search_batch", "xgm_search", "xgm_search_replay",
     "xgm_search_device_results", "xgm_search_device_slab",
     "xgm_searcher_stream", "xgm_search_last_stats", "xgm_unshard", "xgm_merge_msets", "xgm_merge_topk_device",
@@ -122,6 +123,7 @@ def lib():
     L.xgm_searcher_new.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
     L.xgm_searcher_free.argtypes = [C.c_void_p]
     L.xgm_searcher_free.restype = None
+    L.xgm_index_copy_doclengths.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
     L.xgm_search_submit.argtypes = [C.c_void_p, C.POINTER(CQuery), C.c_uint32]
     L.xgm_search_submit_async.argtypes = [C.c_void_p, C.POINTER(CQuery), C.c_uint32]
     L.xgm_search_launched.argtypes = [C.c_void_p]
@@ -357,6 +359,13 @@ class Index:
         if n.value:
             _check(lib().xgm_index_decode_term(self._h, term_id, _ptr(d), _ptr(w), n.value, C.byref(n)))
         return d, w
+
+    def doclengths(self, first_docid: int = 0, n: Optional[int] = None) -> np.ndarray:
+        if n is None:
+            n = self.info().lastdocid + 1 - first_docid
+        out = np.zeros(n, np.uint32)
+        _check(lib().xgm_index_copy_doclengths(self._h, first_docid, n, _ptr(out)))
+        return out
 
 
 class Searcher:
