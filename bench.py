@@ -399,18 +399,22 @@ def ours(args):
     t0 = time.perf_counter()
     inflight = []
     h2d = d2h = 0
+    prev = None
     for k in range(args.steps):
         si = k % NSEARCH
         if len(inflight) == NSEARCH:
             searchers[inflight.pop(0)].wait_raw()
         # the searcher's worker thread plans + enqueues batch k while this thread scatters an earlier one
         searchers[si].submit(batches[1 + k], background=True)
-        if world > 1:
-            if inflight:
-                searchers[inflight.pop(0)].wait_raw()
-            searchers[si].launched()
-            merge_step(si, True)
+        if world > 1 and prev is not None:
+            # all-gather + merge of the previous batch: its kernels were enqueued while we were busy above
+            searchers[prev].launched()
+            merge_step(prev, True)
+        prev = si
         inflight.append(si)
+    if world > 1:
+        searchers[prev].launched()
+        merge_step(prev, True)
     pending = inflight[-1]
     for si in inflight:
         searchers[si].wait_raw()

@@ -39,6 +39,7 @@ struct XgmKernelParams {
     const XgmWorkItem* items_or;  /* OR kernel work list */
     const XgmWorkItem* items_bm;  /* bitmap AND kernel work list */
     uint32_t nitems, nitems_or, nitems_bm;
+    const uint32_t* nitems_bm_dev; /* non-null: item count of the bitmap AND list lives on the device (range-major expansion) */
     uint32_t nq;
     uint32_t* work_counter;       /* [0] AND items, [1] OR items, [2],[3] same for the second pass, [4] #queries to re-run, [5] overflow-pool entries reserved, [6],[7] bitmap-AND items (first / second pass) */
     uint32_t pass;                /* 0 = first pass, 1 = re-run of overflowed queries with their exact b* */
@@ -70,6 +71,9 @@ cudaError_t xgm_launch_and_bm(const XgmKernelParams& p, int grid, cudaStream_t s
 int xgm_and_bm_occupancy_blocks_per_sm();
 cudaError_t xgm_launch_expand(const XgmWorkItem* seg, uint32_t nseg, uint32_t total, const uint32_t* level_start,
                               uint32_t nlevels, uint32_t bpi, XgmWorkItem* out, cudaStream_t s);
+cudaError_t xgm_launch_expand_ranges(const XgmWorkItem* seg, uint32_t nseg, const XgmDevQuery* queries, const XgmBlockHdr* hdr,
+                                     uint32_t nranges, uint32_t range_bits, uint32_t bpi, uint32_t* lo, uint32_t* cnt,
+                                     uint32_t* off, uint32_t* total, XgmWorkItem* out, cudaStream_t s);
 cudaError_t xgm_launch_or(const XgmKernelParams& p, int grid, cudaStream_t s);
 int xgm_or_occupancy_blocks_per_sm();
 cudaError_t xgm_launch_topk(const XgmKernelParams& p, uint32_t nq, cudaStream_t s);

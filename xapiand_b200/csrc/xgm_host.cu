@@ -723,6 +723,14 @@ struct xgm_searcher {
     uint32_t* h_levels[3] = {nullptr, nullptr, nullptr}; /* pinned: level_start arrays of the AND lists */
     uint32_t* d_levels[3] = {nullptr, nullptr, nullptr};
     size_t levels_cap[3] = {0, 0, 0};
+    /* range-major expansion of the bitmap AND list (large batches): per (range, segment) first block, item
+     * count, output offset; [0] of d_rng_total = number of items */
+    uint32_t* d_rng = nullptr;
+    size_t rng_cap = 0;
+    uint32_t* d_rng_total = nullptr;
+    uint32_t* h_rng_total = nullptr;
+    bool range_mode = false;
+    uint32_t range_bits = 18, nranges = 1;
     struct OrGroup { uint32_t seg_off, nseg, level_off, nlevels, out_off, total; };
     std::vector<OrGroup> or_groups; /* OR list: one level-ordered expansion per leaf position */
     unsigned char* d_ctrl = nullptr; /* [16 B work counters][nq x XgmQState][nq x XGM_NBINS x u32] */
@@ -795,6 +803,8 @@ extern "C" void xgm_searcher_free(xgm_searcher* s) {
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->ev2) cudaEventDestroy(s->ev2);
+    cudaFree(s->d_rng); cudaFree(s->d_rng_total);
+    if (s->h_rng_total) cudaFreeHost(s->h_rng_total);
     if (s->ev_in) cudaEventDestroy(s->ev_in);
     if (s->ev_done) cudaEventDestroy(s->ev_done);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -859,6 +869,11 @@ extern "C" xgm_status xgm_searcher_new(const xgm_index* ix, uint32_t max_batch, 
     CUDA_TRY(cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming));
     if (const char* e = getenv("XGM_SHARED_COMPUTE")) s->shared_compute = atoi(e) != 0;
+    if (const char* e = getenv("XGM_RANGE_BITS")) s->range_bits = (uint32_t)std::min(31, std::max(0, atoi(e)));
+    CUDA_TRY(cudaMalloc(&s->d_rng_total, 64));
+    CUDA_TRY(cudaMemset(s->d_rng_total, 0, 64));
+    CUDA_TRY(cudaMallocHost(&s->h_rng_total, 64));
+    s->h_rng_total[0] = 0;
     {
         std::lock_guard<std::mutex> lk(ix->launch_mu);
         if (!ix->compute_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ix->compute_stream, cudaStreamNonBlocking));
@@ -1203,6 +1218,11 @@ static xgm_status launch_batch(xgm_searcher* s) {
                                                s->bpi, s->d_exp[1] + g.out_off, cs));
                     s->stats.kernel_launches++;
                 }
+            } else if (w == 2 && s->range_mode) {
+                const size_t n = (size_t)s->nranges * s->nseg[2];
+                CUDA_TRY(xgm_launch_expand_ranges(segs[2], s->nseg[2], s->d_queries, p.hdr, s->nranges, s->range_bits, s->bpi,
+                                                  s->d_rng, s->d_rng + n, s->d_rng + 2 * n, s->d_rng_total, s->d_exp[2], cs));
+                s->stats.kernel_launches += 3;
             } else {
                 CUDA_TRY(xgm_launch_expand(segs[w], s->nseg[w], totals[w], s->d_levels[w], s->nlevels[w], s->bpi, s->d_exp[w], cs));
                 s->stats.kernel_launches++;
@@ -1309,7 +1329,24 @@ static xgm_status submit_impl(xgm_searcher* s, const xgm_query* queries, uint32_
             uint64_t run = 0;
             XgmWorkItem* h = *hbuf[w];
             s->nlevels[w] = 0;
-            if (w != 1 && !v.empty()) {
+            if (w == 2) s->range_mode = false;
+            if (w == 2 && !v.empty() && nq >= 256 && s->range_bits != 0) {
+                /* range-major order, expanded on the device (xgm_range_*_kernel): the host only bounds the
+                 * number of items — every range can add one partial item per segment */
+                s->range_mode = true;
+                s->nranges = (s->ix->lastdocid >> s->range_bits) + 1;
+                for (size_t i = 0; i < v.size(); ++i) { h[i] = v[i]; run += (v[i].b0 + bpi - 1) / bpi; }
+                run += (uint64_t)v.size() * s->nranges;
+                const size_t need = (size_t)s->nranges * v.size() * 3;
+                if (need > s->rng_cap) {
+                    CUDA_TRY(cudaStreamSynchronize(s->stream));
+                    if (s->ix->compute_stream) CUDA_TRY(cudaStreamSynchronize(s->ix->compute_stream));
+                    cudaFree(s->d_rng);
+                    s->d_rng = nullptr;
+                    CUDA_TRY(cudaMalloc(&s->d_rng, need * 2 * sizeof(uint32_t)));
+                    s->rng_cap = need * 2;
+                }
+            } else if (w != 1 && !v.empty()) {
                 /* AND lists: level order — sort segments by descending length, level k holds the k-th item of
                  * every segment that has one, i.e. a prefix of the sorted segments */
                 std::sort(v.begin(), v.end(), [](const XgmWorkItem& a, const XgmWorkItem& b) { return a.b0 > b.b0; });
@@ -1384,6 +1421,7 @@ static xgm_status submit_impl(xgm_searcher* s, const xgm_query* queries, uint32_
     p.queries = s->d_queries; p.items = s->d_exp[0]; p.nitems = s->nitems; p.nq = nq;
     p.items_or = s->d_exp[1]; p.nitems_or = s->nitems_or;
     p.items_bm = s->d_exp[2]; p.nitems_bm = s->nitems_bm;
+    p.nitems_bm_dev = s->range_mode ? s->d_rng_total : nullptr;
     p.work_counter = reinterpret_cast<uint32_t*>(s->d_ctrl);
     p.qstate = reinterpret_cast<XgmQState*>(s->d_ctrl + 64);
     p.hist = reinterpret_cast<uint32_t*>(s->d_ctrl + 64 + (size_t)s->max_batch * sizeof(XgmQState));
@@ -1405,6 +1443,7 @@ static xgm_status submit_impl(xgm_searcher* s, const xgm_query* queries, uint32_
     if (st != XGM_OK) return st;
     size_t ns = (size_t)nq * s->max_topk;
     CUDA_TRY(cudaMemcpyAsync(s->h_info, s->d_info, (size_t)nq * sizeof(XgmDevResult), cudaMemcpyDeviceToHost, s->stream));
+    if (s->range_mode) CUDA_TRY(cudaMemcpyAsync(s->h_rng_total, s->d_rng_total, 4, cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaMemcpyAsync(s->h_out_w, s->d_out_w, ns * 8, cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaMemcpyAsync(s->h_out_d, s->d_out_d, ns * 4, cudaMemcpyDeviceToHost, s->stream));
     if (s->any_sort) CUDA_TRY(cudaMemcpyAsync(s->h_out_k, s->d_out_k, ns * 8, cudaMemcpyDeviceToHost, s->stream));
@@ -1532,6 +1571,7 @@ extern "C" xgm_status xgm_search_wait(xgm_searcher* s, uint32_t* docids, double*
     cudaEventElapsedTime(&s->stats.match_kernel_ms, s->ev0, s->ev1);
     cudaEventElapsedTime(&s->stats.topk_kernel_ms, s->ev1, s->ev2);
     const auto t_wait0 = std::chrono::steady_clock::now();
+    if (s->range_mode) s->stats.work_items = (uint64_t)s->nitems + s->nitems_or + s->h_rng_total[0];
     s->stats.second_pass_queries = 0;
     for (uint32_t i = 0; i < s->nq; ++i) {
         const PlannedQuery& pq = s->plan[i];

@@ -52,6 +52,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+/* the same on precomputed shared-space addresses (hot loops: no generic→shared conversion per call) */
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "XGM_WAITA:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra XGM_DONEA;\n"
+        "bra XGM_WAITA;\n"
+        "XGM_DONEA:\n"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
 /* ------------------------------------------------------------------ block decode */
 
 #define STAGE_WORDS 132 /* 128 packed words at 32 bits + slack for the funnel-shift's high word; 16B multiple */
@@ -690,13 +713,17 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 4) xgm_and_bm_kernel(XgmKernelP
     __syncthreads();
     uint32_t phases = 0;
     const XgmBlockHdr* __restrict__ hdr = p.hdr;
+    const uint32_t stage_base = smem_u32(ws.dstage[0]);
+#define bar_base (stage_base + (uint32_t)offsetof(BmScratch, dbar))
     if (p.pass != 0 && *reinterpret_cast<volatile uint32_t*>(p.work_counter + 4) == 0) return;
+    /* range-major expansion counts its items on the device */
+    const uint32_t nitems_bm = p.nitems_bm_dev ? __ldg(p.nitems_bm_dev) : p.nitems_bm;
 
     for (;;) {
         uint32_t item = 0;
         if (lane == 0) item = atomicAdd(p.work_counter + 6 + p.pass, 1u);
         item = __shfl_sync(FULL, item, 0);
-        if (item >= p.nitems_bm) break;
+        if (item >= nitems_bm) break;
         const XgmWorkItem wi = p.items_bm[item];
         if (p.pass != 0 && p.qstate[wi.query].rerun == 0) continue;
         const XgmDevQuery* q = &p.queries[wi.query];
@@ -739,8 +766,8 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 4) xgm_and_bm_kernel(XgmKernelP
             const uint32_t bits = XGM_HDR_DOC_BITS(h.meta);
             __syncwarp();
             if (bits != 0 && lane == 0) {
-                mbar_expect_tx(&ws.dbar[b], bits * 16u);
-                bulk_g2s(ws.dstage[b], p.docs + h.doc_off, bits * 16u, &ws.dbar[b]);
+                mbar_expect_tx_a(bar_base + b * 8u, bits * 16u);
+                bulk_g2s_a(stage_base + b * (STAGE_WORDS * 4u), p.docs + h.doc_off, bits * 16u, bar_base + b * 8u);
             }
             return h;
         };
@@ -754,52 +781,51 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 4) xgm_and_bm_kernel(XgmKernelP
             if (db + 2 < wi.b1) n0 = issue(cur ^ 2, db + 2);
             if (db + 3 < wi.b1) n1 = issue((cur ^ 2) + 1, db + 3);
             uint32_t c[8];
-            uint32_t alive = 0;
+            uint32_t alive;
+            const uint32_t cnt0 = XGM_HDR_COUNT(h0.meta), cnt1 = two ? XGM_HDR_COUNT(h1.meta) : 0u;
             {
                 const uint32_t bits = XGM_HDR_DOC_BITS(h0.meta);
-                if (bits) { mbar_wait(&ws.dbar[cur], (phases >> cur) & 1u); phases ^= 1u << cur; }
+                if (bits) { mbar_wait_a(bar_base + cur * 8u, (phases >> cur) & 1u); phases ^= 1u << cur; }
                 decode_docids(ws.dstage[cur], bits, h0.first, lane, c);
-                const uint32_t cnt = XGM_HDR_COUNT(h0.meta);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (4 * lane + k < cnt) alive |= 1u << k;
             }
             if (two) {
                 const uint32_t bits = XGM_HDR_DOC_BITS(h1.meta);
-                if (bits) { mbar_wait(&ws.dbar[cur + 1], (phases >> (cur + 1)) & 1u); phases ^= 1u << (cur + 1); }
+                if (bits) { mbar_wait_a(bar_base + (cur + 1) * 8u, (phases >> (cur + 1)) & 1u); phases ^= 1u << (cur + 1); }
                 decode_docids(ws.dstage[cur + 1], bits, h1.first, lane, c + 4);
-                const uint32_t cnt = XGM_HDR_COUNT(h1.meta);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (4 * lane + k < cnt) alive |= 16u << k;
             } else {
                 c[4] = c[5] = c[6] = c[7] = 0u;
             }
             /* the skip_to/check of the leapfrog: one bitmap word per candidate, all loads issued together */
             uint32_t w[8];
+            if (cnt0 + cnt1 == 2u * XGM_BLOCK) { /* two full blocks (warp-uniform): no per-posting predicates */
+                alive = 0xffu;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) w[k] = (alive >> k & 1u) ? __ldg(bm1 + (c[k] >> 5)) : 0u;
-            uint32_t surv = 0;
+                for (int k = 0; k < 8; ++k) w[k] = __ldg(bm1 + (c[k] >> 5));
+            } else {
+                const int n0 = min(4, max(0, (int)cnt0 - 4 * (int)lane)), n1 = min(4, max(0, (int)cnt1 - 4 * (int)lane));
+                alive = ((1u << n0) - 1u) | (((1u << n1) - 1u) << 4);
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if ((alive >> k & 1u) && (w[k] >> (c[k] & 31) & 1u)) surv |= 1u << k;
+                for (int k = 0; k < 8; ++k) w[k] = (alive >> k & 1u) ? __ldg(bm1 + (c[k] >> 5)) : 0u;
+            }
+            uint32_t surv = 0; /* dead slots carry w = 0 */
+#pragma unroll
+            for (int k = 0; k < 8; ++k) surv |= (__funnelshift_r(w[k], 0u, c[k]) & 1u) << k; /* shifts by c & 31 */
             if (__any_sync(FULL, surv != 0)) {
-                const uint32_t n = __popc(surv);
-                uint32_t incl = n;
+                /* survivors are rare (a few per pair of blocks): one ballot per slot, empty slots skipped */
+                const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t t = __shfl_up_sync(FULL, incl, o);
-                    if ((int)lane >= o) incl += t;
-                }
-                uint32_t slot = qn + incl - n;
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (surv >> k & 1u) {
-                        ws.qdid[slot] = c[k];
-                        ws.qsrc[slot] = ((db - wi.b0 + (k >> 2)) << 7) | (4 * lane + (k & 3));
-                        ++slot;
+                for (int k = 0; k < 8; ++k) {
+                    const bool mine = surv >> k & 1u;
+                    const uint32_t b = __ballot_sync(FULL, mine);
+                    if (b) {
+                        if (mine) {
+                            const uint32_t slot = qn + __popc(b & lt);
+                            ws.qdid[slot] = c[k];
+                            ws.qsrc[slot] = ((db - wi.b0 + (k >> 2)) << 7) | (4 * lane + (k & 3));
+                        }
+                        qn += __popc(b);
                     }
-                qn += __shfl_sync(FULL, incl, 31);
+                }
                 __syncwarp();
                 while (qn >= 32) {
                     qn -= 32;
@@ -817,6 +843,8 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 4) xgm_and_bm_kernel(XgmKernelP
         }
     }
 }
+
+#undef bar_base
 
 cudaError_t xgm_launch_and_bm(const XgmKernelParams& p, int grid, cudaStream_t s) {
     xgm_and_bm_kernel<<<grid, BM_WARPS * 32, 0, s>>>(p);
@@ -1790,6 +1818,129 @@ __global__ void xgm_expand_items_kernel(const XgmWorkItem* __restrict__ seg, uin
         w.pad = sg.pad;
     }
     out[s] = w;
+}
+
+/* Range-major expansion (bitmap AND list, large batches).  The docid space is cut into ranges of
+ * 2^range_bits documents and the work list is ordered range by range, every query's driver blocks of
+ * range 0 first, then range 1, ...: at any moment all warps probe the same slice of every membership
+ * bitmap (lastdocid/8 bytes per term shrink to 2^range_bits/8), which stays in the 126 MB L2 while the
+ * whole batch walks over it — each bitmap is read from HBM about once per batch instead of once per query
+ * that uses it.  Every query still advances through the whole batch, so thresholds rise early as with the
+ * level order.  Three small kernels: per (range, segment) the driver blocks whose first docid falls in
+ * the range (two binary searches over the skip table) and their item count; an exclusive scan in
+ * range-major order; the fill. */
+__device__ __forceinline__ uint32_t first_block_at_or_after(const XgmBlockHdr* __restrict__ h, uint32_t nblk, uint64_t target) {
+    uint32_t lo = 0, hi = nblk;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((uint64_t)h[mid].first < target) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+#define XGM_RNG_THREADS 256
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* warp_sums /* [8] shared */, uint32_t* block_total) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, incl, o);
+        if ((int)lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (uint32_t x = 0; x < XGM_RNG_THREADS / 32; ++x) {
+        const uint32_t ws = warp_sums[x];
+        if (x < warp) before += ws;
+        total += ws;
+    }
+    *block_total = total;
+    return before + incl - v;
+}
+
+__global__ void __launch_bounds__(XGM_RNG_THREADS) xgm_range_count_kernel(
+    const XgmWorkItem* __restrict__ seg, uint32_t nseg, const XgmDevQuery* __restrict__ queries,
+    const XgmBlockHdr* __restrict__ hdr, uint32_t nranges, uint32_t range_bits, uint32_t bpi, uint32_t* __restrict__ lo_out,
+    uint32_t* __restrict__ cnt_out, uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t warp_sums[XGM_RNG_THREADS / 32];
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t cnt = 0;
+    if (t < nranges * nseg) {
+        const uint32_t j = t / nseg, sidx = t - j * nseg; /* range-major: consecutive threads = consecutive segments */
+        const XgmWorkItem sg = seg[sidx];
+        const XgmBlockHdr* h = hdr + queries[sg.query].terms[0].blk_begin;
+        const uint32_t nblk = sg.b0;
+        /* a block belongs to the range of its first docid */
+        const uint32_t lo = j == 0 ? 0u : first_block_at_or_after(h, nblk, (uint64_t)j << range_bits);
+        const uint32_t hi = j + 1 == nranges ? nblk : first_block_at_or_after(h, nblk, (uint64_t)(j + 1) << range_bits);
+        lo_out[t] = lo;
+        cnt = (hi - lo + bpi - 1) / bpi;
+        cnt_out[t] = cnt;
+    }
+    uint32_t total;
+    (void)block_exclusive_scan_256(cnt, warp_sums, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+/* exclusive scan of the per-block sums (a few hundred to a few thousand values), one CTA */
+#define XGM_SCAN_THREADS 1024
+__global__ void __launch_bounds__(XGM_SCAN_THREADS) xgm_range_scan_kernel(uint32_t* __restrict__ block_sums, uint32_t n,
+                                                                         uint32_t* total) {
+    __shared__ uint32_t part[XGM_SCAN_THREADS];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t chunk = (n + XGM_SCAN_THREADS - 1) / XGM_SCAN_THREADS;
+    const uint32_t a = min(n, tid * chunk), b = min(n, a + chunk);
+    uint32_t sum = 0;
+    for (uint32_t i = a; i < b; ++i) sum += block_sums[i];
+    part[tid] = sum;
+    __syncthreads();
+    for (uint32_t o = 1; o < XGM_SCAN_THREADS; o <<= 1) {
+        const uint32_t v = tid >= o ? part[tid - o] : 0u;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    uint32_t run = part[tid] - sum;
+    for (uint32_t i = a; i < b; ++i) { const uint32_t c = block_sums[i]; block_sums[i] = run; run += c; }
+    if (tid == XGM_SCAN_THREADS - 1) *total = part[tid];
+}
+
+__global__ void __launch_bounds__(XGM_RNG_THREADS) xgm_range_fill_kernel(
+    const XgmWorkItem* __restrict__ seg, uint32_t nseg, uint32_t nranges, uint32_t bpi, const uint32_t* __restrict__ lo_in,
+    const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ block_off, XgmWorkItem* __restrict__ out) {
+    __shared__ uint32_t warp_sums[XGM_RNG_THREADS / 32];
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = t < nranges * nseg;
+    const uint32_t n = in ? cnt[t] : 0u;
+    uint32_t total;
+    const uint32_t off = block_off[blockIdx.x] + block_exclusive_scan_256(n, warp_sums, &total);
+    if (n == 0) return;
+    const uint32_t j = t / nseg, sidx = t - j * nseg;
+    const XgmWorkItem sg = seg[sidx];
+    const uint32_t lo = lo_in[t];
+    const uint32_t hi = j + 1 == nranges ? sg.b0 : lo_in[t + nseg];
+    XgmWorkItem w;
+    w.query = sg.query;
+    w.pad = sg.pad;
+    for (uint32_t i = 0; i < n; ++i) {
+        w.b0 = lo + i * bpi;
+        w.b1 = min(hi, w.b0 + bpi);
+        out[off + i] = w;
+    }
+}
+
+cudaError_t xgm_launch_expand_ranges(const XgmWorkItem* seg, uint32_t nseg, const XgmDevQuery* queries, const XgmBlockHdr* hdr,
+                                     uint32_t nranges, uint32_t range_bits, uint32_t bpi, uint32_t* lo, uint32_t* cnt,
+                                     uint32_t* off, uint32_t* total, XgmWorkItem* out, cudaStream_t s) {
+    const uint32_t n = nranges * nseg;
+    if (n == 0) return cudaSuccess;
+    const uint32_t nb = (n + XGM_RNG_THREADS - 1) / XGM_RNG_THREADS; /* `off` holds the nb block sums / offsets */
+    xgm_range_count_kernel<<<nb, XGM_RNG_THREADS, 0, s>>>(seg, nseg, queries, hdr, nranges, range_bits, bpi, lo, cnt, off);
+    xgm_range_scan_kernel<<<1, XGM_SCAN_THREADS, 0, s>>>(off, nb, total);
+    xgm_range_fill_kernel<<<nb, XGM_RNG_THREADS, 0, s>>>(seg, nseg, nranges, bpi, lo, cnt, off, out);
+    return cudaGetLastError();
 }
 
 cudaError_t xgm_launch_expand(const XgmWorkItem* seg, uint32_t nseg, uint32_t total, const uint32_t* level_start,
