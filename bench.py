@@ -352,6 +352,9 @@ def ours(args):
                 srch.launched()
                 merge_step(si, True)
             srch.wait_raw()
+    if world > 1:  # the device-resident loop alternates between two searchers holding the same resident plan
+        searchers[1].submit(batches[0])
+        searchers[1].wait_raw()
     searchers[0].submit(batches[0])
     _, _, _, inf0 = searchers[0].wait_raw()
     bad = sum(1 for i in range(BATCH) if inf0[i].status != 0)
@@ -374,9 +377,16 @@ def ours(args):
     sampler.begin()
     ev0.record(streams[0])
     for k in range(args.steps):
-        searchers[0].replay()
+        # N > 1: the all-gather + merge of step k (searcher k%2's stream) overlaps the kernels of step k+1
+        # (the index's compute stream), consecutive steps being independent batches
+        si = k % 2 if world > 1 else 0
+        searchers[si].replay()
         if world > 1:
-            merge_step(0, False)
+            merge_step(si, False)
+    if world > 1:
+        tail = torch.cuda.Event()
+        tail.record(streams[1])
+        streams[0].wait_event(tail)
     ev1.record(streams[0])
     sampler.sample_now()  # the K replays are queued and running
     barrier()

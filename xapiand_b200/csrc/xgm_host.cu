@@ -862,7 +862,8 @@ extern "C" xgm_status xgm_searcher_new(const xgm_index* ix, uint32_t max_batch, 
     /* candidates a query may buffer before its pruning threshold settles (~k(1+ln(M/k)) arrive above
      * a rising threshold) and how many of them the top-k kernel can hold in shared memory */
     s->match_cap = std::max<uint32_t>(8192, 16 * max_topk);
-    s->keep_cap = std::max<uint32_t>(2048, std::min<uint32_t>(8192, 8 * max_topk));
+    s->keep_cap = 2048; /* a power of two (the top-k kernel sorts in place): 2048, 4096 or 8192 */
+    while (s->keep_cap < 8192 && s->keep_cap < 8 * max_topk) s->keep_cap <<= 1;
     if (s->keep_cap > s->match_cap) s->keep_cap = s->match_cap;
     CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&s->ev0)); CUDA_TRY(cudaEventCreate(&s->ev1)); CUDA_TRY(cudaEventCreate(&s->ev2));

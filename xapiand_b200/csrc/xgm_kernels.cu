@@ -1434,6 +1434,63 @@ __device__ __forceinline__ int match_key_words(uint32_t sort_by, uint32_t revers
     return 5;
 }
 
+/* Weights are >= +0.0 and never NaN, so their IEEE bit patterns order like the values: the ranking loops
+ * compare 64-bit integers (full-rate integer pipe) instead of doubles — the FP64 compare throughput of the
+ * SM is what bounded the top-k CTAs of queries with ~1000 matches. */
+__device__ __forceinline__ uint64_t wbits(double w) { return (uint64_t)__double_as_longlong(w); }
+
+/* Bitonic sort of the CTA's shared-memory candidate arrays (w, k, d), P a power of two, all TOPK_THREADS
+ * threads.  BY_DOCID: ascending docid.  Otherwise the reference's relevance order: weight descending,
+ * docid ascending (msetcmp.cc:54-61). */
+template <bool BY_DOCID>
+__device__ __forceinline__ void bitonic_sort_candidates(double* sw, uint64_t* sk, uint32_t* sd, uint32_t P, uint32_t tid) {
+    for (uint32_t k = 2; k <= P; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = tid; t < P; t += TOPK_THREADS) {
+                const uint32_t x = t ^ j;
+                if (x > t) {
+                    const uint32_t da = sd[t], db = sd[x];
+                    const double wa = sw[t], wb = sw[x];
+                    const uint64_t ba = wbits(wa), bb = wbits(wb);
+                    /* true when the pair is out of order for an ascending run */
+                    const bool wrong = BY_DOCID ? (da > db) : (ba < bb || (ba == bb && da > db));
+                    const bool right = BY_DOCID ? (da < db) : (ba > bb || (ba == bb && da < db));
+                    if (((t & k) == 0) ? wrong : right) {
+                        sd[t] = db; sd[x] = da;
+                        sw[t] = wb; sw[x] = wa;
+                        const uint64_t ka = sk[t]; sk[t] = sk[x]; sk[x] = ka;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+/* Highest bin b with at least `want` entries in bins [b, XGM_NBINS) of a shared-memory histogram (0 if the
+ * whole histogram holds fewer), found by warp 0: 32 bins per lane, a suffix scan over the lanes, then a
+ * walk inside the one lane's bins.  Result in *out (shared); the caller synchronises. */
+__device__ __forceinline__ void threshold_bin(const uint32_t* lh, uint32_t want, uint32_t tid, uint32_t* out) {
+    if (tid >= 32) return;
+    const uint32_t per = XGM_NBINS / 32;
+    uint32_t sum = 0;
+    for (uint32_t i = 0; i < per; ++i) sum += lh[tid * per + i];
+    uint32_t suffix = sum; /* entries in the bins of lanes >= tid */
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_down_sync(FULL, suffix, o);
+        if ((int)tid + o < 32) suffix += t;
+    }
+    const uint32_t ok = __ballot_sync(FULL, suffix >= want);
+    if (ok == 0) { if (tid == 0) *out = 0; return; }
+    const uint32_t lane = 31u - (uint32_t)__clz(ok); /* highest lane whose suffix reaches `want` */
+    if (tid == lane) {
+        uint32_t cum = suffix - sum, b = (tid + 1) * per;
+        while (b > tid * per && cum < want) { --b; cum += lh[b]; }
+        *out = b;
+    }
+}
+
 /* One CTA per query.
  * First pass: survivors (bucket >= final b*) are compacted into shared memory and rank-sorted under
  * the reference's total order; when nothing was pruned the same pass reproduces ProtoMSet's
@@ -1468,12 +1525,37 @@ __global__ void __launch_bounds__(TOPK_THREADS) xgm_topk_kernel(XgmKernelParams 
         const uint32_t stored = st.stored < p.match_cap ? st.stored : p.match_cap;
         const size_t qoff = (size_t)qi * p.match_cap;
         complete = (st.total == st.stored) && (st.stored <= p.keep_cap); /* every match is here */
-        for (uint32_t i = tid; i < stored; i += TOPK_THREADS) {
-            const double w = p.match_w[qoff + i];
-            const uint64_t k = p.match_k[qoff + i];
-            if (complete || match_bucket(q, w, k) >= st.bstar) {
-                const uint32_t pos = atomicAdd(&s_n, 1u);
-                if (pos < p.keep_cap) { sw[pos] = w; sd[pos] = p.match_d[qoff + i]; sk[pos] = k; }
+        /* four independent rounds of loads in flight per thread: a dense query stores thousands of
+         * candidates and one dependent round trip per 256 of them would make its CTA the launch's tail */
+        for (uint32_t base = 0; base < stored; base += 4 * TOPK_THREADS) {
+            double w[4];
+            uint64_t k[4];
+            uint32_t d[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t i = base + u * TOPK_THREADS + tid;
+                if (i < stored) {
+                    w[u] = __ldcs(p.match_w + qoff + i);
+                    k[u] = __ldcs(p.match_k + qoff + i);
+                    d[u] = __ldcs(p.match_d + qoff + i);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t i = base + u * TOPK_THREADS + tid;
+                const bool keep = i < stored && (complete || match_bucket(q, w[u], k[u]) >= st.bstar);
+                /* one shared-memory atomic per warp, not per survivor (an unpruned query keeps everything) */
+                const uint32_t m = __ballot_sync(FULL, keep);
+                if (m) {
+                    const uint32_t lane = tid & 31u, leader = (uint32_t)__ffs(m) - 1u;
+                    uint32_t pos0 = 0;
+                    if (lane == leader) pos0 = atomicAdd(&s_n, (uint32_t)__popc(m));
+                    pos0 = __shfl_sync(FULL, pos0, leader);
+                    if (keep) {
+                        const uint32_t pos = pos0 + __popc(m & ((1u << lane) - 1u));
+                        if (pos < p.keep_cap) { sw[pos] = w[u]; sd[pos] = d[u]; sk[pos] = k[u]; }
+                    }
+                }
             }
         }
         __syncthreads();
@@ -1571,12 +1653,8 @@ __global__ void __launch_bounds__(TOPK_THREADS) xgm_topk_kernel(XgmKernelParams 
         __syncthreads();
         for (uint32_t i = tid; i < n; i += TOPK_THREADS) atomicAdd(&lh[match_bucket(q, sw[i], sk[i])], 1u);
         __syncthreads();
-        if (tid == 0) {
-            uint32_t cum = 0, b = XGM_NBINS;
-            while (b > 0 && cum < topk) { --b; cum += lh[b]; }
-            s_prefix[0] = b;
-            s_n = 0;
-        }
+        threshold_bin(lh, topk, tid, &s_prefix[0]);
+        if (tid == 32) s_n = 0;
         __syncthreads();
         const uint32_t bsel = s_prefix[0];
         /* in-place compaction: read everything into registers first (n <= keep_cap <= 32 per thread) */
@@ -1600,25 +1678,111 @@ __global__ void __launch_bounds__(TOPK_THREADS) xgm_topk_kernel(XgmKernelParams 
     uint32_t known = 0;
     const size_t ooff = (size_t)qi * p.out_stride;
     if (sort_by == 0) {
-        /* relevance order: weight desc, docid asc — no sort keys to compare */
-        for (uint32_t i = tid; i < n; i += TOPK_THREADS) {
-            const double wi = sw[i];
-            const uint32_t di = sd[i];
-            uint32_t rank = 0, before = 0, greater_before = 0;
-            for (uint32_t j = 0; j < n; ++j) {
-                const double wj = sw[j];
-                const uint32_t dj = sd[j];
-                const bool earlier = dj < di, greater = wj > wi;
-                rank += (greater || (wj == wi && earlier)) ? 1u : 0u;
-                before += earlier ? 1u : 0u;
-                greater_before += (earlier && greater) ? 1u : 0u;
+        /* relevance order: weight desc, docid asc — no sort keys to compare.  The docid-order history of
+         * ProtoMSet's count is only needed when the count is reported (unpruned set) and can differ from n
+         * (more matches than the free_count that are counted unconditionally). */
+        const bool need_counts = complete && !st.skipped && n > free_count;
+        if (need_counts) {
+            /* n <= XGM_EXACT_COUNT_MAX.  Sort the survivors by docid (bitonic, in shared memory): "earlier in
+             * docid order" becomes "smaller index", so `before` is the index itself and each pair costs one
+             * or two f64 compares instead of the three-counter test on unsorted data. */
+            uint32_t P = 32;
+            while (P < n) P <<= 1;
+            for (uint32_t t = n + tid; t < P; t += TOPK_THREADS) { sd[t] = 0xffffffffu; sw[t] = 0.0; sk[t] = 0; }
+            __syncthreads();
+            bitonic_sort_candidates<true>(sw, sk, sd, P, tid);
+            /* thread t owns the four consecutive positions 4t..4t+3 (n <= 1024 = 4 * TOPK_THREADS): one pass
+             * over j serves four independent counters per load — the pair loops of a ~1000-match query are
+             * bound by the dependent-issue latency of its 8 warps, not by throughput */
+            const uint64_t* bw = reinterpret_cast<const uint64_t*>(sw);
+            const uint32_t i0 = 4 * tid;
+            if (i0 < n) {
+                uint64_t b[4];
+                uint32_t geb[4] = {0, 0, 0, 0}, gtb[4] = {0, 0, 0, 0}, gta[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) b[u] = i0 + u < n ? bw[i0 + u] : ~0ull;
+                for (uint32_t j = 0; j < i0; ++j) {
+                    const uint64_t bj = bw[j];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        geb[u] += bj >= b[u] ? 1u : 0u; /* ranks before: greater, or equal with a smaller docid */
+                        gtb[u] += bj > b[u] ? 1u : 0u;
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    if (i0 + v < n) {
+                        const uint64_t bj = bw[i0 + v];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (v < u) { geb[u] += bj >= b[u] ? 1u : 0u; gtb[u] += bj > b[u] ? 1u : 0u; }
+                            else if (v > u) gta[u] += bj > b[u] ? 1u : 0u;
+                        }
+                    }
+                }
+                for (uint32_t j = i0 + 4; j < n; ++j) {
+                    const uint64_t bj = bw[j];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) gta[u] += bj > b[u] ? 1u : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t i = i0 + u;
+                    if (i < n) {
+                        const uint32_t rank = geb[u] + gta[u];
+                        if (rank < topk) {
+                            p.out_w[ooff + rank] = sw[i];
+                            p.out_d[ooff + rank] = sd[i];
+                            p.out_k[ooff + rank] = sk[i];
+                        }
+                        if (i < free_count || gtb[u] < topk) ++known;
+                    }
+                }
             }
-            if (rank < topk) {
-                p.out_w[ooff + rank] = wi;
-                p.out_d[ooff + rank] = di;
-                p.out_k[ooff + rank] = sk[i];
+        } else {
+            uint32_t P = 32;
+            while (P < n) P <<= 1;
+            if (n > TOPK_THREADS && P <= p.keep_cap) {
+                /* many survivors (a mass of tied weights, or a dense query): sort instead of ranking pairs */
+                for (uint32_t t = n + tid; t < P; t += TOPK_THREADS) { sd[t] = 0xffffffffu; sw[t] = 0.0; sk[t] = 0; }
+                __syncthreads();
+                bitonic_sort_candidates<false>(sw, sk, sd, P, tid);
+                const uint32_t m = n < topk ? n : topk;
+                for (uint32_t i = tid; i < m; i += TOPK_THREADS) {
+                    p.out_w[ooff + i] = sw[i];
+                    p.out_d[ooff + i] = sd[i];
+                    p.out_k[ooff + i] = sk[i];
+                }
+                if (tid == 0) known = n; /* used only when n <= free_count: every match is counted */
+            } else {
+                /* rank only; two threads share an element when there are few (j split by parity).  The loop
+                 * bound is uniform so that the pair's shuffle is executed by whole warps. */
+                const uint32_t split = n <= TOPK_THREADS / 2 ? 2u : 1u;
+                const uint32_t sub = tid & (split - 1u);
+                for (uint32_t base = 0; base < n; base += TOPK_THREADS / split) {
+                    const uint32_t i = base + tid / split;
+                    const bool act = i < n;
+                    const double wi = act ? sw[i] : 0.0;
+                    const uint64_t bi = wbits(wi);
+                    const uint64_t* bw = reinterpret_cast<const uint64_t*>(sw);
+                    const uint32_t di = act ? sd[i] : 0u;
+                    uint32_t rank = 0;
+                    if (act)
+                        for (uint32_t j = sub; j < n; j += split) {
+                            const uint64_t bj = bw[j]; /* no short-circuit: branches here cost ~100 cycles a pair */
+                            rank += (uint32_t)(bj > bi) | ((uint32_t)(bj == bi) & (uint32_t)(sd[j] < di));
+                        }
+                    if (split == 2u) rank += __shfl_xor_sync(FULL, rank, 1);
+                    if (act && sub == 0u) {
+                        if (rank < topk) {
+                            p.out_w[ooff + rank] = wi;
+                            p.out_d[ooff + rank] = di;
+                            p.out_k[ooff + rank] = sk[i];
+                        }
+                        ++known; /* n <= free_count: every match is counted */
+                    }
+                }
             }
-            if (before < free_count || greater_before < topk) ++known;
         }
     } else {
         for (uint32_t i = tid; i < n; i += TOPK_THREADS) {
