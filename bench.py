@@ -224,6 +224,18 @@ def run_reference_queries(dbs, nqueries: int, steps: int, warmup: int, threads: 
     return info
 
 
+def single_thread_baseline(dbs):
+    """SURVEY.md §8(d) asks for the reference at (i) one thread and (ii) all cores: the one-thread leg, on a
+    small bounded sample (a few seconds)."""
+    n = int(os.environ.get("XGM_BENCH_REF_QUERIES_1T", 256))
+    try:
+        info = run_reference_queries(dbs, n, 1, 1, 1)
+        return {"value": info["qps"], "unit": UNIT, "cores": 1, "p50_ms": info["p50_ms"], "p99_ms": info["p99_ms"],
+                "sample": f"1 pass of {n} queries of the same workload, one thread"}
+    except Exception as e:  # reported, never required
+        return {"value": None, "unit": UNIT, "cores": 1, "sample": f"unavailable: {e}"}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -243,7 +255,8 @@ def reference_arm(args):
             "config": {"workload": "C2: 10M docs, V=1M Zipf(1) terms, 3-term OP_AND, BM25, get_mset(0,100)",
                        "docs": NDOCS, "vocab": VOCAB, "queries_per_step": REF_QUERIES_PER_STEP, "topk": TOPK},
             "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample,
-                             "p50_ms": info["p50_ms"], "p99_ms": info["p99_ms"]},
+                             "p50_ms": info["p50_ms"], "p99_ms": info["p99_ms"],
+                             "single_thread": single_thread_baseline(binfo["dbs"])},
             "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "setup_s": round(time.time() - t0, 1)}
     print(json.dumps(line))
@@ -502,7 +515,8 @@ def ours(args):
                 "value": cinfo["qps"], "unit": UNIT, "cores": cores, "kind": "reference",
                 "sample": (f"3 passes of {REF_QUERIES_PER_STEP} queries of the same workload on the full {NDOCS}-doc "
                            f"glass DB, {cores} threads (one Xapian::Database+Enquire each), timing get_mset only"),
-                "p50_ms": cinfo["p50_ms"], "p99_ms": cinfo["p99_ms"]}
+                "p50_ms": cinfo["p50_ms"], "p99_ms": cinfo["p99_ms"],
+                "single_thread": single_thread_baseline(binfo["dbs"])}
         except Exception as e:  # the baseline is reported, never required for the GPU numbers
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": ref_cores(), "kind": "reference",
                                     "sample": f"unavailable: {e}"}
