@@ -52,7 +52,7 @@ class _Index(C.Structure):
 
 class _Stats(C.Structure):
     _fields_ = [("collection_size", C.c_uint32), ("total_length", C.c_uint64),
-                ("termfreq", C.POINTER(C.c_uint32))]
+                ("termfreq", C.POINTER(C.c_uint32)), ("maybe_termfreq", C.POINTER(C.c_uint32))]
 
 
 class _Query(C.Structure):
@@ -61,7 +61,10 @@ class _Query(C.Structure):
                 ("check_at_least", C.c_uint32), ("stats", C.POINTER(_Stats)),
                 ("k1", C.c_double), ("k3", C.c_double), ("b", C.c_double), ("min_normlen", C.c_double),
                 ("filter", C.c_int), ("range_lo", C.c_uint64), ("range_hi", C.c_uint64),
-                ("sort_by", C.c_int), ("sort_slot", C.c_int), ("sort_reverse", C.c_int)]
+                ("sort_by", C.c_int), ("sort_slot", C.c_int), ("sort_reverse", C.c_int),
+                ("nfilter", C.c_uint32), ("filter_terms", C.POINTER(C.c_uint32)),
+                ("nnot", C.c_uint32), ("not_terms", C.POINTER(C.c_uint32)),
+                ("nmaybe", C.c_uint32), ("maybe_terms", C.POINTER(C.c_uint32))]
 
 
 class _MSet(C.Structure):
@@ -136,8 +139,13 @@ class Query:
     sort_by: int = SORT_REL
     sort_slot: int = 1
     sort_reverse: bool = False
-    # global stats for the two-phase scheme: (collection_size, total_length, [termfreq per term])
+    # global stats for the two-phase scheme: (collection_size, total_length, [termfreq per term]
+    # [, [termfreq per maybe term]])
     stats: Optional[tuple] = None
+    # OP_FILTER(q, AND of boolean terms) / OP_AND_NOT(q, OR of terms) / OP_AND_MAYBE(q, OR of terms), AND base only
+    filter_terms: Sequence[int] = ()
+    not_terms: Sequence[int] = ()
+    maybe_terms: Sequence[int] = ()
 
 
 def _mset_from_c(m: _MSet) -> MSet:
@@ -253,8 +261,17 @@ class Index:
         cq.sort_by, cq.sort_slot, cq.sort_reverse = q.sort_by, q.sort_slot, int(q.sort_reverse)
         if q.stats is not None:
             tf = (C.c_uint32 * len(q.terms))(*q.stats[2])
-            st = _Stats(q.stats[0], q.stats[1], tf)
+            mtf = None
+            if len(q.stats) > 3 and q.stats[3] is not None:
+                mtf = (C.c_uint32 * len(q.maybe_terms))(*q.stats[3])
+            st = _Stats(q.stats[0], q.stats[1], tf, mtf)
             cq.stats = C.pointer(st)
+        keep = []
+        for name, ts in (("filter", q.filter_terms), ("not", q.not_terms), ("maybe", q.maybe_terms)):
+            arr = (C.c_uint32 * max(1, len(ts)))(*ts)
+            keep.append(arr)
+            setattr(cq, "n" + name, len(ts))
+            setattr(cq, name + "_terms", arr)
         m = _MSet()
         rc = L.orc_match(self._p, C.byref(cq), C.byref(m))
         if rc != 0:
@@ -379,8 +396,12 @@ def ref_build_parallel(out_dir: str, ndocs: int, vocab: int, seed: int = 12345, 
 
 
 def query_line(op: str, terms: Sequence[str], first: int, maxitems: int, check_at_least: int = 0,
-               vr: Optional[tuple] = None, sort: Optional[tuple] = None) -> str:
+               vr: Optional[tuple] = None, sort: Optional[tuple] = None, filter_terms: Sequence[str] = (),
+               not_terms: Sequence[str] = (), maybe_terms: Sequence[str] = ()) -> str:
     s = f"{op} {first} {maxitems} {check_at_least} {len(terms)} " + " ".join(terms)
+    for tag, ts in (("FT", filter_terms), ("NOT", not_terms), ("MAYBE", maybe_terms)):
+        if ts:
+            s += f" {tag} {len(ts)} " + " ".join(ts)
     if vr is not None:
         s += f" VR {vr[0]} {vr[1]} {vr[2]}"
     if sort is not None:

@@ -140,6 +140,9 @@ struct QSpec {
     std::vector<std::string> terms;
     bool has_range = false;   /* VR slot lo hi → OP_FILTER(q, OP_VALUE_RANGE) */
     uint32_t r_slot = 0; double r_lo = 0, r_hi = 0;
+    /* FT n t.. → OP_FILTER(q, AND of boolean terms); NOT n t.. → OP_AND_NOT(q, OR of terms);
+     * MAYBE n t.. → OP_AND_MAYBE(q, OR of terms); applied in that order (innermost first) */
+    std::vector<std::string> filter_terms, not_terms, maybe_terms;
     bool has_sort = false;    /* SORT slot reverse → set_sort_by_value_then_relevance */
     uint32_t s_slot = 0; bool s_rev = false;
 };
@@ -160,6 +163,11 @@ static std::vector<QSpec> load_queries(const std::string& path) {
         while (is >> tok) {
             if (tok == "VR") { q.has_range = true; is >> q.r_slot >> q.r_lo >> q.r_hi; }
             else if (tok == "SORT") { q.has_sort = true; int r; is >> q.s_slot >> r; q.s_rev = r != 0; }
+            else if (tok == "FT" || tok == "NOT" || tok == "MAYBE") {
+                uint32_t m; is >> m;
+                std::vector<std::string>& dst = tok == "FT" ? q.filter_terms : tok == "NOT" ? q.not_terms : q.maybe_terms;
+                for (uint32_t i = 0; i < m; ++i) { std::string t; is >> t; dst.push_back(t); }
+            }
             else die("bad token " + tok);
         }
         if (!is.eof() && is.fail()) die("bad query line: " + line);
@@ -179,6 +187,15 @@ static Xapian::Query make_query(const QSpec& q) {
                         Xapian::sortable_serialise(q.r_lo), Xapian::sortable_serialise(q.r_hi));
         base = Xapian::Query(Xapian::Query::OP_FILTER, base, r);
     }
+    auto group = [](Xapian::Query::op op, const std::vector<std::string>& ts) {
+        return ts.size() == 1 ? Xapian::Query(ts[0]) : Xapian::Query(op, ts.begin(), ts.end());
+    };
+    if (!q.filter_terms.empty())
+        base = Xapian::Query(Xapian::Query::OP_FILTER, base, group(Xapian::Query::OP_AND, q.filter_terms));
+    if (!q.not_terms.empty())
+        base = Xapian::Query(Xapian::Query::OP_AND_NOT, base, group(Xapian::Query::OP_OR, q.not_terms));
+    if (!q.maybe_terms.empty())
+        base = Xapian::Query(Xapian::Query::OP_AND_MAYBE, base, group(Xapian::Query::OP_OR, q.maybe_terms));
     return base;
 }
 

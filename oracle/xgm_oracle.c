@@ -478,6 +478,72 @@ static uint64_t sort_value(const orc_index* ix, const orc_query* q, uint32_t did
     }
 }
 
+/* (termfreq min, max, est, max weight) of a subtree, as the reference's PostList classes report them */
+typedef struct { uint32_t mn, mx, est; double maxw; } node_t;
+
+/* OrContext::postlist (api/queryinternal.cc:440-489) over leaves with termfreqs tf[] and max weights mw[]
+ * (NULL = unweighted): OrPostList::get_termfreq_min/max/est (matcher/orpostlist.cc:80-83,353-384) and
+ * recalc_maxweight (l_max + r_max) folded over the Huffman-shaped tree.  prog (size 2n) receives the
+ * postfix program. */
+static node_t or_tree_node(const uint32_t* tf, const double* mw, uint32_t n, uint32_t doccount, int32_t* prog,
+                           uint32_t* nprog_out) {
+    node_t r;
+    uint32_t nprog = orc_or_program(tf, n, prog);
+    if (nprog_out) *nprog_out = nprog;
+    double dbsize = doccount;
+    node_t* st = (node_t*)xcalloc(2 * n + 2, sizeof(node_t));
+    uint32_t sp = 0;
+    for (uint32_t i = 0; i < nprog; ++i) {
+        if (prog[i] >= 0) {
+            st[sp].mn = st[sp].mx = st[sp].est = tf[prog[i]];
+            st[sp].maxw = mw ? mw[prog[i]] : 0.0;
+            ++sp;
+        } else {
+            --sp;
+            node_t* l = &st[sp - 1];
+            const node_t* rr = &st[sp];
+            l->maxw = l->maxw + rr->maxw;
+            l->mn = l->mn > rr->mn ? l->mn : rr->mn;
+            uint32_t t = l->mx + rr->mx;
+            if (t > doccount || t < l->mx) t = doccount;
+            l->mx = t;
+            double a = (double)l->est, b2 = (double)rr->est;
+            l->est = dbsize == 0.0 ? 0 : (uint32_t)(a + b2 - (a * b2 / dbsize) + 0.5);
+        }
+    }
+    r = st[0];
+    free(st);
+    return r;
+}
+
+/* MultiAndPostList over two subtrees (QueryFilter::postlist): get_termfreq_min/max/est
+ * matcher/multiandpostlist.cc:55-105 with the children in ascending-estimate order; the maximum weight is
+ * the sum of the children's (one of them is 0 here, so the order of the sum is immaterial). */
+static node_t and_pair_node(node_t a, node_t b, uint32_t doccount) {
+    node_t c0 = a, c1 = b, r;
+    if (b.est < a.est) { c0 = b; c1 = a; }
+    uint32_t sum = c0.mn;
+    if (sum) {
+        uint32_t old = sum;
+        sum += c1.mn;
+        if (sum >= old && sum <= doccount) sum = 0;
+        else sum -= doccount;
+    }
+    r.mn = sum;
+    r.mx = c0.mx < c1.mx ? c0.mx : c1.mx;
+    double e = doccount ? ((double)c0.est * (double)c1.est) / (double)doccount : 0.0;
+    r.est = doccount ? (uint32_t)(e + 0.5) : 0;
+    r.maxw = c0.maxw + c1.maxw;
+    return r;
+}
+
+static int list_contains(const uint32_t* d, uint32_t n, uint32_t did, uint32_t* where) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { uint32_t m = (lo + hi) / 2; if (d[m] < did) lo = m + 1; else hi = m; }
+    if (where) *where = lo;
+    return lo < n && d[lo] == did;
+}
+
 int orc_match(const orc_index* ix, const orc_query* q, orc_mset* out) {
     memset(out, 0, sizeof(*out));
     uint32_t n = q->nterms;
@@ -566,6 +632,79 @@ int orc_match(const orc_index* ix, const orc_query* q, orc_mset* out) {
         free(sm); free(se); free(smin); free(smax);
     }
 
+    /* §8(f)-1 groups around an AND base */
+    const uint32_t nf = q->nfilter, nx = q->nnot, nm = q->nmaybe;
+    if ((nf || nx || nm) && (q->op != ORC_OP_AND || q->filter != ORC_FILTER_NONE)) return -1;
+    uint32_t* mlen = NULL; double* mtw = NULL; double* mmax = NULL; int32_t* mprog = NULL; uint32_t mnprog = 0;
+    if (nf || nx || nm) {
+        node_t cur; cur.mn = tf_min; cur.mx = tf_max; cur.est = tf_est; cur.maxw = max_possible;
+        if (nf) {
+            node_t f;
+            uint32_t* fl = (uint32_t*)xcalloc(nf, 4);
+            for (uint32_t i = 0; i < nf; ++i) fl[i] = (uint32_t)(ix->off[q->filter_terms[i] + 1] - ix->off[q->filter_terms[i]]);
+            if (nf == 1) { f.mn = f.mx = f.est = fl[0]; }
+            else {
+                /* Query(OP_AND, boolean terms): a MultiAndPostList of unweighted leaves */
+                uint32_t* fo = (uint32_t*)xcalloc(nf, 4);
+                orc_and_order(fl, nf, fo);
+                uint32_t sum = fl[fo[0]];
+                if (sum) for (uint32_t i = 1; i < nf; ++i) {
+                    uint32_t old = sum; sum += fl[fo[i]];
+                    if (sum >= old && sum <= ix->doccount) { sum = 0; break; }
+                    sum -= ix->doccount;
+                }
+                f.mn = sum;
+                f.mx = fl[fo[0]];
+                for (uint32_t i = 1; i < nf; ++i) if (fl[fo[i]] < f.mx) f.mx = fl[fo[i]];
+                double r = fl[fo[0]];
+                for (uint32_t i = 1; i < nf; ++i) r = (r * fl[fo[i]]) / dbsize;
+                f.est = ix->doccount ? (uint32_t)(r + 0.5) : 0;
+                free(fo);
+            }
+            f.maxw = 0.0;
+            cur = and_pair_node(cur, f, ix->doccount);
+            free(fl);
+        }
+        if (nx) {
+            /* AndNotPostList::get_termfreq_min/max/est matcher/andnotpostlist.cc:30-62; the weight is the left's */
+            uint32_t* xl = (uint32_t*)xcalloc(nx, 4);
+            int32_t* xp = (int32_t*)xcalloc(2 * nx + 2, 4);
+            for (uint32_t i = 0; i < nx; ++i) xl[i] = (uint32_t)(ix->off[q->not_terms[i] + 1] - ix->off[q->not_terms[i]]);
+            node_t r;
+            if (nx == 1) { r.mn = r.mx = r.est = xl[0]; r.maxw = 0; }
+            else r = or_tree_node(xl, NULL, nx, ix->doccount, xp, NULL);
+            node_t a = cur;
+            cur.mn = a.mn <= r.mx ? 0 : a.mn - r.mx;
+            cur.mx = ix->doccount - r.mn < a.mx ? ix->doccount - r.mn : a.mx;
+            if (ix->doccount == 0) cur.est = 0;
+            else {
+                double e = a.est;
+                e = (e * (double)(ix->doccount - r.est)) / (double)ix->doccount;
+                cur.est = (uint32_t)(e + 0.5);
+            }
+            free(xl); free(xp);
+        }
+        if (nm) {
+            /* AndMaybePostList: termfreqs are the left's (WrapperPostList), recalc_maxweight = pl_max + r_max
+             * matcher/andmaybepostlist.cc:69-75 */
+            mlen = (uint32_t*)xcalloc(nm, 4); mtw = (double*)xcalloc(nm, 8); mmax = (double*)xcalloc(nm, 8);
+            mprog = (int32_t*)xcalloc(2 * nm + 2, 4);
+            for (uint32_t i = 0; i < nm; ++i) {
+                uint32_t t = q->maybe_terms[i];
+                mlen[i] = (uint32_t)(ix->off[t + 1] - ix->off[t]);
+                uint32_t gtf = (q->stats && q->stats->maybe_termfreq) ? q->stats->maybe_termfreq[i] : mlen[i];
+                double lf;
+                orc_bm25_init(coll, tlen, gtf, 1, 1.0, q->k1, q->k3, q->b, &mtw[i], &lf);
+                mmax[i] = orc_bm25_maxpart(mtw[i], lf, q->k1, q->b, q->min_normlen, ix->wdf_ub[t], ix->doclen_lb);
+            }
+            node_t r;
+            if (nm == 1) { r.maxw = mmax[0]; mprog[0] = 0; mnprog = 1; }
+            else r = or_tree_node(mlen, mmax, nm, ix->doccount, mprog, &mnprog);
+            cur.maxw = cur.maxw + r.maxw;
+        }
+        tf_min = cur.mn; tf_max = cur.mx; tf_est = cur.est; max_possible = cur.maxw;
+    }
+
     proto_t P;
     memset(&P, 0, sizeof(P));
     P.max_size = first + maxitems;
@@ -573,11 +712,11 @@ int orc_match(const orc_index* ix, const orc_query* q, orc_mset* out) {
     P.results = (res_t*)xcalloc((size_t)P.max_size + 1, sizeof(res_t));
     P.cmp.sort_by = q->sort_by;
     P.cmp.reverse = q->sort_reverse;
-    uint32_t total_subqs = n; /* weighted leaves, api/queryinternal.cc:1053-1054 */
+    uint32_t total_subqs = n + nm; /* weighted leaves, api/queryinternal.cc:1053-1054 */
 
     uint64_t* pos = (uint64_t*)xcalloc(n, 8);
-    double* stk = (double*)xcalloc(2 * n + 2, 8);
-    int* stkp = (int*)xcalloc(2 * n + 2, sizeof(int));
+    double* stk = (double*)xcalloc(2 * (n + nm) + 2, 8);
+    int* stkp = (int*)xcalloc(2 * (n + nm) + 2, sizeof(int));
     uint32_t exact = 0;
 
     if (check_at_least != 0) {
@@ -612,6 +751,40 @@ int orc_match(const orc_index* ix, const orc_query* q, orc_mset* out) {
                     weight += orc_bm25_sumpart(tw[j], len_factor, q->k1, q->b, q->min_normlen, wl[j][pos[j]], doclen);
                 }
                 subqs = n;
+                if (nf || nx || nm) {
+                    int keep = 1;
+                    for (uint32_t i = 0; i < nf && keep; ++i) {
+                        uint32_t t = q->filter_terms[i];
+                        keep = list_contains(ix->docids + ix->off[t], (uint32_t)(ix->off[t + 1] - ix->off[t]), did, NULL);
+                    }
+                    for (uint32_t i = 0; i < nx && keep; ++i) {
+                        uint32_t t = q->not_terms[i];
+                        keep = !list_contains(ix->docids + ix->off[t], (uint32_t)(ix->off[t + 1] - ix->off[t]), did, NULL);
+                    }
+                    if (!keep) continue;
+                    if (nm) {
+                        /* AndMaybePostList::get_weight matcher/andmaybepostlist.cc:59-67: l + (r if it matches);
+                         * r is the OrPostList tree over the optional leaves (l, r or l + r per node) */
+                        uint32_t sp = 0, present = 0;
+                        for (uint32_t i = 0; i < mnprog; ++i) {
+                            if (mprog[i] >= 0) {
+                                uint32_t j = (uint32_t)mprog[i], t = q->maybe_terms[j], where;
+                                if (list_contains(ix->docids + ix->off[t], mlen[j], did, &where)) {
+                                    stk[sp] = orc_bm25_sumpart(mtw[j], len_factor, q->k1, q->b, q->min_normlen,
+                                                               ix->wdfs[ix->off[t] + where], doclen);
+                                    stkp[sp] = 1;
+                                    ++present;
+                                } else { stk[sp] = 0; stkp[sp] = 0; }
+                                ++sp;
+                            } else {
+                                --sp;
+                                if (stkp[sp - 1] && stkp[sp]) stk[sp - 1] = stk[sp - 1] + stk[sp];
+                                else if (stkp[sp]) { stk[sp - 1] = stk[sp]; stkp[sp - 1] = 1; }
+                            }
+                        }
+                        if (present) { weight = weight + stk[0]; subqs += present; }
+                    }
+                }
             } else {
                 /* union in docid order; OrPostList::get_weight matcher/orpostlist.cc:93-103 folds
                  * l, r or l+r per node of the Huffman-shaped tree */
@@ -694,6 +867,7 @@ int orc_match(const orc_index* ix, const orc_query* q, orc_mset* out) {
     out->max_attained = P.max_weight;
     out->percent_scale_factor = percent_scale * 100.0;
 
+    free(mlen); free(mtw); free(mmax); free(mprog);
     free(P.results); free(pos); free(stk); free(stkp); free(order); free(prog);
     free(dl); free(wl); free(len); free(tw); free(maxpart);
     return 0;

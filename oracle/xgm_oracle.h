@@ -41,6 +41,7 @@ typedef struct orc_stats {
     uint32_t collection_size;
     uint64_t total_length;
     const uint32_t* termfreq; /* per query term, global */
+    const uint32_t* maybe_termfreq; /* per AND_MAYBE term, global (NULL = this index's own) */
 } orc_stats;
 
 enum { ORC_OP_AND = 0, ORC_OP_OR = 1 };
@@ -61,6 +62,16 @@ typedef struct orc_query {
     int sort_by;              /* ORC_SORT_* */
     int sort_slot;            /* 0: smallest slot-0 value, 1: slot 1, 2: largest slot-0 value */
     int sort_reverse;         /* set_sort_by_value_then_relevance(slot, reverse) */
+    /* SURVEY.md §8(f)-1 shapes around an AND (or single-term) base, innermost first:
+     *   OP_FILTER(base, AND of boolean terms)      QueryFilter::postlist   api/queryinternal.cc:2270-2283
+     *   OP_AND_NOT(…, OR of terms)                 QueryAndNot::postlist   api/queryinternal.cc:2208-2225
+     *   OP_AND_MAYBE(…, OR of weighted terms)      QueryAndMaybe::postlist api/queryinternal.cc:2247-2268 */
+    uint32_t nfilter;
+    const uint32_t* filter_terms;
+    uint32_t nnot;
+    const uint32_t* not_terms;
+    uint32_t nmaybe;
+    const uint32_t* maybe_terms;
 } orc_query;
 
 typedef struct orc_mset {

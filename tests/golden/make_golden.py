@@ -34,7 +34,10 @@ def run_set(tag, ndocs, vocab, queries, nshards=1, twophase=False, values=False,
         lines = []
         for q in queries:
             lines.append(O.query_line("TERM" if len(q["terms"]) == 1 else q["op"], [name(t) for t in q["terms"]],
-                                      q["first"], q["maxitems"], q["check_at_least"], vr=q.get("vr"), sort=q.get("sort")))
+                                      q["first"], q["maxitems"], q["check_at_least"], vr=q.get("vr"), sort=q.get("sort"),
+                                      filter_terms=[name(t) for t in q.get("filter_terms", [])],
+                                      not_terms=[name(t) for t in q.get("not_terms", [])],
+                                      maybe_terms=[name(t) for t in q.get("maybe_terms", [])]))
         info, res = O.ref_query(dbs, lines, os.path.join(tmp, "w"), twophase=twophase)
         fixture = dict(tag=tag, ndocs=ndocs, vocab=vocab, seed=seed, nshards=nshards, twophase=twophase, values=values,
                        queries=[])
@@ -74,9 +77,27 @@ def mixed(rng, n, topranks, ndocs, big_or_items):
     return qs
 
 
+def ops_queries(rng, n, topranks, ndocs):
+    """SURVEY.md §8(f)-1 shapes: OP_FILTER with boolean terms, OP_AND_NOT, OP_AND_MAYBE around an AND base."""
+    qs = []
+    for _ in range(n):
+        nb = rng.choice([1, 2, 2, 3])
+        pool = rng.sample(range(topranks), nb + 9)
+        nf, nx, nm = rng.choice([0, 0, 1, 2, 3]), rng.choice([0, 0, 1, 2, 3]), rng.choice([0, 0, 1, 2, 3])
+        if nf + nx + nm == 0:
+            nx = 1
+        qs.append(dict(op="AND", terms=pool[:nb], first=rng.choice([0, 0, 3]), maxitems=rng.choice([5, 10, 50, 200]),
+                       check_at_least=rng.choice([0, 0, ndocs]), filter_terms=pool[nb:nb + nf],
+                       not_terms=pool[nb + 3:nb + 3 + nx], maybe_terms=pool[nb + 6:nb + 6 + nm]))
+    return qs
+
+
 def main():
     if not O.have_reference():
         raise SystemExit("oracle/_ref not built: run oracle/build_ref.sh (needs /root/reference)")
+    if sys.argv[1:] == ["ops"]:  # only the fixture added after round 1's first batch
+        run_set("ops_6k", 6000, 900, ops_queries(random.Random(20260924), 240, 200, 6000), seed=11)
+        return
     rng = random.Random(20260923)
     # C1: BASELINE config 1 — 1k docs / 100 terms, every single term top-10, plus mixed shapes
     c1 = [dict(op="AND", terms=[t], first=0, maxitems=10, check_at_least=0) for t in range(100)]
@@ -102,6 +123,7 @@ def main():
             q["sort"] = [1, rng.choice([0, 1])]
         vq.append(q)
     run_set("values_5k", 5000, 2000, vq, values=True)
+    run_set("ops_6k", 6000, 900, ops_queries(random.Random(20260924), 240, 200, 6000), seed=11)
 
 
 if __name__ == "__main__":

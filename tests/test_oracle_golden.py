@@ -21,6 +21,9 @@ def o_query(q, stats=None, first=None, maxitems=None):
         kw.update(filter=O.FILTER_VALUE_RANGE_MIN, range_lo=q["vr"][1], range_hi=q["vr"][2])
     if "sort" in q:
         kw.update(sort_by=O.SORT_VAL_REL, sort_slot=q["sort"][0], sort_reverse=bool(q["sort"][1]))
+    for g in ("filter_terms", "not_terms", "maybe_terms"):
+        if q.get(g):
+            kw[g] = q[g]
     return O.Query(**kw)
 
 
@@ -39,6 +42,19 @@ def test_oracle_matches_reference_single_db(tag):
     ix = O.Index.synthetic(fx["ndocs"], fx["vocab"], fx["seed"])
     for i, q in enumerate(fx["queries"]):
         check(ix.match(o_query(q)), q, f"{tag}[{i}] {q['op']} {q['terms']}")
+
+
+def test_oracle_matches_reference_filter_andnot_andmaybe():
+    """OP_FILTER with boolean terms, OP_AND_NOT, OP_AND_MAYBE around an AND base
+    (api/queryinternal.cc:2208-2283, matcher/andnotpostlist.cc, andmaybepostlist.cc) — docids, weights,
+    bounds, max_possible and max_attained bit-equal with the compiled reference."""
+    fx = load("ops_6k")
+    ix = O.Index.synthetic(fx["ndocs"], fx["vocab"], fx["seed"])
+    shapes = set()
+    for i, q in enumerate(fx["queries"]):
+        check(ix.match(o_query(q)), q, f"ops[{i}] {q}")
+        shapes.add((bool(q["filter_terms"]), bool(q["not_terms"]), bool(q["maybe_terms"])))
+    assert len(shapes) >= 7  # every combination of the three groups is present
 
 
 def test_oracle_matches_reference_twophase_shards():
