@@ -150,6 +150,15 @@ typedef struct xgm_query {
     uint32_t filter, filter_slot;
     uint64_t range_lo, range_hi;
     uint32_t sort_by, sort_slot, sort_reverse, sort_use_max; /* sort_use_max: key = largest value of the slot */
+    /* Term groups around an XGM_OP_AND (or single-term) base, innermost first.  Their
+     * terms follow the nterms base terms in terms / term_lens / term_ids (and stats->termfreq):
+     *   nfilter  OP_FILTER(base, AND of boolean terms)   QueryFilter::postlist   api/queryinternal.cc:2270-2283
+     *   nnot     OP_AND_NOT(…, OR of terms)              QueryAndNot::postlist   api/queryinternal.cc:2208-2225,
+     *                                                     AndNotPostList matcher/andnotpostlist.cc
+     *   nmaybe   OP_AND_MAYBE(…, OR of weighted terms)   QueryAndMaybe::postlist api/queryinternal.cc:2247-2268
+     *            — declined for now (XGM_E_UNIMPLEMENTED: the shim lets the reference matcher run it)
+     * nterms + nfilter + nnot + nmaybe <= XGM_MAX_TERMS. */
+    uint32_t nfilter, nnot, nmaybe, reserved;
 } xgm_query;
 
 /* One query's result: the fields of MSet::Internal (src/xapian/api/msetinternal.h:58-99). */

@@ -191,3 +191,32 @@ def test_device_merge_matches_reference_twophase():
         assert got_n == len(q["docids"]), f"merge[{i}]"
         assert list(od[i, :got_n]) == q["docids"], f"merge[{i}] docids"
         assert all(bits(a) == bits(b) for a, b in zip(ow[i, :got_n], q["weights"])), f"merge[{i}] weights"
+
+
+def test_cuda_matches_reference_filter_and_andnot():
+    """SURVEY.md §8(f)-1 on the device: OP_FILTER with boolean terms and OP_AND_NOT around an AND base against
+    the compiled reference's MSets (ops_6k fixture); OP_AND_MAYBE is declined, not guessed."""
+    fx = load("ops_6k")
+    ix = xgm.Index.synthetic(fx["ndocs"], fx["vocab"], fx["seed"])
+    name = lambda t: f"T{t:06d}"
+    qs = [xgm.Query(xgm.OP_AND, [name(t) for t in q["terms"]], first=q["first"], maxitems=q["maxitems"],
+                    check_at_least=q["check_at_least"], filter_terms=[name(t) for t in q["filter_terms"]],
+                    not_terms=[name(t) for t in q["not_terms"]], maybe_terms=[name(t) for t in q["maybe_terms"]])
+          for q in fx["queries"]]
+    res = xgm.Searcher(ix, max_batch=len(qs), max_topk=256).search(qs)
+    checked = 0
+    for i, (q, m) in enumerate(zip(fx["queries"], res)):
+        ctx = f"ops[{i}] {q['terms']} F{q['filter_terms']} N{q['not_terms']} M{q['maybe_terms']}"
+        if q["maybe_terms"]:
+            assert m.status == xgm.E_UNIMPLEMENTED, ctx
+            continue
+        assert m.status == 0, ctx
+        assert list(m.docids) == q["docids"], ctx
+        assert all(bits(a) == bits(b) for a, b in zip(m.weights, q["weights"])), ctx
+        assert bits(m.max_possible) == bits(q["max_possible"]) and bits(m.max_attained) == bits(q["max_attained"]), ctx
+        assert m.matches_upper_bound == q["ub"], ctx
+        if not (m.flags & 1):
+            assert (m.matches_lower_bound, m.get_matches_estimated()) == (q["lb"], q["est"]), ctx
+        checked += 1
+    assert checked > 100
+

@@ -977,6 +977,32 @@ static void build_or_tree(const uint32_t* tf, uint32_t n, OrTree& tr) {
     }
 }
 
+/* Termfreq (min, max, estimate) of an OrContext::postlist tree over leaves with termfreqs tf[]:
+ * OrPostList::get_termfreq_min/max/est (matcher/orpostlist.cc:80-83,353-384) folded bottom-up. */
+struct TfNode { uint32_t mn, mx, est; };
+static TfNode or_group_node(const uint32_t* tf, uint32_t n, uint32_t doccount) {
+    TfNode out{0, 0, 0};
+    if (n == 0) return out;
+    if (n == 1) return TfNode{tf[0], tf[0], tf[0]};
+    OrTree tr;
+    build_or_tree(tf, n, tr);
+    TfNode val[2 * XGM_MAX_TERMS];
+    for (uint32_t i = 0; i < n; ++i) val[i] = TfNode{tf[i], tf[i], tf[i]};
+    const double dbsize = doccount;
+    for (int node = (int)n; node <= tr.root; ++node) { /* internal nodes are created children-first */
+        const TfNode l = val[tr.lch[node]], r = val[tr.rch[node]];
+        TfNode v;
+        v.mn = std::max(l.mn, r.mn);
+        uint32_t t = l.mx + r.mx;
+        if (t > doccount || t < l.mx) t = doccount;
+        v.mx = t;
+        const double a = l.est, b = r.est;
+        v.est = dbsize == 0.0 ? 0 : (uint32_t)(a + b - (a * b / dbsize) + 0.5);
+        val[node] = v;
+    }
+    return val[tr.root];
+}
+
 /* BM25Weight::init (bm25weight.cc:46-130) via Weight::init_ (weight.cc:59-83); host-side because it
  * needs log() and runs once per term per query. */
 static double bm25_termweight(uint32_t N, uint32_t tf, uint32_t wqf, double factor, double k1, double k3) {
@@ -1013,12 +1039,23 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
     memset(&dq, 0, sizeof(dq));
     if (q.nterms == 0 || q.nterms > XGM_MAX_TERMS) { pq.status = XGM_E_UNIMPLEMENTED; return XGM_OK; }
     if (q.op != XGM_OP_AND && q.op != XGM_OP_OR) { pq.status = XGM_E_UNIMPLEMENTED; return XGM_OK; }
+    const uint32_t nfilter = q.nfilter, nnot = q.nnot, ngroups = q.nfilter + q.nnot + q.nmaybe;
+    if (ngroups) {
+        /* OP_FILTER with boolean terms / OP_AND_NOT around an AND (or single-term) base; OP_AND_MAYBE, an OR
+         * base, a value-range filter on top, or the chunked kernel variant are left to the reference */
+        if (q.nmaybe || (q.op != XGM_OP_AND && q.nterms != 1) || q.filter != XGM_FILTER_NONE || s->and_version != 1 ||
+            (uint64_t)q.nterms + ngroups > XGM_MAX_TERMS) {
+            pq.status = XGM_E_UNIMPLEMENTED;
+            return XGM_OK;
+        }
+    }
     if (q.sort_by > XGM_SORT_REL_VAL || q.filter > XGM_FILTER_MULTI_RANGE) { pq.status = XGM_E_INVALID; return XGM_OK; }
     if ((q.filter && q.filter_slot >= XGM_MAX_SLOTS) || (q.sort_by && q.sort_slot >= XGM_MAX_SLOTS)) { pq.status = XGM_E_INVALID; return XGM_OK; }
     const uint32_t n = q.nterms;
+    const uint32_t nall = n + ngroups; /* base terms, then filter terms, then excluded terms */
     uint32_t ids[XGM_MAX_TERMS];
     uint32_t ltf[XGM_MAX_TERMS];
-    for (uint32_t j = 0; j < n; ++j) {
+    for (uint32_t j = 0; j < nall; ++j) {
         uint32_t id = 0xffffffffu;
         if (q.term_ids) id = q.term_ids[j];
         else if (q.terms && q.terms[j]) {
@@ -1056,7 +1093,7 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
         uint32_t wub = ids[j] == 0xffffffffu ? 0 : ix->terms[ids[j]].wdf_ub;
         maxpart[j] = bm25_maxpart(tw[j], len_factor, k1, b, mnl, wub, ix->doclen_lb);
     }
-    dq.op = q.op; dq.nterms = n; dq.topk = pq.topk; dq.check_at_least = cal;
+    dq.op = q.op; dq.nterms = n + nfilter; dq.nweighted = n; dq.topk = pq.topk; dq.check_at_least = cal;
     dq.len_factor = len_factor; dq.k1 = k1; dq.b = b; dq.one_minus_b = 1 - b; dq.min_normlen = mnl;
     dq.filter = q.filter; dq.filter_slot = q.filter_slot; dq.range_lo = q.range_lo; dq.range_hi = q.range_hi;
     dq.sort_by = q.sort_by; dq.sort_slot = q.sort_slot; dq.sort_reverse = q.sort_reverse; dq.sort_use_max = q.sort_use_max;
@@ -1089,16 +1126,87 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
         for (uint32_t i = 1; i < n; ++i) r = (r * ltf[order[i]]) / dbsize;
         pq.tf_est = ix->doccount ? (uint32_t)(r + 0.5) : 0;
         dq.route = 0;
-        for (uint32_t i = 0; i < n; ++i) {
-            uint32_t j = order[i];
-            dq.terms[i].termweight = tw[j];
-            dq.terms[i].maxpart = maxpart[j];
-            dq.terms[i].bm_off = XGM_NO_BITMAP;
+        auto put_term = [&](uint32_t slot, uint32_t j, bool weighted) {
+            dq.terms[slot].termweight = weighted ? tw[j] : 0.0; /* a boolean leaf contributes +0.0: sums unchanged */
+            dq.terms[slot].maxpart = weighted ? maxpart[j] : 0.0;
+            dq.terms[slot].bm_off = XGM_NO_BITMAP;
             if (ids[j] != 0xffffffffu) {
                 const TermInfo& tinf = ix->terms[ids[j]];
-                dq.terms[i].blk_begin = tinf.blk_begin; dq.terms[i].nblocks = tinf.nblocks;
-                dq.terms[i].bm_off = tinf.bm_off; dq.terms[i].rk_off = tinf.rk_off;
+                dq.terms[slot].blk_begin = tinf.blk_begin; dq.terms[slot].nblocks = tinf.nblocks;
+                dq.terms[slot].bm_off = tinf.bm_off; dq.terms[slot].rk_off = tinf.rk_off;
             }
+        };
+        if (ngroups == 0) {
+            for (uint32_t i = 0; i < n; ++i) put_term(i, order[i], true);
+        } else {
+            /* bounds of the nested tree: MultiAnd(base, filter) → AndNot(…, OR of excluded) */
+            TfNode cur{pq.tf_min, pq.tf_max, pq.tf_est};
+            if (nfilter) {
+                /* QueryFilter::postlist: MultiAndPostList of [base, Query(OP_AND, boolean terms)] */
+                const uint32_t* ftf = ltf + n;
+                TfNode f{ftf[0], ftf[0], ftf[0]};
+                if (nfilter > 1) {
+                    TfIdx fin[XGM_MAX_TERMS], fo[XGM_MAX_TERMS];
+                    for (uint32_t j = 0; j < nfilter; ++j) { fin[j].tf = ftf[j]; fin[j].idx = j; }
+                    std::partial_sort_copy(fin, fin + nfilter, fo, fo + nfilter, [](const TfIdx& a, const TfIdx& c) { return a.tf < c.tf; });
+                    uint32_t fs = fo[0].tf;
+                    if (fs) for (uint32_t i = 1; i < nfilter; ++i) {
+                        uint32_t old = fs; fs += fo[i].tf;
+                        if (fs >= old && fs <= ix->doccount) { fs = 0; break; }
+                        fs -= ix->doccount;
+                    }
+                    f.mn = fs;
+                    f.mx = fo[0].tf;
+                    for (uint32_t i = 1; i < nfilter; ++i) f.mx = std::min(f.mx, fo[i].tf);
+                    double fr = fo[0].tf;
+                    for (uint32_t i = 1; i < nfilter; ++i) fr = (fr * fo[i].tf) / dbsize;
+                    f.est = ix->doccount ? (uint32_t)(fr + 0.5) : 0;
+                }
+                TfNode c0 = cur, c1 = f; /* children in ascending-estimate order */
+                if (f.est < cur.est) { c0 = f; c1 = cur; }
+                uint32_t ms = c0.mn;
+                if (ms) {
+                    uint32_t old = ms; ms += c1.mn;
+                    if (ms >= old && ms <= ix->doccount) ms = 0; else ms -= ix->doccount;
+                }
+                cur.mn = ms;
+                cur.mx = std::min(c0.mx, c1.mx);
+                cur.est = ix->doccount ? (uint32_t)(((double)c0.est * (double)c1.est) / dbsize + 0.5) : 0;
+            }
+            if (nnot) {
+                /* AndNotPostList::get_termfreq_min/max/est, matcher/andnotpostlist.cc:30-62 */
+                const TfNode rr = or_group_node(ltf + n + nfilter, nnot, ix->doccount);
+                const TfNode a = cur;
+                cur.mn = a.mn <= rr.mx ? 0 : a.mn - rr.mx;
+                cur.mx = std::min(ix->doccount - rr.mn, a.mx);
+                if (ix->doccount == 0) cur.est = 0;
+                else {
+                    double e = a.est;
+                    e = (e * (double)(ix->doccount - rr.est)) / dbsize;
+                    cur.est = (uint32_t)(e + 0.5);
+                }
+            }
+            pq.tf_min = cur.mn; pq.tf_max = cur.mx; pq.tf_est = cur.est;
+            /* device lists: required = base (its own MultiAndPostList order, which fixes the order of the
+             * weight sum) merged with the boolean filter terms by ascending termfreq; then the excluded lists
+             * that exist in this index */
+            TfIdx fin[XGM_MAX_TERMS], fo[XGM_MAX_TERMS];
+            for (uint32_t j = 0; j < nfilter; ++j) { fin[j].tf = ltf[n + j]; fin[j].idx = n + j; any_absent |= (ltf[n + j] == 0); }
+            std::stable_sort(fin, fin + nfilter, [](const TfIdx& a, const TfIdx& c) { return a.tf < c.tf; });
+            (void)fo;
+            uint32_t slot = 0, bi = 0, fi = 0;
+            while (bi < n || fi < nfilter) {
+                if (fi >= nfilter || (bi < n && ltf[order[bi]] <= fin[fi].tf)) put_term(slot++, order[bi++], true);
+                else put_term(slot++, fin[fi++].idx, false);
+            }
+            uint32_t kept = 0;
+            for (uint32_t j = 0; j < nnot; ++j) {
+                const uint32_t t = n + nfilter + j;
+                if (ltf[t] == 0) continue; /* nothing to exclude */
+                put_term(slot++, t, false);
+                ++kept;
+            }
+            dq.nnot = kept;
         }
     } else {
         /* OR of leaves: Huffman-shaped tree of binary OrPostLists, built from the leaves in query order
@@ -1155,7 +1263,7 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
     }
     /* algorithmic bytes, SURVEY.md §8(d): compressed columns + 16 B per block header of every query
      * term (full lists, no credit for skipping) + 16 B per result; 4 B per candidate added at wait() */
-    for (uint32_t j = 0; j < n; ++j)
+    for (uint32_t j = 0; j < nall; ++j)
         if (ids[j] != 0xffffffffu) pq.alg_bytes += ix->terms[ids[j]].bytes;
     pq.alg_bytes += 16ull * pq.topk;
 
@@ -1176,8 +1284,8 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
     (void)blocks_per_item;
     if (dq.route == 0) {
         /* every list but the driver has a membership bitmap → lean bitmap kernel */
-        bool all_bm = n >= 2 && s->and_version == 1;
-        for (uint32_t i = 1; i < n; ++i) all_bm = all_bm && dq.terms[i].bm_off != XGM_NO_BITMAP;
+        bool all_bm = dq.nterms >= 2 && s->and_version == 1;
+        for (uint32_t i = 1; i < dq.nterms + dq.nnot; ++i) all_bm = all_bm && dq.terms[i].bm_off != XGM_NO_BITMAP;
         std::vector<XgmWorkItem>& dst = all_bm ? items_bm : items;
         XgmWorkItem wi;
         wi.query = qi; wi.b0 = dq.terms[0].nblocks; wi.b1 = 0; wi.pad = 0;

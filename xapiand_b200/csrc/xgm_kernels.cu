@@ -484,10 +484,10 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 3) xgm_and_kernel(XgmKernelP
         const XgmWorkItem wi = p.items[item];
         if (p.pass != 0 && p.qstate[wi.query].rerun == 0) continue;
         const XgmDevQuery* q = &p.queries[wi.query];
-        const uint32_t nterms = q->nterms;
-        /* lane j keeps list j's skip-table cursor */
+        const uint32_t nterms = q->nterms, nnot = q->nnot, nweighted = q->nweighted;
+        /* lane j keeps list j's skip-table cursor (required lists, then the excluded ones of an OP_AND_NOT) */
         uint32_t my_begin = 0, my_nblk = 0, my_cur = 0;
-        if (lane < nterms) {
+        if (lane < nterms + nnot) {
             my_begin = q->terms[lane].blk_begin;
             my_nblk = q->terms[lane].nblocks;
         }
@@ -498,16 +498,18 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 3) xgm_and_kernel(XgmKernelP
          * candidate; candidates confirmed by the second list are queued and finished 32 at a time (one
          * per lane) so that the rank / wdf / BM25 work of the few survivors runs on full warps. */
         bool fast = nterms >= 2;
-        for (uint32_t j = 1; j < nterms; ++j) fast = fast && (q->terms[j].bm_off != XGM_NO_BITMAP);
+        for (uint32_t j = 1; j < nterms + nnot; ++j) fast = fast && (q->terms[j].bm_off != XGM_NO_BITMAP);
         uint32_t qn = 0;
         auto flush = [&](uint32_t from, uint32_t count) {
             uint32_t alive = lane < count ? 1u : 0u;
             const uint32_t d = alive ? ws.qdid[from + lane] : 0u;
             const uint32_t src = alive ? ws.qsrc[from + lane] : 0u;
-            for (uint32_t j = 2; j < nterms && __any_sync(FULL, alive); ++j) {
+            for (uint32_t j = 2; j < nterms + nnot && __any_sync(FULL, alive); ++j) {
                 if (alive) {
                     const uint32_t w = __ldg(p.bitmaps + q->terms[j].bm_off + (d >> 5));
-                    if (!(w >> (d & 31) & 1u)) alive = 0u;
+                    /* required lists must hold the docid; the right side of an OP_AND_NOT must not
+                     * (AndNotPostList::next, matcher/andnotpostlist.cc:97-130) */
+                    if (((w >> (d & 31)) & 1u) == (j < nterms ? 0u : 1u)) alive = 0u;
                 }
             }
             if (alive && q->filter && !doc_passes_filter(p, q, d)) alive = 0u;
@@ -525,7 +527,7 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 3) xgm_and_kernel(XgmKernelP
                 }
             }
             const uint32_t cc[4] = {d, 0u, 0u, 0u};
-            const uint32_t aux[4] = {nterms, nterms, nterms, nterms};
+            const uint32_t aux[4] = {nweighted, nweighted, nweighted, nweighted};
             emit_matches(p, q, wi.query, lane, alive, acc, cc, aux);
         };
 
@@ -666,13 +668,31 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 3) xgm_and_kernel(XgmKernelP
                 }
             }
 
+            /* right side of an OP_AND_NOT: a candidate found in any of these lists is dropped */
+            for (uint32_t j = nterms; j < nterms + nnot; ++j) {
+                if (!__any_sync(FULL, alive != 0)) break;
+                const uint64_t bm_off = q->terms[j].bm_off;
+                if (bm_off != XGM_NO_BITMAP) {
+                    const uint32_t* __restrict__ bm = p.bitmaps + bm_off;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if ((alive >> k & 1u) && ((__ldg(bm + (c[k] >> 5)) >> (c[k] & 31)) & 1u)) alive &= ~(1u << k);
+                } else {
+                    const uint32_t lbegin = __shfl_sync(FULL, my_begin, j);
+                    const uint32_t lnblk = __shfl_sync(FULL, my_nblk, j);
+                    uint32_t cur = __shfl_sync(FULL, my_cur, j);
+                    cur = probe_list(p, hdr + lbegin, lnblk, cur, ws, phase, lane, c, alive,
+                                     [&](int k, uint32_t, const XgmBlockHdr&) { alive &= ~(1u << k); }, [&](int) {});
+                    if (lane == j) my_cur = cur;
+                }
+            }
             /* value-slot filter (OP_FILTER with a range source), applied to the survivors */
             if (q->filter) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if ((alive >> k & 1u) && !doc_passes_filter(p, q, c[k])) alive &= ~(1u << k);
             }
-            const uint32_t aux[4] = {nterms, nterms, nterms, nterms};
+            const uint32_t aux[4] = {nweighted, nweighted, nweighted, nweighted};
             emit_matches(p, q, wi.query, lane, alive, acc, c, aux);
             dh = nh;
             buf ^= 1u;
@@ -727,7 +747,7 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 4) xgm_and_bm_kernel(XgmKernelP
         const XgmWorkItem wi = p.items_bm[item];
         if (p.pass != 0 && p.qstate[wi.query].rerun == 0) continue;
         const XgmDevQuery* q = &p.queries[wi.query];
-        const uint32_t nterms = q->nterms;
+        const uint32_t nterms = q->nterms, nall = nterms + q->nnot;
         const uint32_t drv_begin = q->terms[0].blk_begin;
         const uint32_t* __restrict__ bm1 = p.bitmaps + q->terms[1].bm_off;
         uint32_t qn = 0;
@@ -736,10 +756,11 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 4) xgm_and_bm_kernel(XgmKernelP
             uint32_t alive = lane < count ? 1u : 0u;
             const uint32_t d = alive ? ws.qdid[from + lane] : 0u;
             const uint32_t src = alive ? ws.qsrc[from + lane] : 0u;
-            for (uint32_t j = 2; j < nterms && __any_sync(FULL, alive); ++j) {
+            for (uint32_t j = 2; j < nall && __any_sync(FULL, alive); ++j) {
                 if (alive) {
                     const uint32_t w = __ldg(p.bitmaps + q->terms[j].bm_off + (d >> 5));
-                    if (!(w >> (d & 31) & 1u)) alive = 0u;
+                    /* required lists must hold the docid, the right side of an OP_AND_NOT must not */
+                    if (((w >> (d & 31)) & 1u) == (j < nterms ? 0u : 1u)) alive = 0u;
                 }
             }
             if (alive && q->filter && !doc_passes_filter(p, q, d)) alive = 0u;
@@ -758,7 +779,8 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 4) xgm_and_bm_kernel(XgmKernelP
                 }
             }
             const uint32_t cc[4] = {d, 0u, 0u, 0u};
-            const uint32_t aux[4] = {nterms, nterms, nterms, nterms};
+            const uint32_t nw = q->nweighted;
+            const uint32_t aux[4] = {nw, nw, nw, nw};
             emit_matches(p, q, wi.query, lane, alive, acc, cc, aux);
         };
         auto issue = [&](uint32_t b, uint32_t blk) { /* stage driver block blk into buffer b */
@@ -1567,7 +1589,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) xgm_topk_kernel(XgmKernelParams 
                 if (b < st.bstar) { b = st.bstar; cum = 0; for (uint32_t i = b; i < XGM_NBINS; ++i) cum += hist[i]; }
                 XgmDevResult r;
                 r.n = 0; r.exact = st.total; r.known = 0; r.max_w = __longlong_as_double((long long)st.maxw);
-                r.max_subqs = q->nterms; r.pad = 0;
+                r.max_subqs = q->nweighted; r.pad = 0;
                 const uint32_t off = atomicAdd(p.work_counter + 5, cum);
                 if (cum >= topk && (uint64_t)off + cum <= (uint64_t)p.pool_total) {
                     p.qstate[qi].bstar = b;
@@ -1827,7 +1849,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) xgm_topk_kernel(XgmKernelParams 
         if (st.skipped) r.flags |= 8u; /* whole work items were pruned: the match count is a lower bound */
         if (p.pass != 0) r.flags |= 16u; /* produced by the second pass */
         r.max_w = __longlong_as_double((long long)st.maxw);
-        r.max_subqs = q->nterms;
+        r.max_subqs = q->nweighted;
         r.pad = 0;
         p.out_info[qi] = r;
     }

@@ -69,7 +69,8 @@ class CQuery(C.Structure):
                 ("k1", C.c_double), ("k3", C.c_double), ("b", C.c_double), ("min_normlen", C.c_double),
                 ("filter", C.c_uint32), ("filter_slot", C.c_uint32), ("range_lo", C.c_uint64),
                 ("range_hi", C.c_uint64), ("sort_by", C.c_uint32), ("sort_slot", C.c_uint32),
-                ("sort_reverse", C.c_uint32), ("sort_use_max", C.c_uint32)]
+                ("sort_reverse", C.c_uint32), ("sort_use_max", C.c_uint32),
+                ("nfilter", C.c_uint32), ("nnot", C.c_uint32), ("nmaybe", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class MSetInfo(C.Structure):
@@ -183,6 +184,10 @@ class Query:
     sort_slot: int = 0
     sort_reverse: bool = False
     sort_use_max: bool = False
+    # OP_FILTER(q, AND of boolean terms) / OP_AND_NOT(q, OR of terms) / OP_AND_MAYBE(q, OR of terms): AND base only
+    filter_terms: Sequence[Union[str, bytes, int]] = ()
+    not_terms: Sequence[Union[str, bytes, int]] = ()
+    maybe_terms: Sequence[Union[str, bytes, int]] = ()
 
 
 class QueryBatch:
@@ -195,12 +200,14 @@ class QueryBatch:
         for i, q in enumerate(queries):
             cq = self.arr[i]
             cq.op, cq.nterms = q.op, len(q.terms)
-            if all(isinstance(t, (int, np.integer)) for t in q.terms):
-                ids = (C.c_uint32 * len(q.terms))(*[int(t) for t in q.terms])
+            cq.nfilter, cq.nnot, cq.nmaybe = len(q.filter_terms), len(q.not_terms), len(q.maybe_terms)
+            allterms = list(q.terms) + list(q.filter_terms) + list(q.not_terms) + list(q.maybe_terms)
+            if all(isinstance(t, (int, np.integer)) for t in allterms):
+                ids = (C.c_uint32 * len(allterms))(*[int(t) for t in allterms])
                 cq.term_ids = ids
                 self._keep.append(ids)
             else:
-                bs = [t.encode() if isinstance(t, str) else bytes(t) for t in q.terms]
+                bs = [t.encode() if isinstance(t, str) else bytes(t) for t in allterms]
                 names = (C.c_char_p * len(bs))(*bs)
                 lens = (C.c_uint32 * len(bs))(*[len(b) for b in bs])
                 cq.terms, cq.term_lens = names, lens
@@ -211,7 +218,8 @@ class QueryBatch:
                 self._keep.append(w)
             cq.first, cq.maxitems, cq.check_at_least = q.first, q.maxitems, q.check_at_least
             if q.stats is not None:
-                tf = (C.c_uint32 * len(q.terms))(*q.stats[2])
+                gtf = list(q.stats[2]) + [0] * (len(allterms) - len(q.stats[2]))
+                tf = (C.c_uint32 * len(gtf))(*gtf)
                 st = CStats(q.stats[0], q.stats[1], tf)
                 cq.stats = C.pointer(st)
                 self._keep += [tf, st]
