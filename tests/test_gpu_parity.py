@@ -148,3 +148,28 @@ def test_or_medium_index(medium):
     ix, orc, nd, V = medium
     rng = random.Random(9)
     run_and_compare(ix, orc, gen_queries(rng, 40, 1000, nd, ops=("OR",), ks=(5,), maxitems=(1000,)), max_topk=1000)
+
+
+def test_filter_andnot_andmaybe_against_oracle(small):
+    """§8(f)-1 shapes on a 30k-document index (terms with and without membership bitmaps): every MSet field
+    incl. exact match count and percentage scale against the oracle."""
+    ix, orc, nd, V = small
+    rng = random.Random(91)
+    xq, oq = [], []
+    for i in range(300):
+        nb = rng.choice([1, 2, 2, 3])
+        pool = rng.sample(range(400 if i % 3 else 4000), nb + 9)  # every third query uses rare terms too
+        nf, nx, nm = rng.choice([0, 0, 1, 2]), rng.choice([0, 0, 1, 2, 3]), rng.choice([0, 0, 1, 2, 3])
+        if nf + nx + nm == 0:
+            nm = 2
+        base, f, x, m = pool[:nb], pool[nb:nb + nf], pool[nb + 3:nb + 3 + nx], pool[nb + 6:nb + 6 + nm]
+        kw = dict(first=rng.choice([0, 0, 2]), maxitems=rng.choice([10, 100]), check_at_least=rng.choice([0, 0, nd]))
+        xq.append(xgm.Query(xgm.OP_AND, base, filter_terms=f, not_terms=x, maybe_terms=m, **kw))
+        oq.append(O.Query(op=O.OP_AND, terms=base, filter_terms=f, not_terms=x, maybe_terms=m, **kw))
+    res = xgm.Searcher(ix, max_batch=len(xq), max_topk=128).search(xq)
+    for i, (m, q) in enumerate(zip(res, oq)):
+        ref = orc.match(q)
+        assert_mset_equal(m, ref, ctx=f"ops[{i}] {q.terms} F{q.filter_terms} N{q.not_terms} M{q.maybe_terms}",
+                          check_counts=not (m.flags & 1))
+        assert m.exact_matches == ref.exact and m.matches_upper_bound == ref.ub
+

@@ -60,8 +60,9 @@ struct XgmDevQuery {
     int8_t prog[2 * XGM_DEV_MAX_TERMS]; /* OR: postfix program over leaves (>=0) and '+' (-1) */
     uint32_t route;                     /* 0 = AND kernel, 1 = OR kernel */
     uint32_t nnot;                      /* AND: terms[nterms .. nterms+nnot) must be absent (OP_AND_NOT right side) */
-    uint32_t nweighted;                 /* leaves that carry a weight (OP_FILTER's boolean terms do not) */
-    uint32_t pad;
+    uint32_t nweighted;                 /* required leaves that carry a weight (OP_FILTER's boolean terms do not) */
+    uint32_t nmaybe;                    /* AND: terms[nterms+nnot ..) are the optional leaves of an OP_AND_MAYBE; prog[] is
+                                           the OrPostList tree over them */
     double bucket_scale;                /* XGM_NBINS / max_possible (or / (max sort key + 1)) */
     XgmDevTerm terms[XGM_DEV_MAX_TERMS]; /* AND: ascending termfreq (MultiAndPostList order) */
 };

@@ -691,6 +691,7 @@ struct PlannedQuery {
     uint32_t sort_by = 0;
     uint32_t filter = 0;
     bool count_only = false; /* first >= every possible match count: the MSet is empty, only counts matter */
+    bool aux_subqs = false;  /* the number of matching weighted leaves varies per document (OR, AND_MAYBE) */
 };
 
 struct xgm_searcher {
@@ -1039,11 +1040,11 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
     memset(&dq, 0, sizeof(dq));
     if (q.nterms == 0 || q.nterms > XGM_MAX_TERMS) { pq.status = XGM_E_UNIMPLEMENTED; return XGM_OK; }
     if (q.op != XGM_OP_AND && q.op != XGM_OP_OR) { pq.status = XGM_E_UNIMPLEMENTED; return XGM_OK; }
-    const uint32_t nfilter = q.nfilter, nnot = q.nnot, ngroups = q.nfilter + q.nnot + q.nmaybe;
+    const uint32_t nfilter = q.nfilter, nnot = q.nnot, nmaybe = q.nmaybe, ngroups = q.nfilter + q.nnot + q.nmaybe;
     if (ngroups) {
-        /* OP_FILTER with boolean terms / OP_AND_NOT around an AND (or single-term) base; OP_AND_MAYBE, an OR
+        /* OP_FILTER with boolean terms / OP_AND_NOT / OP_AND_MAYBE around an AND (or single-term) base; an OR
          * base, a value-range filter on top, or the chunked kernel variant are left to the reference */
-        if (q.nmaybe || (q.op != XGM_OP_AND && q.nterms != 1) || q.filter != XGM_FILTER_NONE || s->and_version != 1 ||
+        if ((q.op != XGM_OP_AND && q.nterms != 1) || q.filter != XGM_FILTER_NONE || s->and_version != 1 ||
             (uint64_t)q.nterms + ngroups > XGM_MAX_TERMS) {
             pq.status = XGM_E_UNIMPLEMENTED;
             return XGM_OK;
@@ -1207,6 +1208,51 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
                 ++kept;
             }
             dq.nnot = kept;
+            if (nmaybe) {
+                /* AndMaybePostList: termfreqs are the left's; recalc_maxweight = pl_max + r_max where r is the
+                 * OrContext tree over the optional leaves (matcher/andmaybepostlist.cc:69-75) */
+                const uint32_t mb = n + nfilter + nnot;
+                double mtw[XGM_MAX_TERMS], mmax[XGM_MAX_TERMS];
+                for (uint32_t j = 0; j < nmaybe; ++j) {
+                    const uint32_t gtf = q.stats ? q.stats->termfreq[mb + j] : ltf[mb + j];
+                    mtw[j] = bm25_termweight(N, gtf, 1, 1.0, k1, k3);
+                    const uint32_t wub = ids[mb + j] == 0xffffffffu ? 0 : ix->terms[ids[mb + j]].wdf_ub;
+                    mmax[j] = bm25_maxpart(mtw[j], len_factor, k1, b, mnl, wub, ix->doclen_lb);
+                }
+                double rmax = mmax[0];
+                dq.prog_len = 0;
+                if (nmaybe == 1) {
+                    dq.prog[dq.prog_len++] = 0;
+                } else {
+                    OrTree tr;
+                    build_or_tree(ltf + mb, nmaybe, tr);
+                    int stack[4 * XGM_MAX_TERMS], sp = 0, outrev[2 * XGM_MAX_TERMS], nr = 0;
+                    stack[sp++] = tr.root;
+                    while (sp) {
+                        int x = stack[--sp];
+                        outrev[nr++] = x;
+                        if (x >= (int)nmaybe) { stack[sp++] = tr.lch[x]; stack[sp++] = tr.rch[x]; }
+                    }
+                    double sm[2 * XGM_MAX_TERMS];
+                    int pp = 0;
+                    for (int i = nr - 1; i >= 0; --i) {
+                        int x = outrev[i];
+                        if (x < (int)nmaybe) { dq.prog[dq.prog_len++] = (int8_t)x; sm[pp++] = mmax[x]; }
+                        else { dq.prog[dq.prog_len++] = -1; --pp; sm[pp - 1] = sm[pp - 1] + sm[pp]; }
+                    }
+                    rmax = sm[0];
+                }
+                pq.max_possible = pq.max_possible + rmax;
+                for (uint32_t j = 0; j < nmaybe; ++j) {
+                    put_term(slot, mb + j, false);
+                    dq.terms[slot].termweight = mtw[j];
+                    dq.terms[slot].maxpart = mmax[j];
+                    ++slot;
+                }
+                dq.nmaybe = nmaybe;
+                pq.aux_subqs = true;
+                pq.nterms = n + nmaybe; /* total weighted leaves, for the percentage scale */
+            }
         }
     } else {
         /* OR of leaves: Huffman-shaped tree of binary OrPostLists, built from the leaves in query order
@@ -1415,7 +1461,7 @@ static xgm_status submit_impl(xgm_searcher* s, const xgm_query* queries, uint32_
     }
     const auto t_planned = std::chrono::steady_clock::now();
     for (uint32_t i = 0; i < nq; ++i) {
-        if (s->plan[i].sort_by || s->h_queries[i].route == 1) s->any_sort = true; /* keys/aux needed on the host */
+        if (s->plan[i].sort_by || s->h_queries[i].route == 1 || s->plan[i].aux_subqs) s->any_sort = true; /* keys/aux needed on the host */
         alg += s->plan[i].alg_bytes;
         total_drv_blocks += s->h_queries[i].terms[0].nblocks;
     }
@@ -1687,7 +1733,7 @@ extern "C" xgm_status xgm_search_wait(xgm_searcher* s, uint32_t* docids, double*
         const size_t off = (size_t)i * s->max_topk;
         if (pq.status == XGM_OK && pq.on_device && (s->h_info[i].flags & 16u)) s->stats.second_pass_queries++;
         finish_info(pq, &s->h_info[i], s->h_out_w + off, s->any_sort ? s->h_out_k + off : nullptr,
-                    s->h_queries[i].route == 1, &info[i]);
+                    s->h_queries[i].route == 1 || pq.aux_subqs, &info[i]);
         if (pq.status == XGM_OK && pq.on_device) s->stats.algorithmic_bytes += 4ull * s->h_info[i].exact;
         uint32_t n = info[i].n;
         if (n > stride) return fail(XGM_E_INVALID, "stride %u too small for %u results", stride, n);

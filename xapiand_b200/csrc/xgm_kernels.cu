@@ -463,6 +463,71 @@ __device__ __forceinline__ uint32_t bitmap_rank(const XgmKernelParams& p, const 
     return r;
 }
 
+/* One lane looks docid d up in a term's posting list — for the few documents that reach scoring
+ * (optional leaves of an OP_AND_MAYBE): bitmap + rank directory when the term has them, otherwise a binary
+ * search over the skip table and a sequential decode inside the one block. */
+__device__ __noinline__ bool lookup_posting(const XgmKernelParams& p, const XgmDevTerm& t, uint32_t d, uint32_t* wdf) {
+    const XgmBlockHdr* __restrict__ h = p.hdr + t.blk_begin;
+    if (t.bm_off != XGM_NO_BITMAP) {
+        const uint32_t w = __ldg(p.bitmaps + t.bm_off + (d >> 5));
+        if (!((w >> (d & 31)) & 1u)) return false;
+        const uint32_t r = bitmap_rank(p, t, d);
+        const XgmBlockHdr bh = h[r >> 7];
+        *wdf = unpack_gl(p.tfs, bh.tf_off, r & 127u, XGM_HDR_TF_BITS(bh.meta));
+        return true;
+    }
+    if (t.nblocks == 0) return false;
+    uint32_t lo = 0, hi = t.nblocks; /* last block whose first docid is <= d */
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (h[mid].first <= d) lo = mid; else hi = mid;
+    }
+    const XgmBlockHdr bh = h[lo];
+    if (bh.first > d) return false;
+    const uint32_t cnt = XGM_HDR_COUNT(bh.meta), bits = XGM_HDR_DOC_BITS(bh.meta);
+    uint32_t docid = bh.first, pos = 0;
+    while (docid < d && pos + 1 < cnt) {
+        ++pos;
+        docid += unpack_gl(p.docs, bh.doc_off, pos, bits) + 1u;
+    }
+    if (docid != d) return false;
+    *wdf = unpack_gl(p.tfs, bh.tf_off, pos, XGM_HDR_TF_BITS(bh.meta));
+    return true;
+}
+
+/* AndMaybePostList::get_weight (matcher/andmaybepostlist.cc:59-67): the right side's weight, i.e. the
+ * OrPostList tree (l, r or l + r per node, matcher/orpostlist.cc:93-103) over the optional leaves that hold
+ * docid d, evaluated as the postfix program built on the host.  *present = how many leaves matched. */
+__device__ __noinline__ double maybe_weight(const XgmKernelParams& p, const XgmDevQuery* q, uint32_t d, uint32_t dlen,
+                                            uint32_t* present) {
+    double stk[XGM_DEV_MAX_TERMS];
+    uint32_t has = 0, cnt = 0;
+    int sp = 0;
+    const uint32_t base = q->nterms + q->nnot;
+    for (uint32_t i = 0; i < q->prog_len; ++i) {
+        const int op = q->prog[i];
+        if (op >= 0) {
+            const XgmDevTerm& t = q->terms[base + (uint32_t)op];
+            uint32_t wdf = 0;
+            if (lookup_posting(p, t, d, &wdf)) {
+                stk[sp] = bm25_sumpart(t.termweight, q, wdf, dlen);
+                has |= 1u << sp;
+                ++cnt;
+            } else {
+                has &= ~(1u << sp);
+            }
+            ++sp;
+        } else {
+            --sp;
+            const bool hl = has >> (sp - 1) & 1u, hr = has >> sp & 1u;
+            if (hl && hr) stk[sp - 1] = __dadd_rn(stk[sp - 1], stk[sp]);
+            else if (hr) { stk[sp - 1] = stk[sp]; has |= 1u << (sp - 1); }
+        }
+    }
+    *present = cnt;
+    return cnt ? stk[0] : 0.0;
+}
+
 /* ------------------------------------------------------------------ sparse AND kernel */
 
 __global__ void __launch_bounds__(MATCH_WARPS * 32, 3) xgm_and_kernel(XgmKernelParams p) {
@@ -514,6 +579,7 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 3) xgm_and_kernel(XgmKernelP
             }
             if (alive && q->filter && !doc_passes_filter(p, q, d)) alive = 0u;
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            uint32_t opt = 0;
             if (alive) {
                 const uint32_t dlen = __ldg(&p.doclen[d]);
                 const XgmBlockHdr h0 = hdr[drv_begin + wi.b0 + (src >> 7)];
@@ -525,9 +591,13 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 3) xgm_and_kernel(XgmKernelP
                     /* MultiAndPostList::get_weight: result += plist[i]->get_weight(), in plist order */
                     acc[0] = __dadd_rn(acc[0], bm25_sumpart(q->terms[j].termweight, q, tfj, dlen));
                 }
+                if (q->nmaybe) { /* OP_AND_MAYBE: res = l; if (r matches) res += r */
+                    const double rw = maybe_weight(p, q, d, dlen, &opt);
+                    if (opt) acc[0] = __dadd_rn(acc[0], rw);
+                }
             }
             const uint32_t cc[4] = {d, 0u, 0u, 0u};
-            const uint32_t aux[4] = {nweighted, nweighted, nweighted, nweighted};
+            const uint32_t aux[4] = {nweighted + opt, nweighted, nweighted, nweighted};
             emit_matches(p, q, wi.query, lane, alive, acc, cc, aux);
         };
 
@@ -692,7 +762,18 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 3) xgm_and_kernel(XgmKernelP
                 for (int k = 0; k < 4; ++k)
                     if ((alive >> k & 1u) && !doc_passes_filter(p, q, c[k])) alive &= ~(1u << k);
             }
-            const uint32_t aux[4] = {nweighted, nweighted, nweighted, nweighted};
+            uint32_t aux[4] = {nweighted, nweighted, nweighted, nweighted};
+            if (q->nmaybe) { /* OP_AND_MAYBE: res = l; if (r matches) res += r */
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (alive >> k & 1u) {
+                        uint32_t opt = 0;
+                        const double rw = maybe_weight(p, q, c[k], dl[k], &opt);
+                        if (opt) acc[k] = __dadd_rn(acc[k], rw);
+                        aux[k] += opt;
+                    }
+                }
+            }
             emit_matches(p, q, wi.query, lane, alive, acc, c, aux);
             dh = nh;
             buf ^= 1u;
@@ -765,6 +846,7 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 4) xgm_and_bm_kernel(XgmKernelP
             }
             if (alive && q->filter && !doc_passes_filter(p, q, d)) alive = 0u;
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            uint32_t opt = 0;
             if (alive) {
                 const uint32_t dlen = __ldg(&p.doclen[d]);
                 const XgmBlockHdr h0 = hdr[drv_begin + wi.b0 + (src >> 7)];
@@ -777,10 +859,14 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 4) xgm_and_bm_kernel(XgmKernelP
                     /* MultiAndPostList::get_weight: result += plist[i]->get_weight(), in plist order */
                     acc[0] = __dadd_rn(acc[0], bm25_sumpart(q->terms[j].termweight, q, tfj, dlen));
                 }
+                if (q->nmaybe) { /* OP_AND_MAYBE: res = l; if (r matches) res += r */
+                    const double rw = maybe_weight(p, q, d, dlen, &opt);
+                    if (opt) acc[0] = __dadd_rn(acc[0], rw);
+                }
             }
             const uint32_t cc[4] = {d, 0u, 0u, 0u};
             const uint32_t nw = q->nweighted;
-            const uint32_t aux[4] = {nw, nw, nw, nw};
+            const uint32_t aux[4] = {nw + opt, nw, nw, nw};
             emit_matches(p, q, wi.query, lane, alive, acc, cc, aux);
         };
         auto issue = [&](uint32_t b, uint32_t blk) { /* stage driver block blk into buffer b */
