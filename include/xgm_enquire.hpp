@@ -77,13 +77,17 @@ class Database {
 /* Xapian::Query (src/xapian/query.h): leaves, OP_AND / OP_OR of leaves, OP_FILTER with a value range. */
 class Query {
   public:
-    enum op { OP_AND = 0, OP_OR = 1, OP_FILTER = 5, OP_VALUE_RANGE = 8, LEAF_TERM = 100 };
+    /* values of Xapian::Query::op (src/xapian/query.h:76-243) */
+    enum op { OP_AND = 0, OP_OR = 1, OP_AND_NOT = 2, OP_AND_MAYBE = 4, OP_FILTER = 5, OP_VALUE_RANGE = 8, LEAF_TERM = 100 };
     op type = LEAF_TERM;
     std::vector<std::string> terms;
     std::vector<termcount> wqf;
     bool has_range = false, multi_range = false;
     valueno range_slot = 0;
     uint64_t range_lo = 0, range_hi = 0;
+    /* term groups around an AND (or single-term) base: OP_FILTER(q, boolean terms), OP_AND_NOT(q, terms),
+     * OP_AND_MAYBE(q, terms) — nesting order FILTER, then AND_NOT, then AND_MAYBE (xgm_query, include/xgm.h) */
+    std::vector<std::string> filter_terms, not_terms, maybe_terms;
 
     Query() {}
     explicit Query(const std::string& term, termcount wqf_ = 1) : terms{term}, wqf{wqf_} {}
@@ -92,14 +96,30 @@ class Query {
         for (It i = begin; i != end; ++i) { terms.push_back(*i); wqf.push_back(1); }
     }
     Query(op op_, const Query& a, const Query& b) : type(op_) {
-        if (op_ == OP_FILTER) {  /* OP_FILTER(q, value-range) — QueryFilter::postlist, queryinternal.cc:2270-2298 */
-            if (!b.has_range || !b.terms.empty()) throw UnimplementedError("OP_FILTER needs a value range on the right");
+        if (op_ == OP_FILTER && b.has_range) {  /* OP_FILTER(q, value-range) — QueryFilter::postlist, queryinternal.cc:2270-2298 */
+            if (!b.terms.empty() || a.has_groups()) throw UnimplementedError("OP_FILTER(q, range) over term groups is not covered");
             *this = a;
             has_range = true; multi_range = b.multi_range; range_slot = b.range_slot; range_lo = b.range_lo; range_hi = b.range_hi;
             return;
         }
+        if (op_ == OP_FILTER || op_ == OP_AND_NOT || op_ == OP_AND_MAYBE) {
+            /* left: an AND of terms (or one term), possibly already carrying inner groups; right: terms only —
+             * an AND of boolean terms for OP_FILTER, an OR of terms for the other two */
+            const op rkind = op_ == OP_FILTER ? OP_AND : OP_OR;
+            const bool left_ok = (a.type == LEAF_TERM || a.type == OP_AND || a.terms.size() == 1) && !a.has_range && !a.terms.empty();
+            const bool right_ok = !b.terms.empty() && !b.has_range && !b.has_groups() && (b.terms.size() == 1 || b.type == rkind);
+            const bool order_ok = op_ == OP_FILTER ? (a.not_terms.empty() && a.maybe_terms.empty())
+                                  : op_ == OP_AND_NOT ? a.maybe_terms.empty() : true;
+            if (!left_ok || !right_ok || !order_ok) throw UnimplementedError("operator nesting not covered by the device matcher");
+            *this = a;
+            type = a.terms.size() == 1 ? LEAF_TERM : OP_AND;
+            std::vector<std::string>& dst = op_ == OP_FILTER ? filter_terms : op_ == OP_AND_NOT ? not_terms : maybe_terms;
+            dst.insert(dst.end(), b.terms.begin(), b.terms.end());
+            return;
+        }
         if (op_ != OP_AND && op_ != OP_OR) throw UnimplementedError("operator not covered by the device matcher");
-        if ((a.type != LEAF_TERM && a.type != op_) || (b.type != LEAF_TERM && b.type != op_) || a.has_range || b.has_range)
+        if ((a.type != LEAF_TERM && a.type != op_) || (b.type != LEAF_TERM && b.type != op_) || a.has_range || b.has_range ||
+            a.has_groups() || b.has_groups())
             throw UnimplementedError("nested operators of different kinds are not covered");
         terms = a.terms; terms.insert(terms.end(), b.terms.begin(), b.terms.end());
         wqf = a.wqf; wqf.insert(wqf.end(), b.wqf.begin(), b.wqf.end());
@@ -109,6 +129,7 @@ class Query {
         Query q; q.type = OP_VALUE_RANGE; q.has_range = true; q.multi_range = multi; q.range_slot = slot; q.range_lo = lo; q.range_hi = hi;
         return q;
     }
+    bool has_groups() const { return !filter_terms.empty() || !not_terms.empty() || !maybe_terms.empty(); }
     bool empty() const { return terms.empty(); }
 };
 
@@ -235,13 +256,22 @@ class Enquire {
         }
         std::vector<const char*> tp;
         std::vector<uint32_t> tl;
+        std::vector<termcount> wq(query.wqf);
         for (auto& t : query.terms) { tp.push_back(t.data()); tl.push_back((uint32_t)t.size()); }
+        for (const std::vector<std::string>* g : {&query.filter_terms, &query.not_terms, &query.maybe_terms})
+            for (auto& t : *g) { tp.push_back(t.data()); tl.push_back((uint32_t)t.size()); wq.push_back(1); }
         xgm_query q{};
         q.op = query.type == Query::OP_OR ? XGM_OP_OR : XGM_OP_AND;
         q.nterms = (uint32_t)query.terms.size();
-        q.terms = tp.data(); q.term_lens = tl.data(); q.wqf = query.wqf.data();
+        q.nfilter = (uint32_t)query.filter_terms.size(); q.nnot = (uint32_t)query.not_terms.size();
+        q.nmaybe = (uint32_t)query.maybe_terms.size();
+        q.terms = tp.data(); q.term_lens = tl.data(); q.wqf = wq.data();
         q.first = first; q.maxitems = maxitems; q.check_at_least = checkatleast;
-        if (have_stats) { stats.termfreq = stats_tf.data(); q.stats = &stats; }
+        if (have_stats) {
+            /* one termfreq per term in the order base, filter, not, maybe (the weighted groups use theirs) */
+            if (stats_tf.size() < tp.size()) throw InvalidArgumentError("global statistics must cover every query term");
+            stats.termfreq = stats_tf.data(); q.stats = &stats;
+        }
         if (query.has_range) {
             q.filter = query.multi_range ? XGM_FILTER_MULTI_RANGE : XGM_FILTER_VALUE_RANGE;
             q.filter_slot = query.range_slot; q.range_lo = query.range_lo; q.range_hi = query.range_hi;

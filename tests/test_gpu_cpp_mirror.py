@@ -20,12 +20,18 @@ def test_cpp_enquire_mirror_matches_oracle(tmp_path):
                            "-Wl,-rpath," + os.path.join(ROOT, "xapiand_b200")])
     nd, V = 20000, 3000
     orc = O.Index.synthetic(nd, V)
-    cases = [("AND", 0, 10, 0, [30, 170, 400]), ("OR", 2, 25, 0, [5, 120, 700]), ("AND", 0, 5, nd, [250])]
-    for op, first, maxitems, cal, terms in cases:
+    cases = [("AND", 0, 10, 0, [30, 170, 400], {}), ("OR", 2, 25, 0, [5, 120, 700], {}), ("AND", 0, 5, nd, [250], {}),
+             # OP_AND_MAYBE(OP_AND_NOT(OP_FILTER(AND, boolean term), OR of terms), OR of terms)
+             ("AND", 0, 20, nd, [12, 60], dict(filter_terms=[3], not_terms=[40, 9], maybe_terms=[75, 110]))]
+    for op, first, maxitems, cal, terms, groups in cases:
+        env = dict(os.environ)
+        for key, var in (("filter_terms", "XGM_MIRROR_FILTER"), ("not_terms", "XGM_MIRROR_NOT"), ("maybe_terms", "XGM_MIRROR_MAYBE")):
+            if groups.get(key):
+                env[var] = ",".join(f"T{t:06d}" for t in groups[key])
         out = subprocess.check_output([exe, str(nd), str(V), op, str(first), str(maxitems), str(cal)] +
-                                      [f"T{t:06d}" for t in terms], timeout=240).decode().splitlines()
+                                      [f"T{t:06d}" for t in terms], timeout=240, env=env).decode().splitlines()
         ref = orc.match(O.Query(op=O.OP_AND if op == "AND" else O.OP_OR, terms=terms, first=first, maxitems=maxitems,
-                                check_at_least=cal))
+                                check_at_least=cal, **groups))
         head = out[0].split()
         n = int(head[1])
         assert n == len(ref.docids)
