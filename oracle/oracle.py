@@ -57,7 +57,8 @@ class _Stats(C.Structure):
 
 class _Query(C.Structure):
     _fields_ = [("op", C.c_int), ("nterms", C.c_uint32), ("terms", C.POINTER(C.c_uint32)),
-                ("wqf", C.POINTER(C.c_uint32)), ("first", C.c_uint32), ("maxitems", C.c_uint32),
+                ("wqf", C.POINTER(C.c_uint32)), ("factors", C.POINTER(C.c_double)), ("first", C.c_uint32),
+                ("maxitems", C.c_uint32),
                 ("check_at_least", C.c_uint32), ("stats", C.POINTER(_Stats)),
                 ("k1", C.c_double), ("k3", C.c_double), ("b", C.c_double), ("min_normlen", C.c_double),
                 ("filter", C.c_int), ("range_lo", C.c_uint64), ("range_hi", C.c_uint64),
@@ -133,6 +134,7 @@ class Query:
     maxitems: int = 10
     check_at_least: int = 0
     wqf: Optional[Sequence[int]] = None
+    factors: Optional[Sequence[float]] = None    # OP_SCALE_WEIGHT factor per term (oracle only so far)
     filter: int = FILTER_NONE
     range_lo: int = 0
     range_hi: int = 0
@@ -256,6 +258,9 @@ class Index:
         if q.wqf is not None:
             wqf = (C.c_uint32 * len(q.wqf))(*q.wqf)
             cq.wqf = wqf
+        if q.factors is not None:
+            fac = (C.c_double * len(q.factors))(*q.factors)
+            cq.factors = fac
         cq.first, cq.maxitems, cq.check_at_least = q.first, q.maxitems, q.check_at_least
         cq.filter, cq.range_lo, cq.range_hi = q.filter, q.range_lo, q.range_hi
         cq.sort_by, cq.sort_slot, cq.sort_reverse = q.sort_by, q.sort_slot, int(q.sort_reverse)
@@ -304,6 +309,16 @@ def merge(parts: List[MSet], first: int, maxitems: int, sort_by: int = SORT_REL,
     out = _mset_from_c(m)
     L.orc_mset_free(C.byref(m))
     return out
+
+
+def convert_to_percent(weight: float, percent_scale_factor: float) -> int:
+    """MSet::Internal::convert_to_percent, api/mset.cc:333-365."""
+    if percent_scale_factor == 0.0:
+        return 100
+    if weight <= 0.0:
+        return 0
+    pct = int(weight * percent_scale_factor + 100.0 * 2.220446049250313e-16)
+    return 1 if pct <= 0 else min(pct, 100)
 
 
 def round_estimate(lb: int, ub: int, est: int) -> int:
@@ -414,6 +429,7 @@ class RefResult:
     docids: List[int] = field(default_factory=list)
     weights: List[float] = field(default_factory=list)
     sort_keys: List[str] = field(default_factory=list)
+    percents: List[int] = field(default_factory=list)
     lb: int = 0
     est: int = 0
     ub: int = 0
@@ -436,6 +452,8 @@ def parse_dump(path: str) -> List[RefResult]:
             else:
                 cur.docids.append(int(p[0]))
                 cur.weights.append(float(p[1]))
+                if p[-1].startswith("p"):
+                    cur.percents.append(int(p.pop()[1:]))
                 if len(p) > 2:
                     cur.sort_keys.append(p[2])
     return out

@@ -177,10 +177,19 @@ static std::vector<QSpec> load_queries(const std::string& path) {
 }
 
 static Xapian::Query make_query(const QSpec& q) {
+    /* "term^factor" → OP_SCALE_WEIGHT(term, factor) (Xapiand's _boost, QueryScaleWeight::postlist
+     * api/queryinternal.cc:1075-1080) */
+    auto leaf = [](const std::string& t) {
+        const size_t c = t.find('^');
+        if (c == std::string::npos) return Xapian::Query(t);
+        return Xapian::Query(Xapian::Query::OP_SCALE_WEIGHT, Xapian::Query(t.substr(0, c)), atof(t.c_str() + c + 1));
+    };
+    std::vector<Xapian::Query> leaves;
+    for (const auto& t : q.terms) leaves.push_back(leaf(t));
     Xapian::Query base;
-    if (q.op == "TERM") base = Xapian::Query(q.terms.at(0));
-    else if (q.op == "AND") base = Xapian::Query(Xapian::Query::OP_AND, q.terms.begin(), q.terms.end());
-    else if (q.op == "OR") base = Xapian::Query(Xapian::Query::OP_OR, q.terms.begin(), q.terms.end());
+    if (q.op == "TERM") base = leaves.at(0);
+    else if (q.op == "AND") base = Xapian::Query(Xapian::Query::OP_AND, leaves.begin(), leaves.end());
+    else if (q.op == "OR") base = Xapian::Query(Xapian::Query::OP_OR, leaves.begin(), leaves.end());
     else die("bad op " + q.op);
     if (q.has_range) {
         Xapian::Query r(Xapian::Query::OP_VALUE_RANGE, q.r_slot,
@@ -202,6 +211,7 @@ static Xapian::Query make_query(const QSpec& q) {
 struct QResult {
     std::vector<std::pair<uint32_t, double>> items;
     std::vector<std::string> sort_keys;
+    std::vector<int> percents;   /* MSetIterator::get_percent */
     uint32_t lb = 0, est = 0, ub = 0;
     double max_possible = 0, max_attained = 0;
     double seconds = 0;
@@ -214,9 +224,10 @@ static void setup_enquire(Xapian::Enquire& enq, const QSpec& q) {
 }
 
 static void collect(const Xapian::MSet& m, QResult& r, bool want_keys) {
-    r.items.clear(); r.sort_keys.clear();
+    r.items.clear(); r.sort_keys.clear(); r.percents.clear();
     for (auto it = m.begin(); it != m.end(); ++it) {
         r.items.emplace_back(*it, it.get_weight());
+        r.percents.push_back(it.get_percent());
         if (want_keys) r.sort_keys.push_back(it.get_sort_key());
     }
     r.lb = m.get_matches_lower_bound();
@@ -320,6 +331,7 @@ static int cmd_query(const Args& a) {
                     for (unsigned char c : r.sort_keys[k]) fprintf(f, "%02x", c);
                     if (r.sort_keys[k].empty()) fputc('-', f);
                 }
+                if (k < r.percents.size()) fprintf(f, " p%d", r.percents[k]);
                 fputc('\n', f);
             }
         }

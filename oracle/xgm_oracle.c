@@ -570,9 +570,12 @@ int orc_match(const orc_index* ix, const orc_query* q, orc_mset* out) {
         wl[j] = ix->wdfs + ix->off[t];
         len[j] = (uint32_t)(ix->off[t + 1] - ix->off[t]);
         uint32_t gtf = q->stats ? q->stats->termfreq[j] : len[j];
-        /* LocalSubMatch::open_post_list matcher/localsubmatch.cc:295-299: factor 1.0 per leaf */
-        orc_bm25_init(coll, tlen, gtf, q->wqf ? q->wqf[j] : 1, 1.0, q->k1, q->k3, q->b, &tw[j], &len_factor);
+        /* LocalSubMatch::open_post_list matcher/localsubmatch.cc:295-299: the leaf's factor is the product of
+         * the OP_SCALE_WEIGHT factors above it (1.0 without any); factor 0 → no Weight object at all */
+        const double factor = q->factors ? q->factors[j] : 1.0;
+        orc_bm25_init(coll, tlen, gtf, q->wqf ? q->wqf[j] : 1, factor, q->k1, q->k3, q->b, &tw[j], &len_factor);
         maxpart[j] = orc_bm25_maxpart(tw[j], len_factor, q->k1, q->b, q->min_normlen, ix->wdf_ub[t], ix->doclen_lb);
+        if (factor == 0.0) { tw[j] = 0.0; maxpart[j] = 0.0; }
         (void)max_possible_leafsum;
     }
 
@@ -712,7 +715,9 @@ int orc_match(const orc_index* ix, const orc_query* q, orc_mset* out) {
     P.results = (res_t*)xcalloc((size_t)P.max_size + 1, sizeof(res_t));
     P.cmp.sort_by = q->sort_by;
     P.cmp.reverse = q->sort_reverse;
-    uint32_t total_subqs = n + nm; /* weighted leaves, api/queryinternal.cc:1053-1054 */
+    uint32_t nweighted = 0; /* leaves with a Weight object: QueryTerm::postlist counts them only when factor != 0 */
+    for (uint32_t j = 0; j < n; ++j) nweighted += (!q->factors || q->factors[j] != 0.0) ? 1u : 0u;
+    uint32_t total_subqs = nweighted + nm; /* api/queryinternal.cc:1053-1054 */
 
     uint64_t* pos = (uint64_t*)xcalloc(n, 8);
     double* stk = (double*)xcalloc(2 * (n + nm) + 2, 8);
@@ -750,7 +755,7 @@ int orc_match(const orc_index* ix, const orc_query* q, orc_mset* out) {
                     uint32_t j = order[i];
                     weight += orc_bm25_sumpart(tw[j], len_factor, q->k1, q->b, q->min_normlen, wl[j][pos[j]], doclen);
                 }
-                subqs = n;
+                subqs = nweighted;
                 if (nf || nx || nm) {
                     int keep = 1;
                     for (uint32_t i = 0; i < nf && keep; ++i) {
@@ -804,7 +809,7 @@ int orc_match(const orc_index* ix, const orc_query* q, orc_mset* out) {
                         if (pos[j] < len[j] && dl[j][pos[j]] == did) {
                             stk[sp] = orc_bm25_sumpart(tw[j], len_factor, q->k1, q->b, q->min_normlen, wl[j][pos[j]], doclen);
                             stkp[sp] = 1;
-                            ++subqs;
+                            if (!q->factors || q->factors[j] != 0.0) ++subqs;
                         } else { stk[sp] = 0; stkp[sp] = 0; }
                         ++sp;
                     } else {
@@ -816,6 +821,11 @@ int orc_match(const orc_index* ix, const orc_query* q, orc_mset* out) {
                 weight = stk[0];
             }
             ++exact;
+            /* a value-range / posting-source filter is a matching subquery of every document it lets through
+             * (ValueRangePostList / ExternalPostList::count_matching_subqs return 1) although, being unweighted,
+             * it is not one of the total_subqs (api/queryinternal.cc:1097-1098): percentages of filtered
+             * queries are scaled by (n+1)/n */
+            if (q->filter != ORC_FILTER_NONE) ++subqs;
             /* main loop, matcher/matcher.cc:482-536 */
             if (weight < P.min_weight) continue;
             res_t item;

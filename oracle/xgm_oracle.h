@@ -53,6 +53,8 @@ typedef struct orc_query {
     uint32_t nterms;
     const uint32_t* terms;    /* term ids */
     const uint32_t* wqf;      /* NULL = all 1 */
+    const double* factors;    /* NULL = all 1.0; per term OP_SCALE_WEIGHT factor (api/queryinternal.cc:1075-1080);
+                                 0 makes the leaf unweighted (no Weight object, not a counted subquery) */
     uint32_t first, maxitems, check_at_least;
     const orc_stats* stats;   /* NULL = local */
     /* BM25 parameters (src/xapian/weight.h:665-667 defaults k1=1 k2=0 k3=1 b=0.5 min_normlen=0.5) */

@@ -33,7 +33,9 @@ def run_set(tag, ndocs, vocab, queries, nshards=1, twophase=False, values=False,
             dbs.append(d)
         lines = []
         for q in queries:
-            lines.append(O.query_line("TERM" if len(q["terms"]) == 1 else q["op"], [name(t) for t in q["terms"]],
+            facs = q.get("factors")
+            tnames = [name(t) + ("" if not facs or facs[j] == 1.0 else f"^{facs[j]!r}") for j, t in enumerate(q["terms"])]
+            lines.append(O.query_line("TERM" if len(q["terms"]) == 1 else q["op"], tnames,
                                       q["first"], q["maxitems"], q["check_at_least"], vr=q.get("vr"), sort=q.get("sort"),
                                       filter_terms=[name(t) for t in q.get("filter_terms", [])],
                                       not_terms=[name(t) for t in q.get("not_terms", [])],
@@ -47,6 +49,7 @@ def run_set(tag, ndocs, vocab, queries, nshards=1, twophase=False, values=False,
             e["weights"] = [float(w).hex() for w in r.weights]
             if r.sort_keys:
                 e["sort_keys"] = r.sort_keys
+            e["percents"] = r.percents
             e.update(lb=r.lb, est=r.est, ub=r.ub, max_possible=float(r.max_possible).hex(),
                      max_attained=float(r.max_attained).hex())
             fixture["queries"].append(e)
@@ -92,11 +95,26 @@ def ops_queries(rng, n, topranks, ndocs):
     return qs
 
 
+def scale_queries(rng, n, topranks, ndocs):
+    """OP_SCALE_WEIGHT factors on the leaves of AND / OR queries (Xapiand's _boost); factor 0 = unweighted leaf."""
+    qs = []
+    for _ in range(n):
+        nb = rng.choice([1, 2, 3, 4])
+        fac = [rng.choice([1.0, 1.0, 2.0, 0.5, 3.25, 0.0, 1e-3]) for _ in range(nb)]
+        if all(f == 0.0 for f in fac):
+            fac[0] = 1.5
+        qs.append(dict(op=rng.choice(["AND", "OR"]), terms=rng.sample(range(topranks), nb), factors=fac,
+                       first=rng.choice([0, 0, 3]), maxitems=rng.choice([5, 10, 50, 200]),
+                       check_at_least=rng.choice([0, 0, ndocs])))
+    return qs
+
+
 def main():
     if not O.have_reference():
         raise SystemExit("oracle/_ref not built: run oracle/build_ref.sh (needs /root/reference)")
-    if sys.argv[1:] == ["ops"]:  # only the fixture added after round 1's first batch
+    if sys.argv[1:] == ["ops"]:  # only the fixtures added after round 1's first batch
         run_set("ops_6k", 6000, 900, ops_queries(random.Random(20260924), 240, 200, 6000), seed=11)
+        run_set("scale_6k", 6000, 900, scale_queries(random.Random(20260925), 200, 200, 6000), seed=11)
         return
     rng = random.Random(20260923)
     # C1: BASELINE config 1 — 1k docs / 100 terms, every single term top-10, plus mixed shapes
@@ -124,6 +142,7 @@ def main():
         vq.append(q)
     run_set("values_5k", 5000, 2000, vq, values=True)
     run_set("ops_6k", 6000, 900, ops_queries(random.Random(20260924), 240, 200, 6000), seed=11)
+    run_set("scale_6k", 6000, 900, scale_queries(random.Random(20260925), 200, 200, 6000), seed=11)
 
 
 if __name__ == "__main__":

@@ -21,7 +21,7 @@ def o_query(q, stats=None, first=None, maxitems=None):
         kw.update(filter=O.FILTER_VALUE_RANGE_MIN, range_lo=q["vr"][1], range_hi=q["vr"][2])
     if "sort" in q:
         kw.update(sort_by=O.SORT_VAL_REL, sort_slot=q["sort"][0], sort_reverse=bool(q["sort"][1]))
-    for g in ("filter_terms", "not_terms", "maybe_terms"):
+    for g in ("filter_terms", "not_terms", "maybe_terms", "factors"):
         if q.get(g):
             kw[g] = q[g]
     return O.Query(**kw)
@@ -34,6 +34,9 @@ def check(m, q, ctx, counts=True):
     if counts:
         assert bits(m.max_possible) == bits(q["max_possible"]), f"{ctx}: max_possible"
         assert (m.lb, O.round_estimate(m.lb, m.ub, m.est), m.ub) == (q["lb"], q["est"], q["ub"]), f"{ctx}: bounds"
+    if "percents" in q:  # MSetIterator::get_percent of the reference ← percent_scale_factor (protomset.h:466-471)
+        mine = [O.convert_to_percent(w, m.percent_scale_factor) for w in m.weights]
+        assert mine == q["percents"], f"{ctx}: percentages"
 
 
 @pytest.mark.parametrize("tag", ["c1_1k_100", "mid_20k"])
@@ -55,6 +58,15 @@ def test_oracle_matches_reference_filter_andnot_andmaybe():
         check(ix.match(o_query(q)), q, f"ops[{i}] {q}")
         shapes.add((bool(q["filter_terms"]), bool(q["not_terms"]), bool(q["maybe_terms"])))
     assert len(shapes) >= 7  # every combination of the three groups is present
+
+
+def test_oracle_matches_reference_scale_weight():
+    """OP_SCALE_WEIGHT factors on the leaves (QueryScaleWeight::postlist api/queryinternal.cc:1075-1080 →
+    Weight::init_ factor), incl. factor 0 = unweighted leaf that is not a counted subquery."""
+    fx = load("scale_6k")
+    ix = O.Index.synthetic(fx["ndocs"], fx["vocab"], fx["seed"])
+    for i, q in enumerate(fx["queries"]):
+        check(ix.match(o_query(q)), q, f"scale[{i}] {q['op']} {q['terms']} x {q['factors']}")
 
 
 def test_oracle_matches_reference_twophase_shards():

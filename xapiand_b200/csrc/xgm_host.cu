@@ -1651,6 +1651,10 @@ static void finish_info(const PlannedQuery& pq, const XgmDevResult* dr, const do
         /* AND: every leaf matches; OR sorted by relevance: leaves matching the best document */
         uint32_t subqs = dr->max_subqs;
         if (is_or && pq.sort_by == XGM_SORT_REL && keys) subqs = (uint32_t)keys[0];
+        /* a value-range / posting-source filter counts as a matching subquery (ValueRangePostList /
+         * ExternalPostList::count_matching_subqs return 1) without being one of the total weighted leaves
+         * (api/queryinternal.cc:1097-1098) */
+        if (pq.filter) subqs += 1;
         double percent_scale = (double)subqs / (double)pq.nterms;
         percent_scale /= max_w;
         o->percent_scale_factor = percent_scale * 100.0;
