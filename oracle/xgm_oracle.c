@@ -637,7 +637,7 @@ int orc_match(const orc_index* ix, const orc_query* q, orc_mset* out) {
 
     /* §8(f)-1 groups around an AND base */
     const uint32_t nf = q->nfilter, nx = q->nnot, nm = q->nmaybe;
-    if ((nf || nx || nm) && (q->op != ORC_OP_AND || q->filter != ORC_FILTER_NONE)) return -1;
+    if ((nf || nx || nm) && q->filter != ORC_FILTER_NONE) return -1;
     uint32_t* mlen = NULL; double* mtw = NULL; double* mmax = NULL; int32_t* mprog = NULL; uint32_t mnprog = 0;
     if (nf || nx || nm) {
         node_t cur; cur.mn = tf_min; cur.mx = tf_max; cur.est = tf_est; cur.maxw = max_possible;
@@ -728,7 +728,7 @@ int orc_match(const orc_index* ix, const orc_query* q, orc_mset* out) {
         uint32_t did = 0;
         for (;;) {
             double weight = 0;
-            uint32_t subqs = 0;
+            uint32_t subqs = 0, doclen = 0;
             if (q->op == ORC_OP_AND) {
                 /* MultiAndPostList::find_next_match matcher/multiandpostlist.cc:179-206 */
                 uint32_t d0 = order[0];
@@ -750,46 +750,12 @@ int orc_match(const orc_index* ix, const orc_query* q, orc_mset* out) {
                 if (!ok) continue;
                 if (!pass_filter(ix, q, did)) continue;
                 /* MultiAndPostList::get_weight multiandpostlist.cc:149-159: result = 0; += in plist order */
-                uint32_t doclen = ix->doclen[did];
+                doclen = ix->doclen[did];
                 for (uint32_t i = 0; i < n; ++i) {
                     uint32_t j = order[i];
                     weight += orc_bm25_sumpart(tw[j], len_factor, q->k1, q->b, q->min_normlen, wl[j][pos[j]], doclen);
                 }
                 subqs = nweighted;
-                if (nf || nx || nm) {
-                    int keep = 1;
-                    for (uint32_t i = 0; i < nf && keep; ++i) {
-                        uint32_t t = q->filter_terms[i];
-                        keep = list_contains(ix->docids + ix->off[t], (uint32_t)(ix->off[t + 1] - ix->off[t]), did, NULL);
-                    }
-                    for (uint32_t i = 0; i < nx && keep; ++i) {
-                        uint32_t t = q->not_terms[i];
-                        keep = !list_contains(ix->docids + ix->off[t], (uint32_t)(ix->off[t + 1] - ix->off[t]), did, NULL);
-                    }
-                    if (!keep) continue;
-                    if (nm) {
-                        /* AndMaybePostList::get_weight matcher/andmaybepostlist.cc:59-67: l + (r if it matches);
-                         * r is the OrPostList tree over the optional leaves (l, r or l + r per node) */
-                        uint32_t sp = 0, present = 0;
-                        for (uint32_t i = 0; i < mnprog; ++i) {
-                            if (mprog[i] >= 0) {
-                                uint32_t j = (uint32_t)mprog[i], t = q->maybe_terms[j], where;
-                                if (list_contains(ix->docids + ix->off[t], mlen[j], did, &where)) {
-                                    stk[sp] = orc_bm25_sumpart(mtw[j], len_factor, q->k1, q->b, q->min_normlen,
-                                                               ix->wdfs[ix->off[t] + where], doclen);
-                                    stkp[sp] = 1;
-                                    ++present;
-                                } else { stk[sp] = 0; stkp[sp] = 0; }
-                                ++sp;
-                            } else {
-                                --sp;
-                                if (stkp[sp - 1] && stkp[sp]) stk[sp - 1] = stk[sp - 1] + stk[sp];
-                                else if (stkp[sp]) { stk[sp - 1] = stk[sp]; stkp[sp - 1] = 1; }
-                            }
-                        }
-                        if (present) { weight = weight + stk[0]; subqs += present; }
-                    }
-                }
             } else {
                 /* union in docid order; OrPostList::get_weight matcher/orpostlist.cc:93-103 folds
                  * l, r or l+r per node of the Huffman-shaped tree */
@@ -801,7 +767,7 @@ int orc_match(const orc_index* ix, const orc_query* q, orc_mset* out) {
                 if (best == 0xffffffffu) break;
                 did = best;
                 if (!pass_filter(ix, q, did)) continue;
-                uint32_t doclen = ix->doclen[did];
+                doclen = ix->doclen[did];
                 uint32_t sp = 0;
                 for (uint32_t i = 0; i < nprog; ++i) {
                     if (prog[i] >= 0) {
@@ -819,6 +785,40 @@ int orc_match(const orc_index* ix, const orc_query* q, orc_mset* out) {
                     }
                 }
                 weight = stk[0];
+            }
+            if (nf || nx || nm) {
+                int keep = 1;
+                for (uint32_t i = 0; i < nf && keep; ++i) {
+                    uint32_t t = q->filter_terms[i];
+                    keep = list_contains(ix->docids + ix->off[t], (uint32_t)(ix->off[t + 1] - ix->off[t]), did, NULL);
+                }
+                for (uint32_t i = 0; i < nx && keep; ++i) {
+                    uint32_t t = q->not_terms[i];
+                    keep = !list_contains(ix->docids + ix->off[t], (uint32_t)(ix->off[t + 1] - ix->off[t]), did, NULL);
+                }
+                if (!keep) continue;
+                if (nm) {
+                    /* AndMaybePostList::get_weight matcher/andmaybepostlist.cc:59-67: l + (r if it matches);
+                     * r is the OrPostList tree over the optional leaves (l, r or l + r per node) */
+                    uint32_t sp = 0, present = 0;
+                    for (uint32_t i = 0; i < mnprog; ++i) {
+                        if (mprog[i] >= 0) {
+                            uint32_t j = (uint32_t)mprog[i], t = q->maybe_terms[j], where;
+                            if (list_contains(ix->docids + ix->off[t], mlen[j], did, &where)) {
+                                stk[sp] = orc_bm25_sumpart(mtw[j], len_factor, q->k1, q->b, q->min_normlen,
+                                                           ix->wdfs[ix->off[t] + where], doclen);
+                                stkp[sp] = 1;
+                                ++present;
+                            } else { stk[sp] = 0; stkp[sp] = 0; }
+                            ++sp;
+                        } else {
+                            --sp;
+                            if (stkp[sp - 1] && stkp[sp]) stk[sp - 1] = stk[sp - 1] + stk[sp];
+                            else if (stkp[sp]) { stk[sp - 1] = stk[sp]; stkp[sp - 1] = 1; }
+                        }
+                    }
+                    if (present) { weight = weight + stk[0]; subqs += present; }
+                }
             }
             ++exact;
             /* a value-range / posting-source filter is a matching subquery of every document it lets through

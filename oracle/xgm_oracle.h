@@ -64,7 +64,8 @@ typedef struct orc_query {
     int sort_by;              /* ORC_SORT_* */
     int sort_slot;            /* 0: smallest slot-0 value, 1: slot 1, 2: largest slot-0 value */
     int sort_reverse;         /* set_sort_by_value_then_relevance(slot, reverse) */
-    /* SURVEY.md §8(f)-1 shapes around an AND (or single-term) base, innermost first:
+    /* SURVEY.md §8(f)-1 shapes around an AND, single-term or OR base (the device path covers AND / single-term
+     * bases; OR bases are restated here for the next round), innermost first:
      *   OP_FILTER(base, AND of boolean terms)      QueryFilter::postlist   api/queryinternal.cc:2270-2283
      *   OP_AND_NOT(…, OR of terms)                 QueryAndNot::postlist   api/queryinternal.cc:2208-2225
      *   OP_AND_MAYBE(…, OR of weighted terms)      QueryAndMaybe::postlist api/queryinternal.cc:2247-2268 */
