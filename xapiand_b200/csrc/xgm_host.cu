@@ -1632,6 +1632,12 @@ static void finish_info(const PlannedQuery& pq, const XgmDevResult* dr, const do
         else if (size != pq.topk) lb = est = ub = size;
         else if (known < pq.check_at_least) lb = est = ub = known;
         else { lb = std::max(lb, known); est = std::max(est, known); }
+        /* The kernel counts "among the first max(check_at_least, k+1) or fewer than k earlier matches are
+         * greater", which is ProtoMSet's count when check_at_least <= k+1 (min_weight rises at the heap build)
+         * or is never reached.  In between, the reference's min_weight only starts rising at the first
+         * replacement after known_matching_docs reached check_at_least (protomset.h:377-398), so it counts
+         * more: our count is then a lower bound — flag the bounds. */
+        if (pq.check_at_least > pq.topk + 1 && known < dr->exact && !pq.count_only) o->flags |= XGM_MSET_BOUNDS_APPROX;
         if (dr->flags & 5u) o->status = XGM_E_UNIMPLEMENTED; /* candidates lost: pathological tie mass */
         if (dr->flags & 2u) o->flags |= XGM_MSET_BOUNDS_APPROX;
         if (dr->flags & 8u) o->flags |= XGM_MSET_BOUNDS_APPROX | XGM_MSET_COUNT_LOWER_BOUND;
