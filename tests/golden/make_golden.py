@@ -109,12 +109,28 @@ def scale_queries(rng, n, topranks, ndocs):
     return qs
 
 
+def regime_queries(rng, n, topranks, ndocs):
+    """Intermediate check_at_least (between k+1 and the match count), small k, first > 0, value sorts: the
+    regimes where ProtoMSet's min_weight lags (protomset.h:377-398)."""
+    qs = []
+    for i in range(n):
+        nb = rng.choice([1, 2, 3, 4])
+        q = dict(op=rng.choice(["AND", "OR"]), terms=rng.sample(range(topranks), nb), first=rng.choice([0, 0, 1, 3, 10]),
+                 maxitems=rng.choice([1, 2, 5, 10, 50, 200]),
+                 check_at_least=rng.choice([0, 3, 7, 20, 40, 100, 300, 1000, ndocs]))
+        if i % 4 == 0:
+            q["sort"] = [1, rng.choice([0, 1])]
+        qs.append(q)
+    return qs
+
+
 def main():
     if not O.have_reference():
         raise SystemExit("oracle/_ref not built: run oracle/build_ref.sh (needs /root/reference)")
     if sys.argv[1:] == ["ops"]:  # only the fixtures added after round 1's first batch
         run_set("ops_6k", 6000, 900, ops_queries(random.Random(20260924), 240, 200, 6000), seed=11)
         run_set("scale_6k", 6000, 900, scale_queries(random.Random(20260925), 200, 200, 6000), seed=11)
+        run_set("regimes_6k", 6000, 900, regime_queries(random.Random(20260926), 300, 120, 6000), seed=11, values=True)
         return
     rng = random.Random(20260923)
     # C1: BASELINE config 1 — 1k docs / 100 terms, every single term top-10, plus mixed shapes
@@ -143,6 +159,7 @@ def main():
     run_set("values_5k", 5000, 2000, vq, values=True)
     run_set("ops_6k", 6000, 900, ops_queries(random.Random(20260924), 240, 200, 6000), seed=11)
     run_set("scale_6k", 6000, 900, scale_queries(random.Random(20260925), 200, 200, 6000), seed=11)
+    run_set("regimes_6k", 6000, 900, regime_queries(random.Random(20260926), 300, 120, 6000), seed=11, values=True)
 
 
 if __name__ == "__main__":

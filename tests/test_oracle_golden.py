@@ -69,6 +69,16 @@ def test_oracle_matches_reference_scale_weight():
         check(ix.match(o_query(q)), q, f"scale[{i}] {q['op']} {q['terms']} x {q['factors']}")
 
 
+def test_oracle_matches_reference_count_regimes():
+    """check_at_least between k+1 and the match count, k = 1, first > 0, value sorts: where ProtoMSet's
+    min_weight lags behind the k-th best weight (protomset.h:377-398) and the count rule has its third term
+    (tests/test_protomset_count_model.py)."""
+    fx = load("regimes_6k")
+    ix = O.Index.synthetic(fx["ndocs"], fx["vocab"], fx["seed"], values=True)
+    for i, q in enumerate(fx["queries"]):
+        check(ix.match(o_query(q)), q, f"regimes[{i}] {q}")
+
+
 def test_oracle_matches_reference_twophase_shards():
     fx = load("shard4_20k")
     n = fx["nshards"]
