@@ -179,10 +179,18 @@ static std::vector<QSpec> load_queries(const std::string& path) {
 static Xapian::Query make_query(const QSpec& q) {
     /* "term^factor" → OP_SCALE_WEIGHT(term, factor) (Xapiand's _boost, QueryScaleWeight::postlist
      * api/queryinternal.cc:1075-1080) */
-    auto leaf = [](const std::string& t) {
+    /* "term#wqf" → Query(term, wqf) (within-query frequency, QueryTerm::get_wqf) */
+    auto leaf = [](const std::string& t0) {
+        std::string t = t0;
         const size_t c = t.find('^');
-        if (c == std::string::npos) return Xapian::Query(t);
-        return Xapian::Query(Xapian::Query::OP_SCALE_WEIGHT, Xapian::Query(t.substr(0, c)), atof(t.c_str() + c + 1));
+        double factor = 1.0;
+        bool scaled = false;
+        if (c != std::string::npos) { factor = atof(t.c_str() + c + 1); t = t.substr(0, c); scaled = true; }
+        const size_t h = t.find('#');
+        Xapian::termcount wqf = 1;
+        if (h != std::string::npos) { wqf = (Xapian::termcount)atoi(t.c_str() + h + 1); t = t.substr(0, h); }
+        Xapian::Query q(t, wqf);
+        return scaled ? Xapian::Query(Xapian::Query::OP_SCALE_WEIGHT, q, factor) : q;
     };
     std::vector<Xapian::Query> leaves;
     for (const auto& t : q.terms) leaves.push_back(leaf(t));

@@ -33,8 +33,9 @@ def run_set(tag, ndocs, vocab, queries, nshards=1, twophase=False, values=False,
             dbs.append(d)
         lines = []
         for q in queries:
-            facs = q.get("factors")
-            tnames = [name(t) + ("" if not facs or facs[j] == 1.0 else f"^{facs[j]!r}") for j, t in enumerate(q["terms"])]
+            facs, wq = q.get("factors"), q.get("wqf")
+            tnames = [name(t) + ("" if not wq or wq[j] == 1 else f"#{wq[j]}") +
+                      ("" if not facs or facs[j] == 1.0 else f"^{facs[j]!r}") for j, t in enumerate(q["terms"])]
             lines.append(O.query_line("TERM" if len(q["terms"]) == 1 else q["op"], tnames,
                                       q["first"], q["maxitems"], q["check_at_least"], vr=q.get("vr"), sort=q.get("sort"),
                                       filter_terms=[name(t) for t in q.get("filter_terms", [])],
@@ -124,6 +125,17 @@ def regime_queries(rng, n, topranks, ndocs):
     return qs
 
 
+def wqf_queries(rng, n, topranks, ndocs):
+    """Within-query frequencies > 1 (Query(term, wqf): the (k3+1)*wqf/(k3+wqf) factor of BM25Weight::init)."""
+    qs = []
+    for _ in range(n):
+        nb = rng.choice([1, 2, 3, 4])
+        qs.append(dict(op=rng.choice(["AND", "OR"]), terms=rng.sample(range(topranks), nb),
+                       wqf=[rng.choice([1, 1, 2, 3, 7]) for _ in range(nb)], first=rng.choice([0, 0, 3]),
+                       maxitems=rng.choice([5, 10, 50]), check_at_least=rng.choice([0, 30, ndocs])))
+    return qs
+
+
 def main():
     if not O.have_reference():
         raise SystemExit("oracle/_ref not built: run oracle/build_ref.sh (needs /root/reference)")
@@ -131,6 +143,7 @@ def main():
         run_set("ops_6k", 6000, 900, ops_queries(random.Random(20260924), 240, 200, 6000), seed=11)
         run_set("scale_6k", 6000, 900, scale_queries(random.Random(20260925), 200, 200, 6000), seed=11)
         run_set("regimes_6k", 6000, 900, regime_queries(random.Random(20260926), 300, 120, 6000), seed=11, values=True)
+        run_set("wqf_6k", 6000, 900, wqf_queries(random.Random(20260927), 150, 150, 6000), seed=11)
         return
     rng = random.Random(20260923)
     # C1: BASELINE config 1 — 1k docs / 100 terms, every single term top-10, plus mixed shapes
@@ -160,6 +173,7 @@ def main():
     run_set("ops_6k", 6000, 900, ops_queries(random.Random(20260924), 240, 200, 6000), seed=11)
     run_set("scale_6k", 6000, 900, scale_queries(random.Random(20260925), 200, 200, 6000), seed=11)
     run_set("regimes_6k", 6000, 900, regime_queries(random.Random(20260926), 300, 120, 6000), seed=11, values=True)
+    run_set("wqf_6k", 6000, 900, wqf_queries(random.Random(20260927), 150, 150, 6000), seed=11)
 
 
 if __name__ == "__main__":

@@ -21,7 +21,7 @@ def o_query(q, stats=None, first=None, maxitems=None):
         kw.update(filter=O.FILTER_VALUE_RANGE_MIN, range_lo=q["vr"][1], range_hi=q["vr"][2])
     if "sort" in q:
         kw.update(sort_by=O.SORT_VAL_REL, sort_slot=q["sort"][0], sort_reverse=bool(q["sort"][1]))
-    for g in ("filter_terms", "not_terms", "maybe_terms", "factors"):
+    for g in ("filter_terms", "not_terms", "maybe_terms", "factors", "wqf"):
         if q.get(g):
             kw[g] = q[g]
     return O.Query(**kw)
@@ -67,6 +67,14 @@ def test_oracle_matches_reference_scale_weight():
     ix = O.Index.synthetic(fx["ndocs"], fx["vocab"], fx["seed"])
     for i, q in enumerate(fx["queries"]):
         check(ix.match(o_query(q)), q, f"scale[{i}] {q['op']} {q['terms']} x {q['factors']}")
+
+
+def test_oracle_matches_reference_wqf():
+    """Within-query frequency > 1: Weight::init_'s wqf and BM25Weight::init's (k3+1)*wqf/(k3+wqf) factor."""
+    fx = load("wqf_6k")
+    ix = O.Index.synthetic(fx["ndocs"], fx["vocab"], fx["seed"])
+    for i, q in enumerate(fx["queries"]):
+        check(ix.match(o_query(q)), q, f"wqf[{i}] {q['op']} {q['terms']} wqf {q['wqf']}")
 
 
 def test_oracle_matches_reference_count_regimes():
