@@ -50,7 +50,10 @@ def _worker(rank, world, port, q):
                       and struct.pack("<d", merged.max_possible) == struct.pack("<d", gq["max_possible"])
                       and struct.pack("<d", merged.max_attained) == struct.pack("<d", gq["max_attained"])
                       and (merged.matches_lower_bound, merged.get_matches_estimated(), merged.matches_upper_bound)
-                      == (gq["lb"], gq["est"], gq["ub"]))
+                      == (gq["lb"], gq["est"], gq["ub"])
+                      # MSetIterator::get_percent of the merged MSet: the percent scale of the shard with the
+                      # highest max_attained (MSet::Internal::merge_stats, api/mset.cc:376-395)
+                      and [O.convert_to_percent(w, merged.percent_scale_factor) for w in merged.weights] == gq["percents"])
                 if not ok:
                     bad.append(i)
         if rank == 0:
