@@ -176,8 +176,10 @@ typedef struct xgm_mset_info {
 
 /* ProtoMSet::known_matching_docs depends on the docid-order history of the match (SURVEY.md §7 hard
  * part 3).  It is reproduced exactly whenever the whole match set fits the searcher's candidate
- * buffer; for larger match sets that were pruned on the device the lower bound / estimate are
- * conservative (still valid bounds) and this flag is set.  Docids, weights, max_possible,
+ * buffer and check_at_least is at most first+maxitems+1 (Xapiand's default) or is never reached; for larger
+ * match sets that were pruned on the device, or a check_at_least in between (where the reference's
+ * min_weight lags, protomset.h:377-398), the lower bound / estimate are conservative (still valid
+ * bounds) and this flag is set.  Docids, weights, max_possible,
  * max_attained, the upper bound and exact_matches are always exact. */
 #define XGM_MSET_BOUNDS_APPROX 1u
 /* OR queries only: MaxScore skipped whole posting-list segments that cannot reach the top-k (what
@@ -186,8 +188,11 @@ typedef struct xgm_mset_info {
 #define XGM_MSET_COUNT_LOWER_BOUND 2u
 
 /* ---- searching ---------------------------------------------------------------------------- */
-/* A searcher owns a CUDA stream and pinned/device staging for batches of up to max_batch queries
- * with first+maxitems <= max_topk each. */
+/* A searcher is what one Xapian::Enquire is to the reference (src/xapian/api/enquire.cc:71-298; one per
+ * thread, like Xapiand's one Enquire per DocMatcher, src/database/handler.cc:1250-1371): it owns a CUDA
+ * stream and pinned/device staging for batches of up to max_batch queries with first+maxitems <= max_topk
+ * each.  xgm_search* replace Matcher::get_local_mset (src/xapian/matcher/matcher.cc:346-542, declared in
+ * matcher.h:92-108) for the query shapes listed at xgm_query. */
 xgm_status xgm_searcher_new(const xgm_index*, uint32_t max_batch, uint32_t max_topk, xgm_searcher** out);
 void xgm_searcher_free(xgm_searcher*);
 
