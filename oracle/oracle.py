@@ -421,6 +421,8 @@ def query_line(op: str, terms: Sequence[str], first: int, maxitems: int, check_a
         s += f" VR {vr[0]} {vr[1]} {vr[2]}"
     if sort is not None:
         s += f" SORT {sort[0]} {int(sort[1])}"
+        if len(sort) > 2 and sort[2]:
+            s += f" SORTMODE {int(sort[2])}"  # 1 = value only, 2 = relevance then value
     return s
 
 

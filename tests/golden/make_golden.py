@@ -37,7 +37,8 @@ def run_set(tag, ndocs, vocab, queries, nshards=1, twophase=False, values=False,
             tnames = [name(t) + ("" if not wq or wq[j] == 1 else f"#{wq[j]}") +
                       ("" if not facs or facs[j] == 1.0 else f"^{facs[j]!r}") for j, t in enumerate(q["terms"])]
             lines.append(O.query_line("TERM" if len(q["terms"]) == 1 else q["op"], tnames,
-                                      q["first"], q["maxitems"], q["check_at_least"], vr=q.get("vr"), sort=q.get("sort"),
+                                      q["first"], q["maxitems"], q["check_at_least"], vr=q.get("vr"),
+                                      sort=(q["sort"] + [q.get("sort_mode", 0)]) if q.get("sort") else None,
                                       filter_terms=[name(t) for t in q.get("filter_terms", [])],
                                       not_terms=[name(t) for t in q.get("not_terms", [])],
                                       maybe_terms=[name(t) for t in q.get("maybe_terms", [])]))
@@ -136,6 +137,17 @@ def wqf_queries(rng, n, topranks, ndocs):
     return qs
 
 
+def sortmode_queries(rng, n, topranks, ndocs):
+    """set_sort_by_value (mode 1) and set_sort_by_relevance_then_value (mode 2) next to value-then-relevance (0)."""
+    qs = []
+    for _ in range(n):
+        nb = rng.choice([1, 2, 3])
+        qs.append(dict(op=rng.choice(["AND", "OR"]), terms=rng.sample(range(topranks), nb), first=rng.choice([0, 0, 3]),
+                       maxitems=rng.choice([1, 5, 10, 50, 200]), check_at_least=rng.choice([0, 20, 300, ndocs]),
+                       sort=[1, rng.choice([0, 1])], sort_mode=rng.choice([0, 1, 2])))
+    return qs
+
+
 def main():
     if not O.have_reference():
         raise SystemExit("oracle/_ref not built: run oracle/build_ref.sh (needs /root/reference)")
@@ -144,6 +156,7 @@ def main():
         run_set("scale_6k", 6000, 900, scale_queries(random.Random(20260925), 200, 200, 6000), seed=11)
         run_set("regimes_6k", 6000, 900, regime_queries(random.Random(20260926), 300, 120, 6000), seed=11, values=True)
         run_set("wqf_6k", 6000, 900, wqf_queries(random.Random(20260927), 150, 150, 6000), seed=11)
+        run_set("sortmodes_6k", 6000, 900, sortmode_queries(random.Random(20260928), 200, 100, 6000), seed=11, values=True)
         return
     rng = random.Random(20260923)
     # C1: BASELINE config 1 — 1k docs / 100 terms, every single term top-10, plus mixed shapes
@@ -174,6 +187,7 @@ def main():
     run_set("scale_6k", 6000, 900, scale_queries(random.Random(20260925), 200, 200, 6000), seed=11)
     run_set("regimes_6k", 6000, 900, regime_queries(random.Random(20260926), 300, 120, 6000), seed=11, values=True)
     run_set("wqf_6k", 6000, 900, wqf_queries(random.Random(20260927), 150, 150, 6000), seed=11)
+    run_set("sortmodes_6k", 6000, 900, sortmode_queries(random.Random(20260928), 200, 100, 6000), seed=11, values=True)
 
 
 if __name__ == "__main__":

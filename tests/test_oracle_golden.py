@@ -20,7 +20,8 @@ def o_query(q, stats=None, first=None, maxitems=None):
     if "vr" in q:
         kw.update(filter=O.FILTER_VALUE_RANGE_MIN, range_lo=q["vr"][1], range_hi=q["vr"][2])
     if "sort" in q:
-        kw.update(sort_by=O.SORT_VAL_REL, sort_slot=q["sort"][0], sort_reverse=bool(q["sort"][1]))
+        mode = {0: O.SORT_VAL_REL, 1: O.SORT_VAL, 2: O.SORT_REL_VAL}[q.get("sort_mode", 0)]
+        kw.update(sort_by=mode, sort_slot=q["sort"][0], sort_reverse=bool(q["sort"][1]))
     for g in ("filter_terms", "not_terms", "maybe_terms", "factors", "wqf"):
         if q.get(g):
             kw[g] = q[g]
@@ -75,6 +76,18 @@ def test_oracle_matches_reference_wqf():
     ix = O.Index.synthetic(fx["ndocs"], fx["vocab"], fx["seed"])
     for i, q in enumerate(fx["queries"]):
         check(ix.match(o_query(q)), q, f"wqf[{i}] {q['op']} {q['terms']} wqf {q['wqf']}")
+
+
+def test_oracle_matches_reference_sort_modes():
+    """Enquire::set_sort_by_value / set_sort_by_relevance_then_value / set_sort_by_value_then_relevance:
+    comparators of msetcmp.cc:54-98 and the ProtoMSet paths they select (early_reject, min_weight)."""
+    fx = load("sortmodes_6k")
+    ix = O.Index.synthetic(fx["ndocs"], fx["vocab"], fx["seed"], values=True)
+    seen = set()
+    for i, q in enumerate(fx["queries"]):
+        check(ix.match(o_query(q)), q, f"sortmodes[{i}] {q}")
+        seen.add(q["sort_mode"])
+    assert seen == {0, 1, 2}
 
 
 def test_oracle_matches_reference_count_regimes():
