@@ -135,6 +135,7 @@ class Query:
     check_at_least: int = 0
     wqf: Optional[Sequence[int]] = None
     factors: Optional[Sequence[float]] = None    # OP_SCALE_WEIGHT factor per term (oracle only so far)
+    bm25: Optional[tuple] = None                 # (k1, k3, b, min_normlen); None = BM25Weight defaults
     filter: int = FILTER_NONE
     range_lo: int = 0
     range_hi: int = 0
@@ -261,6 +262,8 @@ class Index:
         if q.factors is not None:
             fac = (C.c_double * len(q.factors))(*q.factors)
             cq.factors = fac
+        if q.bm25 is not None:
+            cq.k1, cq.k3, cq.b, cq.min_normlen = [float(x) for x in q.bm25]
         cq.first, cq.maxitems, cq.check_at_least = q.first, q.maxitems, q.check_at_least
         cq.filter, cq.range_lo, cq.range_hi = q.filter, q.range_lo, q.range_hi
         cq.sort_by, cq.sort_slot, cq.sort_reverse = q.sort_by, q.sort_slot, int(q.sort_reverse)
@@ -412,11 +415,13 @@ def ref_build_parallel(out_dir: str, ndocs: int, vocab: int, seed: int = 12345, 
 
 def query_line(op: str, terms: Sequence[str], first: int, maxitems: int, check_at_least: int = 0,
                vr: Optional[tuple] = None, sort: Optional[tuple] = None, filter_terms: Sequence[str] = (),
-               not_terms: Sequence[str] = (), maybe_terms: Sequence[str] = ()) -> str:
+               not_terms: Sequence[str] = (), maybe_terms: Sequence[str] = (), bm25: Optional[tuple] = None) -> str:
     s = f"{op} {first} {maxitems} {check_at_least} {len(terms)} " + " ".join(terms)
     for tag, ts in (("FT", filter_terms), ("NOT", not_terms), ("MAYBE", maybe_terms)):
         if ts:
             s += f" {tag} {len(ts)} " + " ".join(ts)
+    if bm25 is not None:  # (k1, k3, b, min_normlen)
+        s += " BM25 " + " ".join(repr(float(x)) for x in bm25)
     if vr is not None:
         s += f" VR {vr[0]} {vr[1]} {vr[2]}"
     if sort is not None:

@@ -146,6 +146,8 @@ struct QSpec {
     bool has_sort = false;    /* SORT slot reverse → set_sort_by_value_then_relevance */
     uint32_t s_slot = 0; bool s_rev = false;
     int s_mode = 0;           /* 0 value then relevance, 1 value only, 2 relevance then value */
+    bool has_params = false;  /* BM25 k1 k3 b min_normlen → set_weighting_scheme(BM25Weight(k1, 0, k3, b, min_normlen)) */
+    double k1 = 1, k3 = 1, b = 0.5, mnl = 0.5;
 };
 
 static std::vector<QSpec> load_queries(const std::string& path) {
@@ -165,6 +167,7 @@ static std::vector<QSpec> load_queries(const std::string& path) {
             if (tok == "VR") { q.has_range = true; is >> q.r_slot >> q.r_lo >> q.r_hi; }
             else if (tok == "SORT") { q.has_sort = true; int r; is >> q.s_slot >> r; q.s_rev = r != 0; }
             else if (tok == "SORTMODE") { is >> q.s_mode; }
+            else if (tok == "BM25") { q.has_params = true; is >> q.k1 >> q.k3 >> q.b >> q.mnl; }
             else if (tok == "FT" || tok == "NOT" || tok == "MAYBE") {
                 uint32_t m; is >> m;
                 std::vector<std::string>& dst = tok == "FT" ? q.filter_terms : tok == "NOT" ? q.not_terms : q.maybe_terms;
@@ -229,6 +232,7 @@ struct QResult {
 
 static void setup_enquire(Xapian::Enquire& enq, const QSpec& q) {
     enq.set_query(make_query(q));
+    if (q.has_params) enq.set_weighting_scheme(Xapian::BM25Weight(q.k1, 0.0, q.k3, q.b, q.mnl));
     if (q.has_sort && q.s_mode == 1) enq.set_sort_by_value(q.s_slot, q.s_rev);
     else if (q.has_sort && q.s_mode == 2) enq.set_sort_by_relevance_then_value(q.s_slot, q.s_rev);
     else if (q.has_sort) enq.set_sort_by_value_then_relevance(q.s_slot, q.s_rev);

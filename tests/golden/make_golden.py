@@ -39,6 +39,7 @@ def run_set(tag, ndocs, vocab, queries, nshards=1, twophase=False, values=False,
             lines.append(O.query_line("TERM" if len(q["terms"]) == 1 else q["op"], tnames,
                                       q["first"], q["maxitems"], q["check_at_least"], vr=q.get("vr"),
                                       sort=(q["sort"] + [q.get("sort_mode", 0)]) if q.get("sort") else None,
+                                      bm25=q.get("bm25"),
                                       filter_terms=[name(t) for t in q.get("filter_terms", [])],
                                       not_terms=[name(t) for t in q.get("not_terms", [])],
                                       maybe_terms=[name(t) for t in q.get("maybe_terms", [])]))
@@ -148,6 +149,20 @@ def sortmode_queries(rng, n, topranks, ndocs):
     return qs
 
 
+def bm25_queries(rng, n, topranks, ndocs):
+    """BM25Weight(k1, 0, k3, b, min_normlen) away from the defaults (k1 = 0 and b = 0 switch the length
+    normalisation off, k3 = 0 the wqf factor: bm25weight.cc:46-130), with wqf > 1 mixed in."""
+    qs = []
+    for _ in range(n):
+        nb = rng.choice([1, 2, 3, 4])
+        qs.append(dict(op=rng.choice(["AND", "OR"]), terms=rng.sample(range(topranks), nb),
+                       wqf=[rng.choice([1, 1, 3]) for _ in range(nb)], first=rng.choice([0, 0, 3]),
+                       maxitems=rng.choice([5, 10, 50]), check_at_least=rng.choice([0, 30, ndocs]),
+                       bm25=[rng.choice([0.0, 0.5, 1.0, 1.2, 2.0]), rng.choice([0.0, 1.0, 7.0]),
+                             rng.choice([0.0, 0.25, 0.5, 0.75, 1.0]), rng.choice([0.0, 0.5, 1.0])]))
+    return qs
+
+
 def main():
     if not O.have_reference():
         raise SystemExit("oracle/_ref not built: run oracle/build_ref.sh (needs /root/reference)")
@@ -157,6 +172,7 @@ def main():
         run_set("regimes_6k", 6000, 900, regime_queries(random.Random(20260926), 300, 120, 6000), seed=11, values=True)
         run_set("wqf_6k", 6000, 900, wqf_queries(random.Random(20260927), 150, 150, 6000), seed=11)
         run_set("sortmodes_6k", 6000, 900, sortmode_queries(random.Random(20260928), 200, 100, 6000), seed=11, values=True)
+        run_set("bm25_6k", 6000, 900, bm25_queries(random.Random(20260929), 200, 150, 6000), seed=11)
         return
     rng = random.Random(20260923)
     # C1: BASELINE config 1 — 1k docs / 100 terms, every single term top-10, plus mixed shapes
@@ -188,6 +204,7 @@ def main():
     run_set("regimes_6k", 6000, 900, regime_queries(random.Random(20260926), 300, 120, 6000), seed=11, values=True)
     run_set("wqf_6k", 6000, 900, wqf_queries(random.Random(20260927), 150, 150, 6000), seed=11)
     run_set("sortmodes_6k", 6000, 900, sortmode_queries(random.Random(20260928), 200, 100, 6000), seed=11, values=True)
+    run_set("bm25_6k", 6000, 900, bm25_queries(random.Random(20260929), 200, 150, 6000), seed=11)
 
 
 if __name__ == "__main__":

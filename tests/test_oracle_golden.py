@@ -22,7 +22,7 @@ def o_query(q, stats=None, first=None, maxitems=None):
     if "sort" in q:
         mode = {0: O.SORT_VAL_REL, 1: O.SORT_VAL, 2: O.SORT_REL_VAL}[q.get("sort_mode", 0)]
         kw.update(sort_by=mode, sort_slot=q["sort"][0], sort_reverse=bool(q["sort"][1]))
-    for g in ("filter_terms", "not_terms", "maybe_terms", "factors", "wqf"):
+    for g in ("filter_terms", "not_terms", "maybe_terms", "factors", "wqf", "bm25"):
         if q.get(g):
             kw[g] = q[g]
     return O.Query(**kw)
@@ -88,6 +88,15 @@ def test_oracle_matches_reference_sort_modes():
         check(ix.match(o_query(q)), q, f"sortmodes[{i}] {q}")
         seen.add(q["sort_mode"])
     assert seen == {0, 1, 2}
+
+
+def test_oracle_matches_reference_bm25_parameters():
+    """BM25Weight with non-default k1 / k3 / b / min_normlen (k2 = 0), incl. the k1 = 0 and b = 0 branches of
+    BM25Weight::init (bm25weight.cc:46-130) and get_maxpart."""
+    fx = load("bm25_6k")
+    ix = O.Index.synthetic(fx["ndocs"], fx["vocab"], fx["seed"])
+    for i, q in enumerate(fx["queries"]):
+        check(ix.match(o_query(q)), q, f"bm25[{i}] {q['op']} {q['terms']} {q['bm25']}")
 
 
 def test_oracle_matches_reference_count_regimes():
