@@ -5,7 +5,13 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load it.
  * Parity status: PINNED — checked against the compiled reference itself (oracle/_ref, built from
  * /root/reference/src/xapian by oracle/build_ref.sh) by tests/golden/make_golden.py; the resulting
- * fixtures are committed under tests/golden/ and re-checked by tests/test_oracle_golden.py.
+ * fixtures are committed under tests/golden/ and re-checked by tests/test_oracle_golden.py: docids,
+ * f64 weights, the three bounds, max_possible, max_attained and every item's percentage, for
+ * term / AND / OR, two-phase shards, value range + sort (all three sort modes), FILTER / AND_NOT /
+ * AND_MAYBE groups, OP_SCALE_WEIGHT factors, wqf, non-default BM25 parameters and the check_at_least /
+ * first regimes.  Not pinned by the reference: Xapiand's MultipleValueRange predicate (its sources need
+ * Xapiand's serialisers; restated from src/multivalue/range.cc:351-368), and term groups around an OR
+ * base agree with the reference except for its AndMaybePostList decay quirk.
  */
 #ifndef XGM_ORACLE_H
 #define XGM_ORACLE_H
