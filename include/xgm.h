@@ -159,6 +159,10 @@ typedef struct xgm_query {
      *            — declined for now (XGM_E_UNIMPLEMENTED: the shim lets the reference matcher run it)
      * nterms + nfilter + nnot + nmaybe <= XGM_MAX_TERMS. */
     uint32_t nfilter, nnot, nmaybe, reserved;
+    /* OP_SCALE_WEIGHT factor per base term (QueryScaleWeight::postlist api/queryinternal.cc:1075-1080: the
+     * product of the factors above a leaf reaches Weight::init_); NULL → 1.0 each.  A factor of 0 makes the
+     * leaf unweighted (AND bases only; under an OR it is declined). */
+    const double* factors;
 } xgm_query;
 
 /* One query's result: the fields of MSet::Internal (src/xapian/api/msetinternal.h:58-99). */

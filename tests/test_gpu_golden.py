@@ -217,3 +217,46 @@ def test_cuda_matches_reference_filter_andnot_andmaybe():
         checked += 1
     assert checked == len(qs)
 
+
+@pytest.mark.parametrize("tag", ["wqf_6k", "bm25_6k", "regimes_6k", "sortmodes_6k", "scale_6k"])
+def test_cuda_matches_reference_more_regimes(tag):
+    """The fixtures added late in round 1 (within-query frequencies, non-default BM25 parameters, intermediate
+    check_at_least / first, the three value-sort modes, OP_SCALE_WEIGHT factors) on the device."""
+    from oracle import oracle as O
+    fx = load(tag)
+    ix = xgm.Index.synthetic(fx["ndocs"], fx["vocab"], fx["seed"], values=fx["values"])
+    name = lambda t: f"T{t:06d}"
+    qs, keep = [], []
+    for q in fx["queries"]:
+        kw = dict(first=q["first"], maxitems=q["maxitems"], check_at_least=q["check_at_least"])
+        if q.get("wqf"):
+            kw["wqf"] = q["wqf"]
+        if q.get("factors"):
+            kw["factors"] = q["factors"]
+        if q.get("bm25"):
+            if not any(q["bm25"]):
+                continue  # all-zero parameters mean "defaults" at the C-ABI
+            kw["bm25"] = q["bm25"]
+        if q.get("sort"):
+            mode = {0: xgm.SORT_VAL_REL, 1: xgm.SORT_VAL, 2: xgm.SORT_REL_VAL}[q.get("sort_mode", 0)]
+            kw.update(sort_by=mode, sort_slot=q["sort"][0], sort_reverse=bool(q["sort"][1]))
+        qs.append(xgm.Query(xgm.OP_AND if q["op"] == "AND" else xgm.OP_OR, [name(t) for t in q["terms"]], **kw))
+        keep.append(q)
+    res = xgm.Searcher(ix, max_batch=len(qs), max_topk=256).search(qs)
+    declined = 0
+    for i, (q, m) in enumerate(zip(keep, res)):
+        ctx = f"{tag}[{i}] {q}"
+        if m.status == xgm.E_UNIMPLEMENTED and q.get("factors") and q["op"] == "OR" and 0.0 in q["factors"]:
+            declined += 1
+            continue
+        assert m.status == 0, ctx
+        assert list(m.docids) == q["docids"], ctx
+        assert all(bits(a) == bits(b) for a, b in zip(m.weights, q["weights"])), ctx
+        assert bits(m.max_possible) == bits(q["max_possible"]) and bits(m.max_attained) == bits(q["max_attained"]), ctx
+        assert m.matches_upper_bound == q["ub"], ctx
+        if not (m.flags & 1):
+            assert (m.matches_lower_bound, m.get_matches_estimated()) == (q["lb"], q["est"]), ctx
+        if not (q["op"] == "OR" and q.get("sort")):  # OR + value sort: percent scale is a documented approximation
+            assert [O.convert_to_percent(w, m.percent_scale_factor) for w in m.weights] == q["percents"], ctx
+    assert declined < len(keep) // 4
+

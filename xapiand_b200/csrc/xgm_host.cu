@@ -1088,13 +1088,20 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
         len_factor = avg != 0 ? 1 / avg : 0;
     }
     double tw[XGM_MAX_TERMS], maxpart[XGM_MAX_TERMS];
+    uint32_t nweighted_base = 0;
     for (uint32_t j = 0; j < n; ++j) {
         uint32_t gtf = q.stats ? q.stats->termfreq[j] : ltf[j];
-        tw[j] = bm25_termweight(N, gtf, q.wqf ? q.wqf[j] : 1, 1.0, k1, k3);
+        const double factor = q.factors ? q.factors[j] : 1.0;
+        if (factor < 0.0 || (factor == 0.0 && q.op == XGM_OP_OR && n > 1)) { pq.status = XGM_E_UNIMPLEMENTED; return XGM_OK; }
+        tw[j] = bm25_termweight(N, gtf, q.wqf ? q.wqf[j] : 1, factor, k1, k3);
         uint32_t wub = ids[j] == 0xffffffffu ? 0 : ix->terms[ids[j]].wdf_ub;
         maxpart[j] = bm25_maxpart(tw[j], len_factor, k1, b, mnl, wub, ix->doclen_lb);
+        if (factor == 0.0) { tw[j] = 0.0; maxpart[j] = 0.0; } /* no Weight object: not a counted subquery */
+        else ++nweighted_base;
     }
-    dq.op = q.op; dq.nterms = n + nfilter; dq.nweighted = n; dq.topk = pq.topk; dq.check_at_least = cal;
+    dq.op = q.op; dq.nterms = n + nfilter; dq.nweighted = q.op == XGM_OP_OR && n > 1 ? n : nweighted_base;
+    dq.topk = pq.topk; dq.check_at_least = cal;
+    pq.nterms = nweighted_base; /* total weighted leaves, for the percentage scale */
     dq.len_factor = len_factor; dq.k1 = k1; dq.b = b; dq.one_minus_b = 1 - b; dq.min_normlen = mnl;
     dq.filter = q.filter; dq.filter_slot = q.filter_slot; dq.range_lo = q.range_lo; dq.range_hi = q.range_hi;
     dq.sort_by = q.sort_by; dq.sort_slot = q.sort_slot; dq.sort_reverse = q.sort_reverse; dq.sort_use_max = q.sort_use_max;
@@ -1251,7 +1258,7 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
                 }
                 dq.nmaybe = nmaybe;
                 pq.aux_subqs = true;
-                pq.nterms = n + nmaybe; /* total weighted leaves, for the percentage scale */
+                pq.nterms = nweighted_base + nmaybe; /* total weighted leaves, for the percentage scale */
             }
         }
     } else {

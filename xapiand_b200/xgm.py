@@ -70,7 +70,8 @@ class CQuery(C.Structure):
                 ("filter", C.c_uint32), ("filter_slot", C.c_uint32), ("range_lo", C.c_uint64),
                 ("range_hi", C.c_uint64), ("sort_by", C.c_uint32), ("sort_slot", C.c_uint32),
                 ("sort_reverse", C.c_uint32), ("sort_use_max", C.c_uint32),
-                ("nfilter", C.c_uint32), ("nnot", C.c_uint32), ("nmaybe", C.c_uint32), ("reserved", C.c_uint32)]
+                ("nfilter", C.c_uint32), ("nnot", C.c_uint32), ("nmaybe", C.c_uint32), ("reserved", C.c_uint32),
+                ("factors", C.POINTER(C.c_double))]
 
 
 class MSetInfo(C.Structure):
@@ -188,6 +189,8 @@ class Query:
     filter_terms: Sequence[Union[str, bytes, int]] = ()
     not_terms: Sequence[Union[str, bytes, int]] = ()
     maybe_terms: Sequence[Union[str, bytes, int]] = ()
+    factors: Optional[Sequence[float]] = None     # OP_SCALE_WEIGHT factor per base term
+    bm25: Optional[tuple] = None                  # (k1, k3, b, min_normlen); None = BM25Weight defaults
 
 
 class QueryBatch:
@@ -217,6 +220,12 @@ class QueryBatch:
                 cq.wqf = w
                 self._keep.append(w)
             cq.first, cq.maxitems, cq.check_at_least = q.first, q.maxitems, q.check_at_least
+            if q.factors is not None:
+                fac = (C.c_double * len(q.factors))(*[float(x) for x in q.factors])
+                cq.factors = fac
+                self._keep.append(fac)
+            if q.bm25 is not None:
+                cq.k1, cq.k3, cq.b, cq.min_normlen = [float(x) for x in q.bm25]
             if q.stats is not None:
                 gtf = list(q.stats[2]) + [0] * (len(allterms) - len(q.stats[2]))
                 tf = (C.c_uint32 * len(gtf))(*gtf)
