@@ -1799,53 +1799,74 @@ __global__ void __launch_bounds__(TOPK_THREADS) xgm_topk_kernel(XgmKernelParams 
             for (uint32_t t = n + tid; t < P; t += TOPK_THREADS) { sd[t] = 0xffffffffu; sw[t] = 0.0; sk[t] = 0; }
             __syncthreads();
             bitonic_sort_candidates<true>(sw, sk, sd, P, tid);
-            /* thread t owns the four consecutive positions 4t..4t+3 (n <= 1024 = 4 * TOPK_THREADS): one pass
-             * over j serves four independent counters per load — the pair loops of a ~1000-match query are
-             * bound by the dependent-issue latency of its 8 warps, not by throughput */
-            const uint64_t* bw = reinterpret_cast<const uint64_t*>(sw);
-            const uint32_t i0 = 4 * tid;
-            if (i0 < n) {
-                uint64_t b[4];
-                uint32_t geb[4] = {0, 0, 0, 0}, gtb[4] = {0, 0, 0, 0}, gta[4] = {0, 0, 0, 0};
-#pragma unroll
-                for (int u = 0; u < 4; ++u) b[u] = i0 + u < n ? bw[i0 + u] : ~0ull;
-                for (uint32_t j = 0; j < i0; ++j) {
-                    const uint64_t bj = bw[j];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        geb[u] += bj >= b[u] ? 1u : 0u; /* ranks before: greater, or equal with a smaller docid */
-                        gtb[u] += bj > b[u] ? 1u : 0u;
+            /* Bottom-up merge sort by (weight desc, docid asc) of the docid-ordered survivors.  While run A
+             * (earlier docids) is merged with run B, every b in B learns how many a in A are strictly greater
+             * ("earlier and greater", ProtoMSet's min_weight test) and how many are not smaller; the merged
+             * position of an element is its index in its run plus one binary search in the other run.  After
+             * log2(P) passes the array is the ranked MSet.  O(n log^2 n) instead of the n^2 pair test.
+             * The per-element state travels in the aux word: aux (8 bits) | docid-order position (11) |
+             * greater-before (11) | not-less-before (11). */
+            for (uint32_t t = tid; t < P; t += TOPK_THREADS) sk[t] = (sk[t] & 0xffull) | ((uint64_t)t << 8);
+            __syncthreads();
+            double* w_src = sw; double* w_dst = sw + P;
+            uint64_t* k_src = sk; uint64_t* k_dst = sk + P;
+            uint32_t* d_src = sd; uint32_t* d_dst = sd + P;
+            for (uint32_t L = 1; L < P; L <<= 1) {
+                for (uint32_t t = tid; t < P; t += TOPK_THREADS) {
+                    const uint32_t base = t & ~(2u * L - 1u), off = t - base;
+                    const uint64_t bi = wbits(w_src[t]);
+                    uint64_t st8 = k_src[t];
+                    uint32_t pos;
+                    if (off < L) { /* element of run A: the b's strictly greater go first */
+                        const uint64_t* o = reinterpret_cast<const uint64_t*>(w_src) + base + L;
+                        uint32_t lo = 0, hi = L;
+                        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (o[mid] > bi) lo = mid + 1; else hi = mid; }
+                        pos = base + off + lo;
+                    } else {       /* element of run B: the a's that are not smaller go first */
+                        const uint64_t* o = reinterpret_cast<const uint64_t*>(w_src) + base;
+                        uint32_t lo = 0, hi = L;
+                        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (o[mid] > bi) lo = mid + 1; else hi = mid; }
+                        const uint32_t greater = lo;
+                        hi = L;
+                        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (o[mid] >= bi) lo = mid + 1; else hi = mid; }
+                        const uint32_t notless = lo;
+                        pos = base + (off - L) + notless;
+                        st8 += ((uint64_t)greater << 19) + ((uint64_t)notless << 30);
                     }
+                    w_dst[pos] = w_src[t];
+                    d_dst[pos] = d_src[t];
+                    k_dst[pos] = st8;
                 }
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    if (i0 + v < n) {
-                        const uint64_t bj = bw[i0 + v];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            if (v < u) { geb[u] += bj >= b[u] ? 1u : 0u; gtb[u] += bj > b[u] ? 1u : 0u; }
-                            else if (v > u) gta[u] += bj > b[u] ? 1u : 0u;
-                        }
-                    }
+                __syncthreads();
+                double* tw_ = w_src; w_src = w_dst; w_dst = tw_;
+                uint64_t* tk_ = k_src; k_src = k_dst; k_dst = tk_;
+                uint32_t* td_ = d_src; d_src = d_dst; d_dst = td_;
+            }
+            /* position at which ProtoMSet first raises min_weight: the heap build (k) when check_at_least <=
+             * k + 1, else the first replacement at or after check_at_least - 1 (protomset.h:377-398;
+             * tests/test_protomset_count_model.py) */
+            const uint32_t cal = q->check_at_least;
+            if (tid == 0) s_prefix[0] = cal <= topk + 1 ? topk : 0xffffffffu;
+            __syncthreads();
+            if (cal > topk + 1) {
+                const uint32_t from = cal - 1 > topk ? cal - 1 : topk;
+                for (uint32_t t = tid; t < n; t += TOPK_THREADS) {
+                    const uint64_t st8 = k_src[t];
+                    const uint32_t posd = (uint32_t)(st8 >> 8) & 0x7ffu, ge = (uint32_t)(st8 >> 30) & 0x7ffu;
+                    if (posd >= from && ge < topk) atomicMin(&s_prefix[0], posd);
                 }
-                for (uint32_t j = i0 + 4; j < n; ++j) {
-                    const uint64_t bj = bw[j];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) gta[u] += bj > b[u] ? 1u : 0u;
+                __syncthreads();
+            }
+            const uint32_t r_raise = s_prefix[0];
+            for (uint32_t t = tid; t < n; t += TOPK_THREADS) { /* real matches occupy the first n ranks */
+                const uint64_t st8 = k_src[t];
+                const uint32_t posd = (uint32_t)(st8 >> 8) & 0x7ffu, gt = (uint32_t)(st8 >> 19) & 0x7ffu;
+                if (t < topk) {
+                    p.out_w[ooff + t] = w_src[t];
+                    p.out_d[ooff + t] = d_src[t];
+                    p.out_k[ooff + t] = st8 & 0xffull;
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t i = i0 + u;
-                    if (i < n) {
-                        const uint32_t rank = geb[u] + gta[u];
-                        if (rank < topk) {
-                            p.out_w[ooff + rank] = sw[i];
-                            p.out_d[ooff + rank] = sd[i];
-                            p.out_k[ooff + rank] = sk[i];
-                        }
-                        if (i < free_count || gtb[u] < topk) ++known;
-                    }
-                }
+                if (posd <= r_raise || gt < topk) ++known;
             }
         } else {
             uint32_t P = 32;
