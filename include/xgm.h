@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define XGM_ABI_VERSION 1
+#define XGM_ABI_VERSION 2
 #define XGM_MAX_TERMS 16u      /* leaves per query handled on the device */
 #define XGM_MAX_TOPK 4096u     /* first + maxitems */
 
@@ -75,6 +75,18 @@ xgm_status xgm_builder_add_term(xgm_builder*, const char* term, uint32_t term_le
  * (src/serialise_list.h:301-356, src/sortable_serialise.cc). */
 xgm_status xgm_builder_add_value_slot(xgm_builder*, uint32_t slot, const uint64_t* voff /*[lastdocid+2]*/,
                                       const uint64_t* vals);
+/* The same slot in the form Xapiand stores it (Document::add_value of StringList::serialise over the sorted,
+ * unique serialised values, src/database/schema.cc:2958-2959, src/serialise_list.h:301-356): bytes of docid d
+ * are bytes[off[d] .. off[d+1]) — empty = no value, one value = its bytes, several = '\0' then
+ * (serialise_length(len), bytes)*.  Every element becomes its value key (xgm_value_key below); elements are
+ * kept in stored order.  A slot holding an element longer than 8 bytes is marked inexact and queries that
+ * filter or sort on it are declined (XGM_E_UNIMPLEMENTED). */
+xgm_status xgm_builder_add_value_slot_serialised(xgm_builder*, uint32_t slot, const uint64_t* off /*[lastdocid+2]*/,
+                                                 const unsigned char* bytes);
+/* Database::get_revision (src/xapian/database.h:600) of the snapshot the postings were read from; a query
+ * that names another revision gets XGM_E_STALE (→ Xapian::DatabaseModifiedError, the retry loop of
+ * src/database/handler.cc:1292-1316,1333-1335).  Default 0. */
+xgm_status xgm_builder_set_revision(xgm_builder*, uint64_t revision);
 /* Compress into the HBM block format and upload to `device`. Consumes the builder. */
 xgm_status xgm_builder_finish(xgm_builder*, int device, xgm_index** out);
 void xgm_builder_free(xgm_builder*);
@@ -119,6 +131,25 @@ xgm_status xgm_index_decode_term(const xgm_index*, uint32_t term_id, uint32_t* d
  * docids) — Database::get_doclength (api/database.cc:347), for tests and tools; not on the query path. */
 xgm_status xgm_index_copy_doclengths(const xgm_index*, uint32_t first_docid, uint32_t n, uint32_t* out);
 
+/* Number of documents with a value in `slot` (Database::get_value_freq). */
+xgm_status xgm_index_value_freq(const xgm_index*, uint32_t slot, uint32_t* out);
+
+/* ---- value keys ----------------------------------------------------------------------------
+ * Xapian compares slot values as byte strings (msetcmp.cc:75-85, valuerangepostlist.cc:132-151,
+ * src/multivalue/range.cc:351-368).  On the device a value is its first 8 bytes, big-endian, zero padded:
+ * order-preserving for every string, and one-to-one for strings of at most 8 bytes without trailing NULs —
+ * which covers Xapiand's sortable_serialise() of any number whose binary exponent is below 128 in magnitude
+ * (src/sortable_serialise.cc:41-212: 2 header bytes + up to 54 mantissa bits, trailing zero bytes chopped).
+ * xgm_value_key returns 1 when the key is exact (len <= 8, no trailing NUL), else 0. */
+int xgm_value_key(const void* bytes, size_t len, uint64_t* key);
+/* Inverse for exact keys: writes the value's bytes (<= 8), returns their number. */
+size_t xgm_value_key_bytes(uint64_t key, unsigned char out[8]);
+/* MSetIterator::get_sort_key for Xapiand's sorter: the bytes Multi_MultiValueKeyMaker::operator()
+ * (src/multivalue/keymaker.cc:704-757) builds for ONE SerialiseKey slot from the value with this key —
+ * forward: the value itself; reverse: every byte subtracted from 0xff ('\0' → "\xff\0"), then "\xff\xff".
+ * out needs 20 bytes; returns the length. */
+size_t xgm_sort_key_bytes(uint64_t key, int reverse, unsigned char out[20]);
+
 /* ---- queries ------------------------------------------------------------------------------ */
 enum { XGM_OP_AND = 0, XGM_OP_OR = 1 };                      /* Query::OP_AND / OP_OR of LEAF_TERMs */
 enum { XGM_SORT_REL = 0, XGM_SORT_VAL_REL = 1, XGM_SORT_VAL = 2, XGM_SORT_REL_VAL = 3 };
@@ -155,14 +186,27 @@ typedef struct xgm_query {
      *   nfilter  OP_FILTER(base, AND of boolean terms)   QueryFilter::postlist   api/queryinternal.cc:2270-2283
      *   nnot     OP_AND_NOT(…, OR of terms)              QueryAndNot::postlist   api/queryinternal.cc:2208-2225,
      *                                                     AndNotPostList matcher/andnotpostlist.cc
-     *   nmaybe   OP_AND_MAYBE(…, OR of weighted terms)   QueryAndMaybe::postlist api/queryinternal.cc:2247-2268
-     *            — declined for now (XGM_E_UNIMPLEMENTED: the shim lets the reference matcher run it)
-     * nterms + nfilter + nnot + nmaybe <= XGM_MAX_TERMS. */
+     *   nmaybe   OP_AND_MAYBE(…, OR of weighted terms)   QueryAndMaybe::postlist api/queryinternal.cc:2247-2268,
+     *                                                     AndMaybePostList matcher/andmaybepostlist.cc
+     * nterms + nfilter + nnot + nmaybe <= XGM_MAX_TERMS.  wqf (when given) covers all of them; the filter and
+     * excluded terms carry no weight, so theirs is ignored. */
     uint32_t nfilter, nnot, nmaybe, reserved;
     /* OP_SCALE_WEIGHT factor per base term (QueryScaleWeight::postlist api/queryinternal.cc:1075-1080: the
      * product of the factors above a leaf reaches Weight::init_); NULL → 1.0 each.  A factor of 0 makes the
      * leaf unweighted (AND bases only; under an OR it is declined). */
     const double* factors;
+    /* ---- ABI 2 ---- */
+    uint64_t revision;           /* 0 = any; else must equal the index's revision or the query gets XGM_E_STALE */
+    /* The value-range source on the WEIGHTED side: OP_AND(base, PostingSource) — what
+     * MultipleValueRange::getQuery + Xapiand's query DSL build (src/multivalue/range.cc:110-125): every match
+     * gets filter_factor * get_weight() = filter_factor * 1.0 (range.cc:410-414, externalpostlist.cc:86-95) at
+     * the source's place in the MultiAndPostList order, and max_possible includes filter_factor * DBL_MAX
+     * (api/postingsource.cc:208).  0 = the source only filters (OP_FILTER right side). */
+    uint32_t filter_weighted, reserved2;
+    double filter_factor;        /* used when filter_weighted; 0 is treated as 1.0 */
+    uint64_t sort_missing_key;   /* key of a document without a value in sort_slot: 0 for Enquire::set_sort_by_value*
+                                    (empty string), xgm_value_key("\xff") / ("\0") for Xapiand's SerialiseKey forward /
+                                    reverse (MAX_STR_CMPVALUE / MIN_STR_CMPVALUE, src/multivalue/keymaker.h:53-54) */
 } xgm_query;
 
 /* One query's result: the fields of MSet::Internal (src/xapian/api/msetinternal.h:58-99). */

@@ -20,8 +20,35 @@ if [ ! -d "$R/xapian" ]; then
   echo "build_ref: $R/xapian not present (GPU box?) — keeping prebuilt $O" >&2
   exit 0
 fi
+# ---- Xapiand's multivalue classes (src/multivalue), on top of the library above ------------------------
+# MultipleValueRange (range.cc:351-414), Multi_MultiValueKeyMaker (keymaker.cc:704-757), StringList
+# (serialise_list.h, header only) and Xapiand's own sortable_serialise(long double), compiled from the seven
+# source files where they lie (+ geospatial/cartesian.cc, whose constructor a header constant needs).  The query-DSL halves of those files (MultipleValueRange::getQuery, GeoKey)
+# call into Xapiand's schema / cast / datetime / geospatial code, which is NOT built: those are function
+# symbols only, left undefined in the shared object and bound lazily (-z lazy) — nothing on the matching
+# path calls them.  Pins SURVEY.md section 8 rows a15 / a16 against the reference's real code.
+build_mv() {
+  local MV="$O/libxapiand_mv_ref.so"
+  if [ -f "$MV" ] && [ "$MV" -nt "$HERE/ref_mv_glue.cc" ] && [ "${FORCE:-0}" != "1" ]; then return 0; fi
+  mkdir -p "$O/obj_mv"
+  local MVFLAGS="-std=c++17 -O2 -DNDEBUG -fPIC -w -include limits -include cstdint -include functional -I$O/gen -I$R -I$REF"
+  local objs=""
+  for f in multivalue/range.cc multivalue/keymaker.cc sortable_serialise.cc length.cc exception.cc fmt/format.cc geospatial/cartesian.cc; do
+    local o="$O/obj_mv/$(echo "$f" | tr '/' '_' | sed 's/\.cc$/.o/')"
+    objs="$objs $o"
+    ( if [ ! -f "$o" ] || [ "$R/$f" -nt "$o" ]; then g++ $MVFLAGS -c "$R/$f" -o "$o"; fi ) &
+  done
+  # our factory functions around those classes (oracle/ref_mv_glue.cc)
+  objs="$objs $O/obj_mv/ref_mv_glue.o"
+  g++ $MVFLAGS -c "$HERE/ref_mv_glue.cc" -o "$O/obj_mv/ref_mv_glue.o" &
+  wait
+  g++ -shared -o "$MV" $objs -L"$O" -lxapian_ref -Wl,-z,lazy -Wl,-rpath,'$ORIGIN'
+  echo "build_ref: built $MV"
+}
+
 if [ -f "$O/libxapian_ref.so" ] && [ "${FORCE:-0}" != "1" ]; then
   echo "build_ref: $O/libxapian_ref.so already built (FORCE=1 to rebuild)"
+  build_mv
   exit 0
 fi
 
@@ -66,3 +93,4 @@ done
 xargs -P "$JOBS" -L 1 bash -c 'if [ ! -f "$1" ] || [ "$0" -nt "$1" ]; then g++ '"$CXXFLAGS"' -c "$0" -o "$1" || exit 255; fi' < "$O/obj/.list"
 g++ -shared -o "$O/libxapian_ref.so" $(awk '{print $2}' "$O/obj/.list") -lz -lpthread
 echo "build_ref: built $O/libxapian_ref.so ($(wc -l < "$O/obj/.list") objects)"
+build_mv

@@ -5,10 +5,13 @@
  * its public API.  It is the oracle the CUDA path is checked against and the CPU baseline arm of
  * bench.py.  The product never links or executes this.
  *
- *   ref_runner build  --out DIR --docs N --vocab V --seed S [--nshards n --shard s] [--values]
+ *   ref_runner build  --out DIR --docs N --vocab V --seed S [--nshards n --shard s] [--values | --mvalues]
  *                     [--termlist] [--range-first a --range-last b]
  *                                                       write a glass DB through WritableDatabase
  *                                                       (--range-*: only global docids a..b, as local 1..)
+ *                                                       --mvalues: value slots the way Xapiand writes them —
+ *                                                       slot 0 a StringList (src/serialise_list.h:301-356) of 1..3
+ *                                                       Serialise::positive() keys, slot 1 one such key
  *   ref_runner compact --db DIR [--db DIR ...] --out DIR   Database::compact (renumbering by offset, so
  *                                                       contiguous docid-range parts give back the corpus)
  *   ref_runner query  --db DIR [--db DIR ...] [--twophase] --queries FILE [--threads T]
@@ -23,6 +26,15 @@
  */
 #include <xapian.h>
 
+/* Xapiand's own multivalue classes live in oracle/_ref/libxapiand_mv_ref.so (oracle/build_ref.sh); the factory
+ * functions are oracle/ref_mv_glue.cc */
+namespace xgmref {
+std::string serialise_number(long double v);
+std::string serialise_slot(const std::vector<std::string>& sorted_unique_values);
+Xapian::PostingSource* make_multiple_value_range(unsigned slot, const std::string& start, const std::string& end);
+Xapian::KeyMaker* make_key_maker(const std::vector<std::pair<unsigned, bool>>& slots);
+}
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -30,7 +42,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <fstream>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -77,6 +91,7 @@ static int cmd_build(const Args& a) {
     uint32_t nshards = (uint32_t)strtoul(a.get("--nshards", "1").c_str(), nullptr, 10);
     uint32_t shard = (uint32_t)strtoul(a.get("--shard", "0").c_str(), nullptr, 10);
     bool values = a.flag("--values");
+    bool mvalues = a.flag("--mvalues");
     uint32_t rfirst = (uint32_t)strtoul(a.get("--range-first", "1").c_str(), nullptr, 10);
     uint32_t rlast = (uint32_t)strtoul(a.get("--range-last", "0").c_str(), nullptr, 10);
     if (rlast == 0 || rlast > N) rlast = N;
@@ -109,6 +124,17 @@ static int cmd_build(const Args& a) {
             doc.add_value(0, Xapian::sortable_serialise((double)v0[0]));
             doc.add_value(1, Xapian::sortable_serialise((double)v1));
             doc.add_value(2, Xapian::sortable_serialise((double)v0[n0 - 1]));
+        }
+        if (mvalues) {
+            uint64_t v0[3], v1;
+            uint32_t n0 = xgm_corpus_values(seed, d, v0, &v1);
+            std::vector<std::string> ser;
+            for (uint32_t i = 0; i < n0; ++i) ser.push_back(xgmref::serialise_number((long double)v0[i]));
+            /* Xapiand keeps the values of a slot in a std::set of serialised strings and writes
+             * StringList::serialise of it (src/database/schema.cc:2958-2959, 5346): sorted, unique */
+            ser.erase(std::unique(ser.begin(), ser.end()), ser.end());
+            doc.add_value(0, xgmref::serialise_slot(ser));
+            doc.add_value(1, xgmref::serialise_number((long double)v1));
         }
         Xapian::docid got = db.add_document(doc).did;
         if (got != ++local) die("unexpected docid");
@@ -146,6 +172,14 @@ struct QSpec {
     bool has_sort = false;    /* SORT slot reverse → set_sort_by_value_then_relevance */
     uint32_t s_slot = 0; bool s_rev = false;
     int s_mode = 0;           /* 0 value then relevance, 1 value only, 2 relevance then value */
+    /* MVR slot lo hi  → OP_FILTER(q, MultipleValueRange(slot, ser(lo), ser(hi)))   (unweighted right side)
+     * MVRW slot lo hi → OP_AND(q, MultipleValueRange(...))  — the source on the weighted side, the shape
+     *                   MultipleValueRange::getQuery + query_dsl produce (src/multivalue/range.cc:110-125)
+     * KEYSORT slot reverse → Enquire::set_sort_by_key_then_relevance(Multi_MultiValueKeyMaker{SerialiseKey}, false)
+     *                   exactly as DocMatcher does (src/database/handler.cc:1269-1271) */
+    int mvr = 0;              /* 0 none, 1 filter, 2 weighted */
+    uint32_t mvr_slot = 0; double mvr_lo = 0, mvr_hi = 0;
+    bool has_keysort = false; uint32_t ks_slot = 0; bool ks_rev = false;
     bool has_params = false;  /* BM25 k1 k3 b min_normlen → set_weighting_scheme(BM25Weight(k1, 0, k3, b, min_normlen)) */
     double k1 = 1, k3 = 1, b = 0.5, mnl = 0.5;
 };
@@ -167,6 +201,8 @@ static std::vector<QSpec> load_queries(const std::string& path) {
             if (tok == "VR") { q.has_range = true; is >> q.r_slot >> q.r_lo >> q.r_hi; }
             else if (tok == "SORT") { q.has_sort = true; int r; is >> q.s_slot >> r; q.s_rev = r != 0; }
             else if (tok == "SORTMODE") { is >> q.s_mode; }
+            else if (tok == "MVR" || tok == "MVRW") { q.mvr = tok == "MVR" ? 1 : 2; is >> q.mvr_slot >> q.mvr_lo >> q.mvr_hi; }
+            else if (tok == "KEYSORT") { q.has_keysort = true; int r; is >> q.ks_slot >> r; q.ks_rev = r != 0; }
             else if (tok == "BM25") { q.has_params = true; is >> q.k1 >> q.k3 >> q.b >> q.mnl; }
             else if (tok == "FT" || tok == "NOT" || tok == "MAYBE") {
                 uint32_t m; is >> m;
@@ -209,6 +245,12 @@ static Xapian::Query make_query(const QSpec& q) {
                         Xapian::sortable_serialise(q.r_lo), Xapian::sortable_serialise(q.r_hi));
         base = Xapian::Query(Xapian::Query::OP_FILTER, base, r);
     }
+    if (q.mvr) {
+        Xapian::PostingSource* src = xgmref::make_multiple_value_range(
+            q.mvr_slot, xgmref::serialise_number((long double)q.mvr_lo), xgmref::serialise_number((long double)q.mvr_hi));
+        Xapian::Query r(src->release());
+        base = Xapian::Query(q.mvr == 1 ? Xapian::Query::OP_FILTER : Xapian::Query::OP_AND, base, r);
+    }
     auto group = [](Xapian::Query::op op, const std::vector<std::string>& ts) {
         return ts.size() == 1 ? Xapian::Query(ts[0]) : Xapian::Query(op, ts.begin(), ts.end());
     };
@@ -232,6 +274,11 @@ struct QResult {
 
 static void setup_enquire(Xapian::Enquire& enq, const QSpec& q) {
     enq.set_query(make_query(q));
+    if (q.has_keysort) {
+        if (q.has_params) enq.set_weighting_scheme(Xapian::BM25Weight(q.k1, 0.0, q.k3, q.b, q.mnl));
+        enq.set_sort_by_key_then_relevance(xgmref::make_key_maker({{q.ks_slot, q.ks_rev}})->release(), false);
+        return;
+    }
     if (q.has_params) enq.set_weighting_scheme(Xapian::BM25Weight(q.k1, 0.0, q.k3, q.b, q.mnl));
     if (q.has_sort && q.s_mode == 1) enq.set_sort_by_value(q.s_slot, q.s_rev);
     else if (q.has_sort && q.s_mode == 2) enq.set_sort_by_relevance_then_value(q.s_slot, q.s_rev);
@@ -264,30 +311,47 @@ static int cmd_query(const Args& a) {
     std::string dump = a.get("--dump", "");
     std::vector<QResult> res(qs.size());
 
-    auto run_pass = [&](bool timed) {
-        std::vector<std::thread> th;
-        for (int t = 0; t < T; ++t) {
-            th.emplace_back([&, t]() {
-                try {
-                    if (!twophase) {
-                        Xapian::Database db;
-                        for (auto& p : dbs) db.add_database(Xapian::Database(p));
-                        Xapian::Enquire enq(db);
-                        for (size_t i = t; i < qs.size(); i += T) {
-                            setup_enquire(enq, qs[i]);
+    /* One worker per thread for the whole run: each opens its own Xapian::Database (+ Enquire) ONCE, outside
+     * every timed wall, then takes part in the passes (warm-up and timed) released by the main thread.  A
+     * pass's wall clock therefore covers Enquire::set_query + get_mset (+ MSet read-out) only — not thread
+     * creation or the B-tree opens. */
+    struct Gate {
+        std::mutex mu; std::condition_variable cv;
+        int pass = 0, done = 0, ready = 0; bool timed = false, quit = false;
+    } gate;
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t) {
+        th.emplace_back([&, t]() {
+            try {
+                Xapian::Database db;
+                std::vector<Xapian::Database> sh;
+                if (!twophase) { for (auto& p : dbs) db.add_database(Xapian::Database(p)); }
+                else { for (auto& p : dbs) sh.emplace_back(p); }
+                Xapian::Enquire enq(twophase ? Xapian::Database() : db);
+                size_t n = sh.size();
+                int seen = 0;
+                { std::lock_guard<std::mutex> lk(gate.mu); ++gate.ready; }
+                gate.cv.notify_all();
+                for (;;) {
+                    bool timed;
+                    {
+                        std::unique_lock<std::mutex> lk(gate.mu);
+                        gate.cv.wait(lk, [&] { return gate.quit || gate.pass != seen; });
+                        if (gate.quit) return;
+                        seen = gate.pass;
+                        timed = gate.timed;
+                    }
+                    for (size_t i = t; i < qs.size(); i += T) {
+                        const QSpec& q = qs[i];
+                        if (!twophase) {
+                            setup_enquire(enq, q);
                             double t0 = now_s();
-                            Xapian::MSet m = enq.get_mset(qs[i].first, qs[i].maxitems, qs[i].check_at_least);
+                            Xapian::MSet m = enq.get_mset(q.first, q.maxitems, q.check_at_least);
                             double dt = now_s() - t0;
                             if (timed) res[i].seconds = dt;
-                            collect(m, res[i], qs[i].has_sort);
-                        }
-                    } else {
-                        /* Xapiand's DocMatcher scheme, src/database/handler.cc:1485-1551 */
-                        std::vector<Xapian::Database> sh;
-                        for (auto& p : dbs) sh.emplace_back(p);
-                        size_t n = sh.size();
-                        for (size_t i = t; i < qs.size(); i += T) {
-                            const QSpec& q = qs[i];
+                            collect(m, res[i], q.has_sort || q.has_keysort);
+                        } else {
+                            /* Xapiand's DocMatcher scheme, src/database/handler.cc:1485-1551 */
                             double t0 = now_s();
                             Xapian::Enquire merger{Xapian::Database()};
                             std::vector<Xapian::Enquire> enqs;
@@ -309,15 +373,29 @@ static int cmd_query(const Args& a) {
                             Xapian::MSet m = merger.merge_mset(msets, doccount, q.first, q.maxitems);
                             double dt = now_s() - t0;
                             if (timed) res[i].seconds = dt;
-                            collect(m, res[i], q.has_sort);
+                            collect(m, res[i], q.has_sort || q.has_keysort);
                         }
                     }
-                } catch (const Xapian::Error& e) {
-                    die("xapian: " + e.get_description());
+                    { std::lock_guard<std::mutex> lk(gate.mu); ++gate.done; }
+                    gate.cv.notify_all();
                 }
-            });
+            } catch (const Xapian::Error& e) {
+                die("xapian: " + e.get_description());
+            }
+        });
+    }
+    {
+        std::unique_lock<std::mutex> lk(gate.mu);
+        gate.cv.wait(lk, [&] { return gate.ready == T; });
+    }
+    auto run_pass = [&](bool timed) {
+        {
+            std::lock_guard<std::mutex> lk(gate.mu);
+            gate.timed = timed; gate.done = 0; ++gate.pass;
         }
-        for (auto& x : th) x.join();
+        gate.cv.notify_all();
+        std::unique_lock<std::mutex> lk(gate.mu);
+        gate.cv.wait(lk, [&] { return gate.done == T; });
     };
 
     for (int w = 0; w < warm; ++w) run_pass(false);
@@ -331,6 +409,12 @@ static int cmd_query(const Args& a) {
         best_wall = std::min(best_wall, w);
         for (auto& x : res) lat.push_back(x.seconds);
     }
+    {
+        std::lock_guard<std::mutex> lk(gate.mu);
+        gate.quit = true;
+    }
+    gate.cv.notify_all();
+    for (auto& x : th) x.join();
     std::sort(lat.begin(), lat.end());
     auto pct = [&](double p) { return lat.empty() ? 0.0 : lat[std::min(lat.size() - 1, (size_t)(p * lat.size()))]; };
     if (!dump.empty()) {

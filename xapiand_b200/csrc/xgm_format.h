@@ -40,6 +40,7 @@ struct XgmBlockHdr {
 #define XGM_HDR_COUNT(m) ((((m) >> 16) & 0xffu) + 1u)
 
 #define XGM_NO_BITMAP 0xFFFFFFFFFFFFFFFFull
+#define XGM_NO_SRC 0xFFFFFFFFu
 
 struct XgmDevTerm {
     uint32_t blk_begin;   /* index of the term's first header in hdr[] */
@@ -64,6 +65,12 @@ struct XgmDevQuery {
     uint32_t nmaybe;                    /* AND: terms[nterms+nnot ..) are the optional leaves of an OP_AND_MAYBE; prog[] is
                                            the OrPostList tree over them */
     double bucket_scale;                /* XGM_NBINS / max_possible (or / (max sort key + 1)) */
+    uint64_t sort_missing;              /* sort key of a document without a value in sort_slot */
+    uint64_t bucket_key_min;            /* value sorts: smallest key of the slot (bucket = (key - min) * scale) */
+    double src_weight;                  /* weighted value-range source: factor * 1.0 added to every match ... */
+    uint32_t src_pos;                   /* ... before the weight of required list src_pos (MultiAndPostList order);
+                                           nterms = after all; XGM_NO_SRC = the source only filters */
+    uint32_t pad1;
     XgmDevTerm terms[XGM_DEV_MAX_TERMS]; /* AND: ascending termfreq (MultiAndPostList order) */
 };
 

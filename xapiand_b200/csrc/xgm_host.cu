@@ -91,6 +91,7 @@ struct TermInfo {
 
 struct HostSlot {
     bool present = false;
+    bool exact = true; /* every value is represented one-to-one by its 8-byte key */
     std::vector<uint32_t> voff;
     std::vector<uint64_t> vals;
 };
@@ -103,7 +104,7 @@ struct xgm_index {
     uint64_t npostings = 0, nblocks = 0;
     uint64_t bytes_docs = 0, bytes_tfs = 0, bytes_hdr = 0, bytes_doclen = 0, bytes_bitmaps = 0;
     uint32_t nbitmaps = 0;
-    uint64_t revision = 1;
+    uint64_t revision = 0;
     std::vector<TermInfo> terms;
     std::unordered_map<std::string, uint32_t> dict;
     bool synthetic_names = false; /* "T%06u" names resolved arithmetically, no dictionary */
@@ -117,6 +118,9 @@ struct xgm_index {
     uint32_t* d_voff[XGM_MAX_SLOTS] = {};
     uint64_t* d_vals[XGM_MAX_SLOTS] = {};
     uint64_t slot_max[XGM_MAX_SLOTS] = {};
+    uint64_t slot_min[XGM_MAX_SLOTS] = {};
+    uint32_t slot_freq[XGM_MAX_SLOTS] = {}; /* documents with a value in the slot (Database::get_value_freq) */
+    bool slot_exact[XGM_MAX_SLOTS] = {};
     int sm_count = 148;
     /* Large batches fill the GPU on their own: the kernels of all searchers of this index go through one
      * FIFO compute stream (copies stay on the searchers' streams), so that batch k's results are not
@@ -236,6 +240,7 @@ struct xgm_builder {
     Chunk chunk; /* sequential builder: one chunk */
     HostSlot slots[XGM_MAX_SLOTS];
     bool have_docs = false;
+    uint64_t revision = 0;
 };
 
 static xgm_status upload_index(xgm_index* ix, std::vector<Chunk>& chunks, const std::vector<size_t>& chunk_first_term,
@@ -309,7 +314,10 @@ static xgm_status upload_index(xgm_index* ix, std::vector<Chunk>& chunks, const 
         CUDA_TRY(cudaMalloc(&ix->d_vals[s], std::max<size_t>(1, slots[s].vals.size()) * 8));
         if (!slots[s].vals.empty())
             CUDA_TRY(cudaMemcpy(ix->d_vals[s], slots[s].vals.data(), slots[s].vals.size() * 8, cudaMemcpyHostToDevice));
-        for (uint64_t v : slots[s].vals) ix->slot_max[s] = std::max(ix->slot_max[s], v);
+        ix->slot_min[s] = slots[s].vals.empty() ? 0 : ~0ull;
+        for (uint64_t v : slots[s].vals) { ix->slot_max[s] = std::max(ix->slot_max[s], v); ix->slot_min[s] = std::min(ix->slot_min[s], v); }
+        for (size_t d = 0; d + 1 < slots[s].voff.size(); ++d) ix->slot_freq[s] += slots[s].voff[d + 1] > slots[s].voff[d];
+        ix->slot_exact[s] = slots[s].exact;
     }
     ix->nblocks = 0;
     ix->npostings = 0;
@@ -345,6 +353,8 @@ extern "C" xgm_status xgm_builder_add_term(xgm_builder* b, const char* term, uin
                                            const uint32_t* wdfs, uint32_t n, uint64_t collfreq, uint32_t wdf_ub,
                                            uint32_t* term_id) {
     if (!b || !term || (n && (!docids || !wdfs))) return fail(XGM_E_INVALID, "null argument");
+    if (!b->have_docs) return fail(XGM_E_INVALID, "call xgm_builder_set_docs before xgm_builder_add_term");
+    if (n && docids[n - 1] > b->lastdocid) return fail(XGM_E_INVALID, "docid %u of term beyond lastdocid %u", docids[n - 1], b->lastdocid);
     for (uint32_t i = 0; i < n; ++i) {
         if (docids[i] == 0 || docids[i] == XGM_SENTINEL || (i && docids[i] <= docids[i - 1]))
             return fail(XGM_E_INVALID, "docids of term must be strictly ascending and in [1, 2^32-2]");
@@ -370,8 +380,108 @@ extern "C" xgm_status xgm_builder_add_value_slot(xgm_builder* b, uint32_t slot, 
     size_t n = (size_t)b->lastdocid + 2;
     if (voff[n - 1] >= 0xffffffffull) return fail(XGM_E_INVALID, "too many values");
     s.voff.resize(n);
-    for (size_t i = 0; i < n; ++i) s.voff[i] = (uint32_t)voff[i];
+    for (size_t i = 0; i < n; ++i) {
+        if (i && voff[i] < voff[i - 1]) return fail(XGM_E_INVALID, "value offsets must not decrease");
+        s.voff[i] = (uint32_t)voff[i];
+    }
     s.vals.assign(vals, vals + voff[n - 1]);
+    s.present = true;
+    return XGM_OK;
+}
+
+extern "C" xgm_status xgm_builder_set_revision(xgm_builder* b, uint64_t revision) {
+    if (!b) return fail(XGM_E_INVALID, "null argument");
+    b->revision = revision;
+    return XGM_OK;
+}
+
+/* ---- value keys: a slot value is its first 8 bytes, big-endian, zero padded (xgm.h) ---- */
+extern "C" int xgm_value_key(const void* bytes, size_t len, uint64_t* key) {
+    const unsigned char* p = static_cast<const unsigned char*>(bytes);
+    uint64_t k = 0;
+    for (size_t i = 0; i < 8; ++i) k = (k << 8) | (i < len ? p[i] : 0u);
+    if (key) *key = k;
+    return len <= 8 && (len == 0 || p[len - 1] != 0) ? 1 : 0;
+}
+
+extern "C" size_t xgm_value_key_bytes(uint64_t key, unsigned char out[8]) {
+    size_t n = 8;
+    while (n > 0 && ((key >> (8 * (8 - n))) & 0xffu) == 0) --n;
+    for (size_t i = 0; i < n; ++i) out[i] = (unsigned char)(key >> (8 * (7 - i)));
+    return n;
+}
+
+/* Multi_MultiValueKeyMaker::operator() (src/multivalue/keymaker.cc:704-757) for one SerialiseKey slot: the
+ * slot is the last one, so a forward value is appended as it is (:727-731); a reverse one is subtracted
+ * bytewise from 0xff, '\0' becoming "\xff\0", and followed by "\xff\xff" (:733-743). */
+extern "C" size_t xgm_sort_key_bytes(uint64_t key, int reverse, unsigned char out[20]) {
+    unsigned char v[8];
+    const size_t n = xgm_value_key_bytes(key, v);
+    size_t o = 0;
+    if (!reverse) {
+        for (size_t i = 0; i < n; ++i) out[o++] = v[i];
+        return o;
+    }
+    for (size_t i = 0; i < n; ++i) {
+        out[o++] = (unsigned char)(255 - v[i]);
+        if (v[i] == 0) out[o++] = 0;
+    }
+    out[o++] = 0xff; out[o++] = 0xff;
+    return o;
+}
+
+/* unserialise_length, src/length.cc:62-85 (the StringList element length prefix) */
+static bool read_length(const unsigned char*& p, const unsigned char* end, uint64_t& len) {
+    if (p == end) return false;
+    len = *p++;
+    if (len == 0xff) {
+        len = 0;
+        unsigned shift = 0;
+        unsigned char ch;
+        do {
+            if (p == end || shift > 63) return false;
+            ch = *p++;
+            len |= (uint64_t)(ch & 0x7f) << shift;
+            shift += 7;
+        } while ((ch & 0x80) == 0);
+        len += 255;
+    }
+    return true;
+}
+
+extern "C" xgm_status xgm_builder_add_value_slot_serialised(xgm_builder* b, uint32_t slot, const uint64_t* off,
+                                                            const unsigned char* bytes) {
+    if (!b || !off || slot >= XGM_MAX_SLOTS) return fail(XGM_E_INVALID, "bad slot");
+    if (!b->have_docs) return fail(XGM_E_INVALID, "call xgm_builder_set_docs first");
+    HostSlot& s = b->slots[slot];
+    const size_t n = (size_t)b->lastdocid + 2;
+    s.voff.assign(n, 0);
+    s.vals.clear();
+    s.exact = true;
+    for (size_t d = 0; d + 1 < n; ++d) {
+        s.voff[d] = (uint32_t)s.vals.size();
+        if (off[d + 1] < off[d]) return fail(XGM_E_INVALID, "value offsets must not decrease");
+        const unsigned char* p = bytes + off[d];
+        const unsigned char* end = bytes + off[d + 1];
+        if (p == end) continue;
+        uint64_t key;
+        if (*p != 0) { /* a single value is stored as it is (StringList::serialise, serialise_list.h:318-322) */
+            if (!xgm_value_key(p, (size_t)(end - p), &key)) s.exact = false;
+            s.vals.push_back(key);
+            continue;
+        }
+        ++p; /* SERIALISED_LIST_MAGIC */
+        while (p != end) {
+            uint64_t len;
+            if (!read_length(p, end, len) || len > (uint64_t)(end - p))
+                return fail(XGM_E_INVALID, "slot %u, docid %zu: bad StringList encoding", slot, d);
+            if (!xgm_value_key(p, (size_t)len, &key)) s.exact = false;
+            s.vals.push_back(key);
+            p += len;
+        }
+        if (s.vals.size() >= 0xffffffffull) return fail(XGM_E_INVALID, "too many values");
+    }
+    s.voff[n - 1] = (uint32_t)s.vals.size();
     s.present = true;
     return XGM_OK;
 }
@@ -382,6 +492,7 @@ extern "C" xgm_status xgm_builder_finish(xgm_builder* b, int device, xgm_index**
     std::unique_ptr<xgm_index> ix(new xgm_index());
     ix->doccount = b->doccount; ix->lastdocid = b->lastdocid; ix->total_length = b->total_length;
     ix->doclen_lb = b->doclen_lb; ix->doclen_ub = b->doclen_ub;
+    ix->revision = b->revision;
     ix->terms = b->terms;
     for (size_t t = 0; t < ix->terms.size(); ++t) {
         if (!b->ub_given[t])
@@ -603,6 +714,12 @@ trunc:
     return fail(XGM_E_IO, "%s: truncated", path);
 }
 
+extern "C" xgm_status xgm_index_value_freq(const xgm_index* ix, uint32_t slot, uint32_t* out) {
+    if (!ix || !out || slot >= XGM_MAX_SLOTS) return fail(XGM_E_INVALID, "bad arguments");
+    *out = ix->slot_freq[slot];
+    return XGM_OK;
+}
+
 extern "C" xgm_status xgm_index_info_get(const xgm_index* ix, xgm_index_info* o) {
     if (!ix || !o) return fail(XGM_E_INVALID, "null argument");
     memset(o, 0, sizeof(*o));
@@ -690,6 +807,8 @@ struct PlannedQuery {
     uint64_t alg_bytes = 0;
     uint32_t sort_by = 0;
     uint32_t filter = 0;
+    double bucket_max = 0;   /* finite bound of the weights, for the pruning buckets (max_possible is DBL_MAX with a weighted source) */
+    bool mv_source = false;  /* a Xapiand range source is a child of the AND: its termfreq estimates are restated */
     bool count_only = false; /* first >= every possible match count: the MSet is empty, only counts matter */
     bool aux_subqs = false;  /* the number of matching weighted leaves varies per document (OR, AND_MAYBE) */
 };
@@ -857,6 +976,7 @@ static xgm_status ensure_expanded(xgm_searcher* s, size_t need, int which) {
 extern "C" xgm_status xgm_searcher_new(const xgm_index* ix, uint32_t max_batch, uint32_t max_topk, xgm_searcher** out) {
     if (!ix || !out || max_batch == 0 || max_topk == 0) return fail(XGM_E_INVALID, "bad arguments");
     if (max_topk > XGM_MAX_TOPK) return fail(XGM_E_INVALID, "max_topk %u > %u", max_topk, XGM_MAX_TOPK);
+    if (max_batch >= (1u << 25)) return fail(XGM_E_INVALID, "max_batch %u too large", max_batch);
     CUDA_TRY(cudaSetDevice(ix->device));
     std::unique_ptr<xgm_searcher, void (*)(xgm_searcher*)> s(new xgm_searcher(), xgm_searcher_free);
     s->ix = ix; s->max_batch = max_batch; s->max_topk = max_topk;
@@ -1052,6 +1172,19 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
     }
     if (q.sort_by > XGM_SORT_REL_VAL || q.filter > XGM_FILTER_MULTI_RANGE) { pq.status = XGM_E_INVALID; return XGM_OK; }
     if ((q.filter && q.filter_slot >= XGM_MAX_SLOTS) || (q.sort_by && q.sort_slot >= XGM_MAX_SLOTS)) { pq.status = XGM_E_INVALID; return XGM_OK; }
+    if (q.revision != 0 && q.revision != ix->revision) { pq.status = XGM_E_STALE; return XGM_OK; }
+    if ((q.filter && !ix->slot_exact[q.filter_slot] && ix->d_voff[q.filter_slot]) ||
+        (q.sort_by && !ix->slot_exact[q.sort_slot] && ix->d_voff[q.sort_slot])) {
+        pq.status = XGM_E_UNIMPLEMENTED; /* values longer than 8 bytes: their keys do not decide the comparison */
+        return XGM_OK;
+    }
+    /* the source of a Xapiand range (MultipleValueRange) takes part in the MultiAndPostList like a term with
+     * termfreq (min, est, max) = (0, value_freq, value_freq) (range.cc:457-464, api/postingsource.cc:201-214) */
+    const bool mv_source = q.filter == XGM_FILTER_MULTI_RANGE;
+    const bool src_weighted = mv_source && q.filter_weighted;
+    if (q.filter_weighted && (!mv_source || (q.op != XGM_OP_AND && q.nterms != 1) || ngroups || s->and_version != 1)) { pq.status = XGM_E_UNIMPLEMENTED; return XGM_OK; }
+    const double src_w = src_weighted ? (q.filter_factor != 0.0 ? q.filter_factor : 1.0) * 1.0 : 0.0;
+    if (src_w < 0.0) { pq.status = XGM_E_UNIMPLEMENTED; return XGM_OK; }
     const uint32_t n = q.nterms;
     const uint32_t nall = n + ngroups; /* base terms, then filter terms, then excluded terms */
     uint32_t ids[XGM_MAX_TERMS];
@@ -1101,38 +1234,61 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
     }
     dq.op = q.op; dq.nterms = n + nfilter; dq.nweighted = q.op == XGM_OP_OR && n > 1 ? n : nweighted_base;
     dq.topk = pq.topk; dq.check_at_least = cal;
-    pq.nterms = nweighted_base; /* total weighted leaves, for the percentage scale */
+    pq.nterms = nweighted_base + (src_weighted ? 1u : 0u); /* total weighted subqueries, for the percentage scale */
     dq.len_factor = len_factor; dq.k1 = k1; dq.b = b; dq.one_minus_b = 1 - b; dq.min_normlen = mnl;
     dq.filter = q.filter; dq.filter_slot = q.filter_slot; dq.range_lo = q.range_lo; dq.range_hi = q.range_hi;
     dq.sort_by = q.sort_by; dq.sort_slot = q.sort_slot; dq.sort_reverse = q.sort_reverse; dq.sort_use_max = q.sort_use_max;
+    dq.sort_missing = q.sort_missing_key;
+    dq.src_pos = XGM_NO_SRC; dq.src_weight = 0.0;
     double dbsize = ix->doccount;
     uint32_t order[XGM_MAX_TERMS];
     bool any_absent = false;
     for (uint32_t j = 0; j < n; ++j) any_absent |= (ltf[j] == 0);
     if (q.op == XGM_OP_AND || n == 1) {
-        TfIdx in[XGM_MAX_TERMS], outv[XGM_MAX_TERMS];
+        /* children of the MultiAndPostList: the base terms and, for a Xapiand range, its source — sorted by
+         * get_termfreq_est with the very call of multiandpostlist.h:126-131 */
+        const uint32_t nch = n + (mv_source ? 1u : 0u);
+        const uint32_t src_vf = mv_source ? ix->slot_freq[q.filter_slot] : 0u;
+        TfIdx in[XGM_MAX_TERMS + 1], outv[XGM_MAX_TERMS + 1];
         for (uint32_t j = 0; j < n; ++j) { in[j].tf = ltf[j]; in[j].idx = j; }
-        std::partial_sort_copy(in, in + n, outv, outv + n, [](const TfIdx& a, const TfIdx& c) { return a.tf < c.tf; });
-        for (uint32_t j = 0; j < n; ++j) order[j] = outv[j].idx;
-        /* MultiAndPostList::recalc_maxweight / get_termfreq_{min,max,est}, multiandpostlist.cc:55-105,161-171 */
-        double mp = 0;
-        for (uint32_t i = 0; i < n; ++i) mp += maxpart[order[i]];
-        pq.max_possible = n == 1 ? maxpart[0] : mp;
-        uint32_t sum = ltf[order[0]];
+        if (mv_source) { in[n].tf = src_vf; in[n].idx = n; }
+        std::partial_sort_copy(in, in + nch, outv, outv + nch, [](const TfIdx& a, const TfIdx& c) { return a.tf < c.tf; });
+        uint32_t src_pos = XGM_NO_SRC;
+        {
+            uint32_t k = 0;
+            for (uint32_t j = 0; j < nch; ++j) {
+                if (outv[j].idx == n && mv_source) src_pos = k;
+                else order[k++] = outv[j].idx;
+            }
+        }
+        /* MultiAndPostList::recalc_maxweight / get_termfreq_{min,max,est}, multiandpostlist.cc:55-105,161-171,
+         * over the children in that order (child = base term order[i], or the source at src_pos) */
+        auto ch_min = [&](uint32_t c) { return outv[c].idx == n && mv_source ? 0u : ltf[outv[c].idx]; };
+        auto ch_max = [&](uint32_t c) { return outv[c].idx == n && mv_source ? src_vf : ltf[outv[c].idx]; };
+        double mp = 0, mp_real = 0;
+        for (uint32_t c = 0; c < nch; ++c) {
+            if (outv[c].idx == n && mv_source) { mp += src_weighted ? src_w * 1.7976931348623157e308 : 0.0; mp_real += src_w; }
+            else { mp += maxpart[outv[c].idx]; mp_real += maxpart[outv[c].idx]; }
+        }
+        pq.max_possible = nch == 1 ? maxpart[0] : mp;
+        pq.bucket_max = nch == 1 ? maxpart[0] : mp_real;
+        uint32_t sum = ch_min(0);
         if (sum) {
-            for (uint32_t i = 1; i < n; ++i) {
+            for (uint32_t i = 1; i < nch; ++i) {
                 uint32_t old = sum;
-                sum += ltf[order[i]];
+                sum += ch_min(i);
                 if (sum >= old && sum <= ix->doccount) { sum = 0; break; }
                 sum -= ix->doccount;
             }
         }
         pq.tf_min = sum;
-        pq.tf_max = ltf[order[0]];
-        for (uint32_t i = 1; i < n; ++i) pq.tf_max = std::min(pq.tf_max, ltf[order[i]]);
-        double r = ltf[order[0]];
-        for (uint32_t i = 1; i < n; ++i) r = (r * ltf[order[i]]) / dbsize;
+        pq.tf_max = ch_max(0);
+        for (uint32_t i = 1; i < nch; ++i) pq.tf_max = std::min(pq.tf_max, ch_max(i));
+        double r = ch_max(0);
+        for (uint32_t i = 1; i < nch; ++i) r = (r * ch_max(i)) / dbsize;
         pq.tf_est = ix->doccount ? (uint32_t)(r + 0.5) : 0;
+        if (src_weighted) { dq.src_pos = src_pos; dq.src_weight = src_w; }
+        pq.mv_source = mv_source;
         dq.route = 0;
         auto put_term = [&](uint32_t slot, uint32_t j, bool weighted) {
             dq.terms[slot].termweight = weighted ? tw[j] : 0.0; /* a boolean leaf contributes +0.0: sums unchanged */
@@ -1222,7 +1378,7 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
                 double mtw[XGM_MAX_TERMS], mmax[XGM_MAX_TERMS];
                 for (uint32_t j = 0; j < nmaybe; ++j) {
                     const uint32_t gtf = q.stats ? q.stats->termfreq[mb + j] : ltf[mb + j];
-                    mtw[j] = bm25_termweight(N, gtf, 1, 1.0, k1, k3);
+                    mtw[j] = bm25_termweight(N, gtf, q.wqf ? q.wqf[mb + j] : 1, 1.0, k1, k3);
                     const uint32_t wub = ids[mb + j] == 0xffffffffu ? 0 : ix->terms[ids[mb + j]].wdf_ub;
                     mmax[j] = bm25_maxpart(mtw[j], len_factor, k1, b, mnl, wub, ix->doclen_lb);
                 }
@@ -1250,6 +1406,7 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
                     rmax = sm[0];
                 }
                 pq.max_possible = pq.max_possible + rmax;
+                pq.bucket_max = pq.max_possible;
                 for (uint32_t j = 0; j < nmaybe; ++j) {
                     put_term(slot, mb + j, false);
                     dq.terms[slot].termweight = mtw[j];
@@ -1301,6 +1458,7 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
             }
         }
         pq.max_possible = sm[0]; pq.tf_min = smin[0]; pq.tf_max = smax[0]; pq.tf_est = (uint32_t)se[0];
+        pq.bucket_max = pq.max_possible;
         dq.route = 1;
         for (uint32_t i = 0; i < n; ++i) {
             uint32_t j = order[i];
@@ -1325,10 +1483,12 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
     if (pq.first >= pq.tf_max && cal != 0) { pq.count_only = true; dq.topk = 0; }
     else if (pq.topk > s->max_topk) { pq.status = XGM_E_INVALID; return XGM_OK; }
     /* pruning buckets: linear in the primary sort key (weight, or the sort value for VAL sorts) */
-    if (q.sort_by == XGM_SORT_REL || q.sort_by == XGM_SORT_REL_VAL)
-        dq.bucket_scale = pq.max_possible > 0 ? (double)XGM_NBINS / pq.max_possible : 0.0;
-    else
-        dq.bucket_scale = (double)XGM_NBINS / ((double)ix->slot_max[q.sort_slot] + 1.0);
+    if (q.sort_by == XGM_SORT_REL || q.sort_by == XGM_SORT_REL_VAL) {
+        dq.bucket_scale = pq.bucket_max > 0 ? (double)XGM_NBINS / pq.bucket_max : 0.0;
+    } else {
+        dq.bucket_key_min = ix->slot_min[q.sort_slot];
+        dq.bucket_scale = (double)XGM_NBINS / ((double)(ix->slot_max[q.sort_slot] - ix->slot_min[q.sort_slot]) + 1.0);
+    }
 
     if (cal == 0) { pq.on_device = false; return XGM_OK; } /* bounds only, matcher.cc:437-461 */
     if (dq.route == 0 && any_absent) { pq.on_device = false; return XGM_OK; } /* AND with an absent term: empty */

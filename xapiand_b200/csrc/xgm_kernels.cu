@@ -15,10 +15,26 @@
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "xgm_device.h"
 
 #define FULL 0xffffffffu
+
+/* cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute and one process may drive several
+ * GPUs through the C-ABI (an xgm_index carries its device): remember the opted-in size per (kernel, device). */
+#define XGM_MAX_DEVICES 64
+static cudaError_t optin_smem(const void* fn, int which, size_t bytes) {
+    static size_t have[4][XGM_MAX_DEVICES]; /* raised monotonically; racing threads set the same or a larger value */
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= XGM_MAX_DEVICES) return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (bytes <= have[which][dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have[which][dev] = bytes;
+    return e;
+}
 
 /* ------------------------------------------------------------------ PTX helpers */
 
@@ -217,9 +233,9 @@ __device__ __forceinline__ bool doc_passes_filter(const XgmKernelParams& p, cons
 
 __device__ __forceinline__ uint64_t doc_sort_key(const XgmKernelParams& p, const XgmDevQuery* q, uint32_t did) {
     const XgmDevSlot& s = p.slots[q->sort_slot];
-    if (!s.voff) return 0;
+    if (!s.voff) return q->sort_missing;
     uint32_t a = __ldg(&s.voff[did]), b = __ldg(&s.voff[did + 1]);
-    if (a == b) return 0;
+    if (a == b) return q->sort_missing; /* no value: "" for Enquire's value sorts, "\xff" / "\0" for Xapiand's SerialiseKey */
     return __ldg(&s.vals[q->sort_use_max ? b - 1 : a]);
 }
 
@@ -234,7 +250,8 @@ __device__ __forceinline__ uint32_t match_bucket(const XgmDevQuery* q, double w,
         uint32_t b = x >= (double)(XGM_NBINS - 1) ? XGM_NBINS - 1 : (uint32_t)x;
         return b;
     }
-    double x = (double)key * q->bucket_scale;
+    /* monotone in the key: the slot's [smallest, largest] key mapped linearly, anything outside clamped */
+    double x = key > q->bucket_key_min ? (double)(key - q->bucket_key_min) * q->bucket_scale : 0.0;
     uint32_t b = x >= (double)(XGM_NBINS - 1) ? XGM_NBINS - 1 : (uint32_t)x;
     return q->sort_reverse ? b : (XGM_NBINS - 1 - b);
 }
@@ -583,14 +600,18 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 3) xgm_and_kernel(XgmKernelP
             if (alive) {
                 const uint32_t dlen = __ldg(&p.doclen[d]);
                 const XgmBlockHdr h0 = hdr[drv_begin + wi.b0 + (src >> 7)];
-                acc[0] = bm25_sumpart(tw0, q, unpack_gl(p.tfs, h0.tf_off, src & 127u, XGM_HDR_TF_BITS(h0.meta)), dlen);
+                const uint32_t sp = q->src_pos; /* weighted range source: the child at this place of the sum */
+                if (sp == 0) acc[0] = q->src_weight;
+                acc[0] = __dadd_rn(acc[0], bm25_sumpart(tw0, q, unpack_gl(p.tfs, h0.tf_off, src & 127u, XGM_HDR_TF_BITS(h0.meta)), dlen));
                 for (uint32_t j = 1; j < nterms; ++j) {
+                    if (sp == j) acc[0] = __dadd_rn(acc[0], q->src_weight);
                     const uint32_t r = bitmap_rank(p, q->terms[j], d);
                     const XgmBlockHdr bh = hdr[q->terms[j].blk_begin + (r >> 7)];
                     const uint32_t tfj = unpack_gl(p.tfs, bh.tf_off, r & 127u, XGM_HDR_TF_BITS(bh.meta));
                     /* MultiAndPostList::get_weight: result += plist[i]->get_weight(), in plist order */
                     acc[0] = __dadd_rn(acc[0], bm25_sumpart(q->terms[j].termweight, q, tfj, dlen));
                 }
+                if (sp == nterms) acc[0] = __dadd_rn(acc[0], q->src_weight);
                 if (q->nmaybe) { /* OP_AND_MAYBE: res = l; if (r matches) res += r */
                     const double rw = maybe_weight(p, q, d, dlen, &opt);
                     if (opt) acc[0] = __dadd_rn(acc[0], rw);
@@ -678,6 +699,8 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 3) xgm_and_kernel(XgmKernelP
                         uint32_t tf = tb ? unpack_sm(ws.stage, 4 * lane + k, tb, tmask) : 0u;
                         dl[k] = __ldg(&p.doclen[c[k]]);
                         acc[k] = bm25_sumpart(tw0, q, tf, dl[k]);
+                        if (q->src_pos == 0) acc[k] = __dadd_rn(q->src_weight, acc[k]);
+                        else if (q->src_pos == 1) acc[k] = __dadd_rn(acc[k], q->src_weight);
                     }
                 }
                 __syncwarp();
@@ -694,10 +717,13 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 3) xgm_and_kernel(XgmKernelP
                         dl[k] = __ldg(&p.doclen[c[k]]);
                         uint32_t tf0 = unpack_gl(p.tfs, dh.tf_off, 4 * lane + k, XGM_HDR_TF_BITS(dh.meta));
                         acc[k] = bm25_sumpart(tw0, q, tf0, dl[k]);
+                        if (q->src_pos == 0) acc[k] = __dadd_rn(q->src_weight, acc[k]);
                     }
+                    if (q->src_pos == j) acc[k] = __dadd_rn(acc[k], q->src_weight);
                     uint32_t tfj = unpack_gl(p.tfs, bh.tf_off, pos, XGM_HDR_TF_BITS(bh.meta));
                     /* MultiAndPostList::get_weight: result += plist[i]->get_weight(), in plist order */
                     acc[k] = __dadd_rn(acc[k], bm25_sumpart(twj, q, tfj, dl[k]));
+                    if (j + 1 == nterms && q->src_pos == nterms) acc[k] = __dadd_rn(acc[k], q->src_weight);
                 };
                 const uint64_t bm_off = q->terms[j].bm_off;
                 if (bm_off != XGM_NO_BITMAP) {
@@ -954,14 +980,338 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 4) xgm_and_bm_kernel(XgmKernelP
 
 #undef bar_base
 
+/* ------------------------------------------------------------------ bitmap AND kernel, two-stage queues */
+
+/* Same contract as xgm_and_bm_kernel.  What changed is where the rare work happens.  Of the driver postings
+ * ~1 % pass the second list's bitmap and ~0.01 % are matches, yet in the kernel above every work item ended
+ * with a partially filled flush that ran the whole scoring code (two rank look-ups, three wdf unpacks, three
+ * f64 divisions, emission) for a handful of live lanes.  Here a warp keeps two queues in shared memory for
+ * its whole lifetime, entries tagged with their query:
+ *   stage 1  candidates confirmed by the second list       → flushed 32 at a time: remaining bitmaps
+ *            (required / excluded lists), value-range predicate; the survivors — the matches — go to
+ *   stage 2  matches                                       → flushed 32 at a time: rank → wdf, doc length,
+ *            BM25 in MultiAndPostList order (multiandpostlist.cc:149-159), per-lane emission.
+ * Both are only drained when the warp runs out of work, so every flush but the last runs on a full warp.
+ * Stage-1 slots come from four ballots per iteration (lanes with a survivor + the bits of their count)
+ * instead of one ballot per posting slot. */
+#define BM3_WARPS 8
+#define BM3_Q1CAP 288 /* < 32 left over + up to 256 new candidates per iteration */
+#define BM3_Q2CAP 64
+
+struct __align__(16) Bm3Scratch {
+    uint32_t dstage[4][STAGE_WORDS];
+    uint32_t q1did[BM3_Q1CAP]; /* stage 1 belongs to the current work item (one query) */
+    uint16_t q1src[BM3_Q1CAP]; /* (driver block - b0) << 7 | position */
+    uint32_t q2did[BM3_Q2CAP]; /* stage 2 lives as long as the warp: entries carry their query */
+    uint32_t q2src[BM3_Q2CAP]; /* index of the driver block's header in hdr[] */
+    uint32_t q2qi[BM3_Q2CAP];  /* query | position in the driver block << 25 */
+    uint64_t dbar[4];
+};
+/* 4.6 KB per warp, 37 KB per CTA: with 4 CTAs per SM the shared-memory carve-out stays at 164 KB and the
+ * bitmap probes keep ~90 KB of L1 (a first version with 51 KB per CTA pushed the carve-out to 228 KB and lost
+ * 19 % to L1 misses of the probes). */
+
+/* Highest bin with at least topk stored matches at or above it → raise the query's pruning bucket
+ * (the warp-cooperative half of emit_matches_impl). */
+__device__ __noinline__ void raise_bstar_warp(const XgmKernelParams& p, uint32_t qi, uint32_t lane) {
+    const XgmDevQuery* q = &p.queries[qi];
+    XgmQState* st = &p.qstate[qi];
+    const volatile uint32_t* vh = p.hist + (size_t)qi * XGM_NBINS;
+    __threadfence();
+    uint32_t mine = 0;
+    for (int i = 0; i < XGM_NBINS / 32; ++i) mine += vh[lane * (XGM_NBINS / 32) + i];
+    uint32_t sfx = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_down_sync(FULL, sfx, o);
+        if ((int)lane + o < 32) sfx += t;
+    }
+    const uint32_t ok = __ballot_sync(FULL, sfx >= q->topk);
+    if (ok) {
+        const uint32_t L = 31 - __clz(ok);
+        if (lane == L) {
+            uint32_t cum = sfx - mine;
+            uint32_t nb = L * (XGM_NBINS / 32);
+            for (int i = XGM_NBINS / 32 - 1; i >= 0; --i) {
+                cum += vh[L * (XGM_NBINS / 32) + i];
+                if (cum >= q->topk) { nb = L * (XGM_NBINS / 32) + i; break; }
+            }
+            atomicMax(&st->bstar, nb);
+        }
+    }
+}
+
+/* Per-lane emission of one match (lanes of a flush belong to different queries): count it, keep it unless
+ * its bucket is already below the query's pruning bucket.  Warp-converged call. */
+__device__ __forceinline__ void emit_match_lanes(const XgmKernelParams& p, uint32_t lane, bool alive, uint32_t qi, double w,
+                                                 uint32_t d, uint32_t aux) {
+    bool crossed = false;
+    if (alive) {
+        const XgmDevQuery* q = &p.queries[qi];
+        XgmQState* st = &p.qstate[qi];
+        if (p.pass == 0) {
+            atomicAdd(&st->total, 1u);
+            atomicMax(&st->maxw, (unsigned long long)__double_as_longlong(w));
+        }
+        const uint64_t key = q->sort_by != 0 ? doc_sort_key(p, q, d) : 0ull;
+        const uint32_t bkt = match_bucket(q, w, key);
+        const uint32_t bstar = *reinterpret_cast<volatile uint32_t*>(&st->bstar);
+        if (bkt >= bstar && q->topk != 0) {
+            const uint32_t idx = atomicAdd(&st->stored, 1u);
+            const uint64_t kv = q->sort_by != 0 ? key : (uint64_t)aux;
+            if (p.pass == 0) {
+                atomicAdd(p.hist + (size_t)qi * XGM_NBINS + bkt, 1u);
+                if (idx < p.match_cap) {
+                    const size_t o = (size_t)qi * p.match_cap + idx;
+                    p.match_w[o] = w; p.match_d[o] = d; p.match_k[o] = kv;
+                }
+                const uint32_t after = idx + 1;
+                crossed = (idx >> 8) != (after >> 8) && after >= q->topk && after >= p.keep_cap / 2;
+            } else if (idx < st->pool_cap) {
+                const size_t o = (size_t)st->pool_off + idx;
+                p.pool_w[o] = w; p.pool_d[o] = d; p.pool_k[o] = kv;
+            }
+        }
+    }
+    uint32_t m = __ballot_sync(FULL, crossed);
+    while (m) {
+        const uint32_t l = (uint32_t)__ffs(m) - 1u;
+        m &= m - 1u;
+        raise_bstar_warp(p, __shfl_sync(FULL, qi, l), lane);
+    }
+}
+
+/* One flat loop with four states, so that each piece of code exists once and nothing is called from the hot
+ * path: score 32 matches (stage 2 full, or out of work) → finish 32 candidates (stage 1 full, or the item
+ * ended) → fetch the next work item → decode and probe the next pair of driver blocks. */
+template <int MINB>
+__global__ void __launch_bounds__(BM3_WARPS * 32, MINB) xgm_and_bm3_kernel(const __grid_constant__ XgmKernelParams p) {
+    extern __shared__ __align__(16) unsigned char bm3_raw[];
+    Bm3Scratch* scratch = reinterpret_cast<Bm3Scratch*>(bm3_raw);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    Bm3Scratch& ws = scratch[warp];
+    if (lane < 4) mbar_init(&ws.dbar[lane], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    uint32_t phases = 0;
+    const XgmBlockHdr* __restrict__ hdr = p.hdr;
+    const uint32_t stage_base = smem_u32(ws.dstage[0]);
+    const uint32_t bar_base = stage_base + (uint32_t)offsetof(Bm3Scratch, dbar);
+    if (p.pass != 0 && *reinterpret_cast<volatile uint32_t*>(p.work_counter + 4) == 0) return;
+    const uint32_t nitems_bm = p.nitems_bm_dev ? __ldg(p.nitems_bm_dev) : p.nitems_bm;
+    uint32_t qn1 = 0, qn2 = 0; /* warp-uniform queue lengths */
+    bool done = false;
+    /* current work item: driver blocks [db, it_b1) of query it_query are left (db >= it_b1: none) */
+    uint32_t it_query = 0, it_b0 = 0, it_b1 = 0, db = 0, drv_begin = 0, cur = 0;
+    const XgmDevQuery* q = p.queries;
+    const uint32_t* __restrict__ bm1 = p.bitmaps;
+    uint2 h0 = make_uint2(0u, 0u), h1 = h0; /* (first docid, meta) of the staged pair */
+
+    /* stage driver block blk into buffer b; only (first docid, meta) of its header stay live */
+    auto issue = [&](uint32_t b, uint32_t blk) {
+        const uint4 h = __ldg(reinterpret_cast<const uint4*>(hdr + drv_begin + blk));
+        const uint32_t bits = XGM_HDR_DOC_BITS(h.w);
+        __syncwarp();
+        if (bits != 0 && lane == 0) {
+            mbar_expect_tx_a(bar_base + b * 8u, bits * 16u);
+            bulk_g2s_a(stage_base + b * (STAGE_WORDS * 4u), p.docs + h.y, bits * 16u, bar_base + b * 8u);
+        }
+        return make_uint2(h.x, h.w);
+    };
+
+    for (;;) {
+        /* ---- stage 2: score queued matches (one per lane) and emit them ---- */
+        if (qn2 >= 32 || (done && qn2 != 0)) {
+            const uint32_t count = min(qn2, 32u);
+            qn2 -= count;
+            const bool alive = lane < count;
+            const uint32_t d = alive ? ws.q2did[qn2 + lane] : 0u;
+            const uint32_t src = alive ? ws.q2src[qn2 + lane] : 0u;
+            const uint32_t qp = alive ? ws.q2qi[qn2 + lane] : 0u;
+            const uint32_t qi = qp & 0x1ffffffu, pos = qp >> 25;
+            double acc = 0.0;
+            uint32_t aux = 0;
+            if (alive) {
+                const XgmDevQuery* mq = &p.queries[qi];
+                const uint32_t dlen = __ldg(&p.doclen[d]);
+                const XgmBlockHdr hh = hdr[src];
+                const uint32_t nterms = mq->nterms, sp = mq->src_pos;
+                /* MultiAndPostList::get_weight: result += plist[i]->get_weight(), in plist order
+                 * (multiandpostlist.cc:149-159); a weighted range source is the child at position src_pos */
+                if (sp == 0) acc = mq->src_weight;
+                acc = __dadd_rn(acc, bm25_sumpart(mq->terms[0].termweight, mq, unpack_gl(p.tfs, hh.tf_off, pos, XGM_HDR_TF_BITS(hh.meta)), dlen));
+                for (uint32_t j = 1; j < nterms; ++j) {
+                    if (sp == j) acc = __dadd_rn(acc, mq->src_weight);
+                    const uint32_t r = bitmap_rank(p, mq->terms[j], d);
+                    const XgmBlockHdr bh = hdr[mq->terms[j].blk_begin + (r >> 7)];
+                    const uint32_t tfj = unpack_gl(p.tfs, bh.tf_off, r & 127u, XGM_HDR_TF_BITS(bh.meta));
+                    acc = __dadd_rn(acc, bm25_sumpart(mq->terms[j].termweight, mq, tfj, dlen));
+                }
+                if (sp == nterms) acc = __dadd_rn(acc, mq->src_weight);
+                uint32_t opt = 0;
+                if (mq->nmaybe) { /* OP_AND_MAYBE: res = l; if (r matches) res += r */
+                    const double rw = maybe_weight(p, mq, d, dlen, &opt);
+                    if (opt) acc = __dadd_rn(acc, rw);
+                }
+                aux = mq->nweighted + opt;
+            }
+            emit_match_lanes(p, lane, alive, qi, acc, d, aux);
+            __syncwarp();
+            continue;
+        }
+        const bool item_end = db >= it_b1;
+        /* ---- stage 1: finish the boolean test of queued candidates of the current item ---- */
+        if (qn1 >= 32 || (item_end && qn1 != 0)) {
+            __syncwarp();
+            const uint32_t count = min(qn1, 32u);
+            qn1 -= count;
+            bool alive = lane < count;
+            const uint32_t d = alive ? ws.q1did[qn1 + lane] : 0u;
+            const uint32_t src = alive ? ws.q1src[qn1 + lane] : 0u;
+            const uint32_t nterms = q->nterms, nall = nterms + q->nnot;
+            for (uint32_t j = 2; j < nall && __any_sync(FULL, alive); ++j) {
+                if (alive) {
+                    const uint32_t w = __ldg(p.bitmaps + q->terms[j].bm_off + (d >> 5));
+                    /* required lists must hold the docid; the right side of an OP_AND_NOT must not
+                     * (AndNotPostList::next, matcher/andnotpostlist.cc:97-130) */
+                    if (((w >> (d & 31)) & 1u) == (j < nterms ? 0u : 1u)) alive = false;
+                }
+            }
+            if (alive && q->filter && !doc_passes_filter(p, q, d)) alive = false;
+            const uint32_t m = __ballot_sync(FULL, alive);
+            if (alive) {
+                const uint32_t slot = qn2 + __popc(m & ((1u << lane) - 1u));
+                ws.q2did[slot] = d;
+                ws.q2src[slot] = drv_begin + it_b0 + (src >> 7);
+                ws.q2qi[slot] = it_query | ((src & 127u) << 25);
+            }
+            qn2 += __popc(m);
+            __syncwarp();
+            continue;
+        }
+        if (done) break;
+        /* ---- next work item ---- */
+        if (item_end) {
+            uint32_t item = 0;
+            if (lane == 0) item = atomicAdd(p.work_counter + 6 + p.pass, 1u);
+            item = __shfl_sync(FULL, item, 0);
+            if (item >= nitems_bm) { done = true; continue; }
+            const XgmWorkItem wi = p.items_bm[item];
+            if (p.pass != 0 && p.qstate[wi.query].rerun == 0) continue;
+            it_query = wi.query; it_b0 = wi.b0; it_b1 = wi.b1; db = wi.b0;
+            q = &p.queries[wi.query];
+            drv_begin = q->terms[0].blk_begin;
+            bm1 = p.bitmaps + q->terms[1].bm_off;
+            h0 = issue(0, db);
+            h1 = h0;
+            if (db + 1 < it_b1) h1 = issue(1, db + 1);
+            cur = 0; /* buffers cur, cur+1 hold the current pair; (cur^2), (cur^2)+1 the next */
+            continue;
+        }
+        /* ---- one pair of driver blocks ---- */
+        {
+            const bool two = db + 1 < it_b1;
+            uint2 n0 = h0, n1 = h1;
+            if (db + 2 < it_b1) n0 = issue(cur ^ 2, db + 2);
+            if (db + 3 < it_b1) n1 = issue((cur ^ 2) + 1, db + 3);
+            uint32_t c[8];
+            uint32_t alive;
+            const uint32_t cnt0 = XGM_HDR_COUNT(h0.y), cnt1 = two ? XGM_HDR_COUNT(h1.y) : 0u;
+            {
+                const uint32_t bits = XGM_HDR_DOC_BITS(h0.y);
+                if (bits) { mbar_wait_a(bar_base + cur * 8u, (phases >> cur) & 1u); phases ^= 1u << cur; }
+                decode_docids(ws.dstage[cur], bits, h0.x, lane, c);
+            }
+            if (two) {
+                const uint32_t bits = XGM_HDR_DOC_BITS(h1.y);
+                if (bits) { mbar_wait_a(bar_base + (cur + 1) * 8u, (phases >> (cur + 1)) & 1u); phases ^= 1u << (cur + 1); }
+                decode_docids(ws.dstage[cur + 1], bits, h1.x, lane, c + 4);
+            } else {
+                c[4] = c[5] = c[6] = c[7] = 0u;
+            }
+            /* the skip_to/check of the leapfrog: one bitmap word per candidate, all loads issued together */
+            uint32_t w[8];
+            if (cnt0 + cnt1 == 2u * XGM_BLOCK) { /* two full blocks (warp-uniform): no per-posting predicates */
+                alive = 0xffu;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) w[k] = __ldg(bm1 + (c[k] >> 5));
+            } else {
+                const int m0 = min(4, max(0, (int)cnt0 - 4 * (int)lane)), m1 = min(4, max(0, (int)cnt1 - 4 * (int)lane));
+                alive = ((1u << m0) - 1u) | (((1u << m1) - 1u) << 4);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) w[k] = (alive >> k & 1u) ? __ldg(bm1 + (c[k] >> 5)) : 0u;
+            }
+            uint32_t surv = 0; /* dead slots carry w = 0 */
+#pragma unroll
+            for (int k = 0; k < 8; ++k) surv |= (__funnelshift_r(w[k], 0u, c[k]) & 1u) << k; /* shifts by c & 31 */
+            /* Queue slots without a scan: survivors are rare, so a lane's count n is 1..8 in the few lanes that
+             * have one; four ballots (lanes with survivors, and the three bits of n - 1) give every lane the
+             * number of survivors in the lanes below it. */
+            const uint32_t B = __ballot_sync(FULL, surv != 0);
+            if (B) {
+                const uint32_t nm1 = (uint32_t)__popc(surv) - 1u;
+                const uint32_t B0 = __ballot_sync(FULL, surv != 0 && (nm1 & 1u));
+                const uint32_t B1 = __ballot_sync(FULL, surv != 0 && (nm1 & 2u));
+                const uint32_t B2 = __ballot_sync(FULL, surv != 0 && (nm1 & 4u));
+                if (surv) {
+                    const uint32_t lt = (1u << lane) - 1u;
+                    uint32_t slot = qn1 + __popc(B & lt) + __popc(B0 & lt) + 2u * __popc(B1 & lt) + 4u * __popc(B2 & lt);
+                    const uint32_t rb = (db - it_b0) << 7 | 4 * lane;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (surv >> k & 1u) {
+                            ws.q1did[slot] = c[k];
+                            ws.q1src[slot] = (uint16_t)(rb + ((k >> 2) << 7) + (k & 3));
+                            ++slot;
+                        }
+                }
+                qn1 += __popc(B) + __popc(B0) + 2u * __popc(B1) + 4u * __popc(B2);
+            }
+            h0 = n0;
+            h1 = n1;
+            cur ^= 2u;
+            db += 2;
+        }
+    }
+}
+
+static int g_bm_variant = -1; /* XGM_BM_VARIANT: 1 = one-stage kernel above; 33/34/35 = two-stage with launch bounds for 3/4/5 CTAs per SM */
+static int bm_variant() {
+    if (g_bm_variant < 0) {
+        const char* e = getenv("XGM_BM_VARIANT");
+        g_bm_variant = e ? atoi(e) : 34;
+        if (g_bm_variant != 1 && (g_bm_variant < 33 || g_bm_variant > 35)) g_bm_variant = 34;
+    }
+    return g_bm_variant;
+}
+
+typedef void (*bm3_fn)(const XgmKernelParams);
+static bm3_fn bm3_kernel(int v) {
+    return v == 33 ? xgm_and_bm3_kernel<3> : v == 35 ? xgm_and_bm3_kernel<5> : xgm_and_bm3_kernel<4>;
+}
+
 cudaError_t xgm_launch_and_bm(const XgmKernelParams& p, int grid, cudaStream_t s) {
-    xgm_and_bm_kernel<<<grid, BM_WARPS * 32, 0, s>>>(p);
+    const int v = bm_variant();
+    if (v == 1) {
+        xgm_and_bm_kernel<<<grid, BM_WARPS * 32, 0, s>>>(p);
+    } else {
+        bm3_kernel(v)<<<grid, BM3_WARPS * 32, sizeof(Bm3Scratch) * BM3_WARPS, s>>>(p);
+    }
     return cudaGetLastError();
 }
 
+/* Also opts the kernel in to its dynamic shared memory on the CURRENT device (the attribute is per device:
+ * call once per searcher, after cudaSetDevice). */
 int xgm_and_bm_occupancy_blocks_per_sm() {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, xgm_and_bm_kernel, BM_WARPS * 32, 0);
+    const int v = bm_variant();
+    if (v == 1) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, xgm_and_bm_kernel, BM_WARPS * 32, 0);
+    } else {
+        const size_t smem = sizeof(Bm3Scratch) * BM3_WARPS;
+        cudaFuncSetAttribute(bm3_kernel(v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bm3_kernel(v), BM3_WARPS * 32, smem);
+    }
     return n;
 }
 
@@ -1294,12 +1644,8 @@ __global__ void __launch_bounds__(A2_THREADS, 3) xgm_and2_kernel(XgmKernelParams
 }
 
 cudaError_t xgm_launch_and2(const XgmKernelParams& p, int grid, cudaStream_t s) {
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(xgm_and2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(A2Smem));
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
+    cudaError_t e = optin_smem((const void*)xgm_and2_kernel, 2, sizeof(A2Smem));
+    if (e != cudaSuccess) return e;
     xgm_and2_kernel<<<grid, A2_THREADS, sizeof(A2Smem), s>>>(p);
     return cudaGetLastError();
 }
@@ -1676,11 +2022,12 @@ __global__ void __launch_bounds__(TOPK_THREADS) xgm_topk_kernel(XgmKernelParams 
                 XgmDevResult r;
                 r.n = 0; r.exact = st.total; r.known = 0; r.max_w = __longlong_as_double((long long)st.maxw);
                 r.max_subqs = q->nweighted; r.pad = 0;
-                const uint32_t off = atomicAdd(p.work_counter + 5, cum);
-                if (cum >= topk && (uint64_t)off + cum <= (uint64_t)p.pool_total) {
+                /* 64-bit reservation counter (words 8, 9): the sum over a batch of tie-mass queries cannot wrap */
+                const unsigned long long off = atomicAdd(reinterpret_cast<unsigned long long*>(p.work_counter + 8), (unsigned long long)cum);
+                if (cum >= topk && off + cum <= (unsigned long long)p.pool_total) {
                     p.qstate[qi].bstar = b;
                     p.qstate[qi].stored = 0;
-                    p.qstate[qi].pool_off = off;
+                    p.qstate[qi].pool_off = (uint32_t)off;
                     p.qstate[qi].pool_cap = cum;
                     p.qstate[qi].rerun = 1;
                     atomicAdd(p.work_counter + 4, 1u);
@@ -2030,11 +2377,9 @@ cudaError_t xgm_launch_merge(const double* gw, const uint32_t* gd, const XgmDevR
                              cudaStream_t s) {
     if (nparts > XGM_MERGE_MAX_PARTS) return cudaErrorInvalidValue;
     size_t smem = (size_t)nparts * k * 12;
-    static size_t attr_bytes = 48 * 1024;
-    if (smem > attr_bytes) {
-        cudaError_t e = cudaFuncSetAttribute(xgm_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024) {
+        cudaError_t e = optin_smem((const void*)xgm_merge_kernel, 0, smem);
         if (e != cudaSuccess) return e;
-        attr_bytes = smem;
     }
     xgm_merge_kernel<<<nq, 256, smem, s>>>(gw, gd, ginfo, part_w, part_d, part_info, nparts, nq, stride, k, out_w, out_d, out_n);
     return cudaGetLastError();
@@ -2259,11 +2604,9 @@ size_t xgm_topk_smem_bytes(uint32_t keep_cap) { return (size_t)keep_cap * (8 + 8
 
 cudaError_t xgm_launch_topk(const XgmKernelParams& p, uint32_t nq, cudaStream_t s) {
     size_t smem = xgm_topk_smem_bytes(p.keep_cap);
-    static size_t attr_bytes = 48 * 1024; /* raised monotonically; benign race: same value per device */
-    if (smem > attr_bytes) {
-        cudaError_t e = cudaFuncSetAttribute(xgm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024) {
+        cudaError_t e = optin_smem((const void*)xgm_topk_kernel, 1, smem);
         if (e != cudaSuccess) return e;
-        attr_bytes = smem;
     }
     xgm_topk_kernel<<<nq, TOPK_THREADS, smem, s>>>(p);
     return cudaGetLastError();

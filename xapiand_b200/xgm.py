@@ -33,6 +33,8 @@ EXPORTS = [
     "xgm_search_device_results", "xgm_search_device_slab",
     "xgm_searcher_stream", "xgm_search_last_stats", "xgm_unshard", "xgm_merge_msets", "xgm_merge_topk_device",
     "xgm_merge_topk_device_slab",
+    "xgm_builder_add_value_slot_serialised", "xgm_builder_set_revision", "xgm_index_value_freq",
+    "xgm_value_key", "xgm_value_key_bytes", "xgm_sort_key_bytes",
 ]
 
 
@@ -71,7 +73,10 @@ class CQuery(C.Structure):
                 ("range_hi", C.c_uint64), ("sort_by", C.c_uint32), ("sort_slot", C.c_uint32),
                 ("sort_reverse", C.c_uint32), ("sort_use_max", C.c_uint32),
                 ("nfilter", C.c_uint32), ("nnot", C.c_uint32), ("nmaybe", C.c_uint32), ("reserved", C.c_uint32),
-                ("factors", C.POINTER(C.c_double))]
+                ("factors", C.POINTER(C.c_double)),
+                # ABI 2
+                ("revision", C.c_uint64), ("filter_weighted", C.c_uint32), ("reserved2", C.c_uint32),
+                ("filter_factor", C.c_double), ("sort_missing_key", C.c_uint64)]
 
 
 class MSetInfo(C.Structure):
@@ -110,6 +115,15 @@ def lib():
     L.xgm_builder_add_term.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
                                        C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32)]
     L.xgm_builder_add_value_slot.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.xgm_builder_add_value_slot_serialised.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.xgm_builder_set_revision.argtypes = [C.c_void_p, C.c_uint64]
+    L.xgm_index_value_freq.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    L.xgm_value_key.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_uint64)]
+    L.xgm_value_key.restype = C.c_int
+    L.xgm_value_key_bytes.argtypes = [C.c_uint64, C.c_char_p]
+    L.xgm_value_key_bytes.restype = C.c_size_t
+    L.xgm_sort_key_bytes.argtypes = [C.c_uint64, C.c_int, C.c_char_p]
+    L.xgm_sort_key_bytes.restype = C.c_size_t
     L.xgm_builder_finish.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
     L.xgm_builder_free.argtypes = [C.c_void_p]
     L.xgm_builder_free.restype = None
@@ -191,6 +205,10 @@ class Query:
     maybe_terms: Sequence[Union[str, bytes, int]] = ()
     factors: Optional[Sequence[float]] = None     # OP_SCALE_WEIGHT factor per base term
     bm25: Optional[tuple] = None                  # (k1, k3, b, min_normlen); None = BM25Weight defaults
+    revision: int = 0                             # expected Database::get_revision (0 = any)
+    filter_weighted: bool = False                 # the range source is an AND child with weight factor * 1.0
+    filter_factor: float = 0.0
+    sort_missing_key: int = 0                     # key of documents without a value in sort_slot
 
 
 class QueryBatch:
@@ -236,6 +254,8 @@ class QueryBatch:
             cq.range_lo, cq.range_hi = q.range_lo, q.range_hi
             cq.sort_by, cq.sort_slot = q.sort_by, q.sort_slot
             cq.sort_reverse, cq.sort_use_max = int(q.sort_reverse), int(q.sort_use_max)
+            cq.revision, cq.filter_weighted, cq.filter_factor = q.revision, int(q.filter_weighted), float(q.filter_factor)
+            cq.sort_missing_key = q.sort_missing_key
 
 
 @dataclass
@@ -314,8 +334,11 @@ class Index:
 
     @classmethod
     def from_postings(cls, doclen: np.ndarray, terms, doccount: Optional[int] = None,
-                      total_length: Optional[int] = None, value_slots=None, device: int = 0) -> "Index":
-        """terms: iterable of (name, docids u32[], wdfs u32[]) — what PostingIterator yields."""
+                      total_length: Optional[int] = None, value_slots=None, device: int = 0,
+                      serialised_slots=None, revision: int = 0) -> "Index":
+        """terms: iterable of (name, docids u32[], wdfs u32[]) — what PostingIterator yields.
+        serialised_slots: {slot: [bytes per docid 0..lastdocid]} — Document::get_value bytes as Xapiand stores
+        them (StringList of serialised values)."""
         L = lib()
         b = C.c_void_p()
         _check(L.xgm_builder_new(C.byref(b)))
@@ -337,6 +360,15 @@ class Index:
                 voff = np.ascontiguousarray(voff, np.uint64)
                 vals = np.ascontiguousarray(vals, np.uint64)
                 _check(L.xgm_builder_add_value_slot(b, slot, _ptr(voff), _ptr(vals)))
+            for slot, per_doc in (serialised_slots or {}).items():
+                per_doc = list(per_doc) + [b""] * (lastdocid + 1 - len(per_doc))
+                off = np.zeros(lastdocid + 2, np.uint64)
+                off[1:] = np.cumsum([len(x) for x in per_doc])
+                blob = b"".join(per_doc)
+                buf = np.frombuffer(blob + b"\0", np.uint8)
+                _check(L.xgm_builder_add_value_slot_serialised(b, slot, _ptr(off), _ptr(buf)))
+            if revision:
+                _check(L.xgm_builder_set_revision(b, revision))
             h = C.c_void_p()
             st = L.xgm_builder_finish(b, device, C.byref(h))
             b = None
@@ -514,3 +546,23 @@ def merge_msets(parts: Sequence[MSet], first: int, maxitems: int, sort_by: int =
     return MSet(od[:oi.n], ow[:oi.n], ok[:oi.n], first, oi.matches_lower_bound, oi.matches_estimated,
                 oi.matches_upper_bound, oi.max_possible, oi.max_attained, oi.percent_scale_factor,
                 oi.exact_matches, oi.status, oi.flags)
+
+
+def value_key(b: bytes):
+    """(key, exact): the device's 8-byte big-endian key of a serialised slot value (include/xgm.h)."""
+    k = C.c_uint64()
+    exact = lib().xgm_value_key(b, len(b), C.byref(k))
+    return int(k.value), bool(exact)
+
+
+def value_key_bytes(key: int) -> bytes:
+    buf = C.create_string_buffer(8)
+    n = lib().xgm_value_key_bytes(key, buf)
+    return buf.raw[:n]
+
+
+def sort_key_bytes(key: int, reverse: bool) -> bytes:
+    """MSetIterator::get_sort_key under Xapiand's Multi_MultiValueKeyMaker with one SerialiseKey slot."""
+    buf = C.create_string_buffer(20)
+    n = lib().xgm_sort_key_bytes(key, int(reverse), buf)
+    return buf.raw[:n]
