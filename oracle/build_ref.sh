@@ -27,8 +27,8 @@ fi
 # call into Xapiand's schema / cast / datetime / geospatial code, which is NOT built: those are function
 # symbols only, left undefined in the shared object and bound lazily (-z lazy) — nothing on the matching
 # path calls them.  Pins SURVEY.md section 8 rows a15 / a16 against the reference's real code.
-build_mv() {
-  local MV="$O/libxapiand_mv_ref.so"
+build_mv() {   # $1 = "" (against libxapian_ref.so) or "_xgm" (against libxapian_ref_xgm.so)
+  local MV="$O/libxapiand_mv_ref$1.so"
   if [ -f "$MV" ] && [ "$MV" -nt "$HERE/ref_mv_glue.cc" ] && [ "${FORCE:-0}" != "1" ]; then return 0; fi
   mkdir -p "$O/obj_mv"
   local MVFLAGS="-std=c++17 -O2 -DNDEBUG -fPIC -w -include limits -include cstdint -include functional -I$O/gen -I$R -I$REF"
@@ -42,13 +42,37 @@ build_mv() {
   objs="$objs $O/obj_mv/ref_mv_glue.o"
   g++ $MVFLAGS -c "$HERE/ref_mv_glue.cc" -o "$O/obj_mv/ref_mv_glue.o" &
   wait
-  g++ -shared -o "$MV" $objs -L"$O" -lxapian_ref -Wl,-z,lazy -Wl,-rpath,'$ORIGIN'
+  g++ -shared -o "$MV" $objs -L"$O" -lxapian_ref$1 -Wl,-z,lazy -Wl,-rpath,'$ORIGIN'
   echo "build_ref: built $MV"
+}
+
+# ---- the variant a maintainer would ship: the same library with the xgm shim at the Matcher::get_mset seam ----
+# xapiand_b200/shim/xgm_shim.{h,cc} (ours) + ONE patched line of src/xapian/matcher/matcher.cc (:595, the call of
+# get_local_mset): the patched copy is generated with sed into oracle/_ref/gen/ (git-ignored), the reference
+# sources stay where they lie.  Every other object file is shared with libxapian_ref.so.
+build_xgm() {
+  local X="$O/libxapian_ref_xgm.so"
+  local SH="$HERE/../xapiand_b200/shim"
+  if [ -f "$X" ] && [ "$X" -nt "$SH/xgm_shim.cc" ] && [ "$X" -nt "$SH/xgm_shim.h" ] && [ "$X" -nt "$HERE/../include/xgm.h" ] && [ "${FORCE:-0}" != "1" ]; then
+    build_mv _xgm; return 0
+  fi
+  local XFLAGS="-std=c++17 -O3 -DNDEBUG -fPIC -w -include limits -include cstdint -I$O/gen -I$R -I$R/xapian -I$SH"
+  sed -e 's|^#include "xapian/matcher/matcher.h"$|#include "xapian/matcher/matcher.h"\n#include "xgm_shim.h"|' \
+      -e 's|local_mset = get_local_mset(first, maxitems, check_at_least,|if (!XGM_SHIM_TRY_LOCAL_MSET(local_mset)) local_mset = get_local_mset(first, maxitems, check_at_least,|' \
+      "$R/xapian/matcher/matcher.cc" > "$O/gen/matcher_xgm.cc"
+  grep -q XGM_SHIM_TRY_LOCAL_MSET "$O/gen/matcher_xgm.cc" || { echo "build_ref: seam not found in matcher.cc" >&2; exit 1; }
+  g++ $XFLAGS -I"$R/xapian/matcher" -c "$O/gen/matcher_xgm.cc" -o "$O/obj/xgm_matcher.o" &
+  g++ $XFLAGS -c "$SH/xgm_shim.cc" -o "$O/obj/xgm_shim.o" &
+  wait
+  g++ -shared -o "$X" $(awk '{print $2}' "$O/obj/.list" | grep -v 'xapian_matcher_matcher\.o$') "$O/obj/xgm_matcher.o" "$O/obj/xgm_shim.o" -lz -lpthread -ldl
+  echo "build_ref: built $X"
+  build_mv _xgm
 }
 
 if [ -f "$O/libxapian_ref.so" ] && [ "${FORCE:-0}" != "1" ]; then
   echo "build_ref: $O/libxapian_ref.so already built (FORCE=1 to rebuild)"
-  build_mv
+  build_mv ""
+  build_xgm
   exit 0
 fi
 
@@ -93,4 +117,5 @@ done
 xargs -P "$JOBS" -L 1 bash -c 'if [ ! -f "$1" ] || [ "$0" -nt "$1" ]; then g++ '"$CXXFLAGS"' -c "$0" -o "$1" || exit 255; fi' < "$O/obj/.list"
 g++ -shared -o "$O/libxapian_ref.so" $(awk '{print $2}' "$O/obj/.list") -lz -lpthread
 echo "build_ref: built $O/libxapian_ref.so ($(wc -l < "$O/obj/.list") objects)"
-build_mv
+build_mv ""
+build_xgm

@@ -20,6 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libxgm_oracle.so")
 REF_DIR = os.path.join(HERE, "_ref")
 REF_RUNNER = os.path.join(REF_DIR, "ref_runner")
+REF_RUNNER_XGM = os.path.join(REF_DIR, "ref_runner_xgm")  # same driver on libxapian_ref_xgm.so (the xgm shim)
 
 OP_AND, OP_OR = 0, 1
 SORT_REL, SORT_VAL_REL, SORT_VAL, SORT_REL_VAL = 0, 1, 2, 3
@@ -47,7 +48,7 @@ class _Index(C.Structure):
                 ("wdfs", C.POINTER(C.c_uint32)), ("collfreq", C.POINTER(C.c_uint64)),
                 ("wdf_ub", C.POINTER(C.c_uint32)), ("names", C.POINTER(C.c_char_p)),
                 ("nvals0", C.POINTER(C.c_uint8)), ("vals0", C.POINTER(C.c_uint64)),
-                ("val1", C.POINTER(C.c_uint64))]
+                ("val1", C.POINTER(C.c_uint64)), ("has1", C.POINTER(C.c_uint8))]
 
 
 class _Stats(C.Structure):
@@ -65,7 +66,9 @@ class _Query(C.Structure):
                 ("sort_by", C.c_int), ("sort_slot", C.c_int), ("sort_reverse", C.c_int),
                 ("nfilter", C.c_uint32), ("filter_terms", C.POINTER(C.c_uint32)),
                 ("nnot", C.c_uint32), ("not_terms", C.POINTER(C.c_uint32)),
-                ("nmaybe", C.c_uint32), ("maybe_terms", C.POINTER(C.c_uint32))]
+                ("nmaybe", C.c_uint32), ("maybe_terms", C.POINTER(C.c_uint32)),
+                ("filter_weighted", C.c_int), ("filter_factor", C.c_double),
+                ("sort_keymaker", C.c_int), ("sort_missing", C.c_uint64)]
 
 
 class _MSet(C.Structure):
@@ -91,6 +94,7 @@ def lib():
         L.orc_index_load_flat.restype = C.POINTER(_Index)
         L.orc_index_load_flat.argtypes = [C.c_char_p]
         L.orc_index_free.argtypes = [C.POINTER(_Index)]
+        L.orc_index_make_sparse.argtypes = [C.POINTER(_Index), C.c_uint32, C.c_uint32]
         L.orc_query_defaults.argtypes = [C.POINTER(_Query)]
         L.orc_match.argtypes = [C.POINTER(_Index), C.POINTER(_Query), C.POINTER(_MSet)]
         L.orc_merge.argtypes = [C.POINTER(_MSet), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
@@ -149,6 +153,11 @@ class Query:
     filter_terms: Sequence[int] = ()
     not_terms: Sequence[int] = ()
     maybe_terms: Sequence[int] = ()
+    # Xapiand's MultipleValueRange as a weighted AND child / Multi_MultiValueKeyMaker sort (see xgm_oracle.h)
+    filter_weighted: bool = False
+    filter_factor: float = 0.0
+    sort_keymaker: bool = False
+    sort_missing: int = 0
 
 
 def _mset_from_c(m: _MSet) -> MSet:
@@ -181,6 +190,10 @@ class Index:
     @classmethod
     def load_flat(cls, path: str) -> "Index":
         return cls(lib().orc_index_load_flat(path.encode()))
+
+    def make_sparse(self, mod0: int, mod1: int):
+        """Drop slot values by the rule of `ref_runner build --mvalues-sparse mod0 mod1`."""
+        lib().orc_index_make_sparse(self._p, mod0, mod1)
 
     def close(self):
         if self._p:
@@ -267,6 +280,8 @@ class Index:
         cq.first, cq.maxitems, cq.check_at_least = q.first, q.maxitems, q.check_at_least
         cq.filter, cq.range_lo, cq.range_hi = q.filter, q.range_lo, q.range_hi
         cq.sort_by, cq.sort_slot, cq.sort_reverse = q.sort_by, q.sort_slot, int(q.sort_reverse)
+        cq.filter_weighted, cq.filter_factor = int(q.filter_weighted), float(q.filter_factor)
+        cq.sort_keymaker, cq.sort_missing = int(q.sort_keymaker), int(q.sort_missing)
         if q.stats is not None:
             tf = (C.c_uint32 * len(q.terms))(*q.stats[2])
             mtf = None
@@ -353,11 +368,15 @@ def have_reference() -> bool:
 
 
 def ref_build(out_dir: str, ndocs: int, vocab: int, seed: int = 12345, nshards: int = 1, shard: int = 0,
-              values: bool = False, env=None) -> dict:
+              values: bool = False, env=None, mvalues: bool = False, sparse=None) -> dict:
     cmd = [REF_RUNNER, "build", "--out", out_dir, "--docs", str(ndocs), "--vocab", str(vocab),
            "--seed", str(seed), "--nshards", str(nshards), "--shard", str(shard)]
     if values:
         cmd.append("--values")
+    if mvalues:  # Xapiand's slot encoding: StringList of Serialise::positive keys
+        cmd.append("--mvalues")
+        if sparse:
+            cmd += ["--mvalues-sparse", str(sparse[0]), str(sparse[1])]
     e = dict(os.environ)
     e.setdefault("XAPIAN_FLUSH_THRESHOLD", "200000")
     if env:
@@ -366,7 +385,8 @@ def ref_build(out_dir: str, ndocs: int, vocab: int, seed: int = 12345, nshards: 
 
 
 def ref_build_parallel(out_dir: str, ndocs: int, vocab: int, seed: int = 12345, procs: int = 8,
-                       values: bool = False, compact: bool = True) -> dict:
+                       values: bool = False, compact: bool = True, mvalues: bool = False, nshards: int = 1,
+                       shard: int = 0) -> dict:
     """Write the corpus as `procs` contiguous docid-range glass DBs in parallel (one writer process
     each), then Database::compact them into one DB whose docids are the corpus docids.  Returns timing
     info; the result lives in out_dir/db (or out_dir/part*/ when compact=False)."""
@@ -388,9 +408,11 @@ def ref_build_parallel(out_dir: str, ndocs: int, vocab: int, seed: int = 12345, 
         d = os.path.join(out_dir, f"part{i:03d}")
         parts.append(d)
         cmd = [REF_RUNNER, "build", "--out", d, "--docs", str(ndocs), "--vocab", str(vocab), "--seed", str(seed),
-               "--range-first", str(a), "--range-last", str(b)]
+               "--range-first", str(a), "--range-last", str(b), "--nshards", str(nshards), "--shard", str(shard)]
         if values:
             cmd.append("--values")
+        if mvalues:
+            cmd.append("--mvalues")
         ps.append(subprocess.Popen(cmd, env=e, stdout=subprocess.DEVNULL))
     for p in ps:
         if p.wait() != 0:
@@ -415,7 +437,8 @@ def ref_build_parallel(out_dir: str, ndocs: int, vocab: int, seed: int = 12345, 
 
 def query_line(op: str, terms: Sequence[str], first: int, maxitems: int, check_at_least: int = 0,
                vr: Optional[tuple] = None, sort: Optional[tuple] = None, filter_terms: Sequence[str] = (),
-               not_terms: Sequence[str] = (), maybe_terms: Sequence[str] = (), bm25: Optional[tuple] = None) -> str:
+               not_terms: Sequence[str] = (), maybe_terms: Sequence[str] = (), bm25: Optional[tuple] = None,
+               mvr: Optional[tuple] = None, keysort: Optional[tuple] = None) -> str:
     s = f"{op} {first} {maxitems} {check_at_least} {len(terms)} " + " ".join(terms)
     for tag, ts in (("FT", filter_terms), ("NOT", not_terms), ("MAYBE", maybe_terms)):
         if ts:
@@ -424,6 +447,10 @@ def query_line(op: str, terms: Sequence[str], first: int, maxitems: int, check_a
         s += " BM25 " + " ".join(repr(float(x)) for x in bm25)
     if vr is not None:
         s += f" VR {vr[0]} {vr[1]} {vr[2]}"
+    if mvr is not None:  # (slot, lo, hi, weighted): Xapiand's MultipleValueRange as OP_FILTER right side / OP_AND child
+        s += f" {'MVRW' if len(mvr) > 3 and mvr[3] else 'MVR'} {mvr[0]} {mvr[1]} {mvr[2]}"
+    if keysort is not None:  # (slot, reverse): Multi_MultiValueKeyMaker{SerialiseKey}, set_sort_by_key_then_relevance
+        s += f" KEYSORT {keysort[0]} {int(keysort[1])}"
     if sort is not None:
         s += f" SORT {sort[0]} {int(sort[1])}"
         if len(sort) > 2 and sort[2]:
@@ -442,6 +469,9 @@ class RefResult:
     ub: int = 0
     max_possible: float = 0.0
     max_attained: float = 0.0
+    served: int = -1      # shim runner only: 1 = libxgm answered, 0 = the reference matcher did
+    flags: int = 0
+    reason: str = ""
 
 
 def parse_dump(path: str) -> List[RefResult]:
@@ -455,6 +485,8 @@ def parse_dump(path: str) -> List[RefResult]:
             if p[0] == "Q":
                 cur = RefResult(lb=int(p[3]), est=int(p[4]), ub=int(p[5]),
                                 max_possible=float(p[6]), max_attained=float(p[7]))
+                if len(p) > 10 and p[8].startswith("S"):
+                    cur.served, cur.flags, cur.reason = int(p[8][1:]), int(p[9][1:]), p[10]
                 out.append(cur)
             else:
                 cur.docids.append(int(p[0]))
@@ -466,20 +498,31 @@ def parse_dump(path: str) -> List[RefResult]:
     return out
 
 
+def have_shim_reference() -> bool:
+    return os.path.exists(REF_RUNNER_XGM) and os.path.exists(os.path.join(REF_DIR, "libxapian_ref_xgm.so"))
+
+
 def ref_query(dbs: Sequence[str], query_lines: Sequence[str], workdir: str, threads: int = 1,
-              twophase: bool = False, repeat: int = 1, warmup: int = 0, dump: bool = True):
+              twophase: bool = False, repeat: int = 1, warmup: int = 0, dump: bool = True, shim: bool = False,
+              env=None):
+    """shim=True: the same driver linked against libxapian_ref_xgm.so — Matcher::get_mset tries libxgm first."""
     os.makedirs(workdir, exist_ok=True)
     qf = os.path.join(workdir, "queries.txt")
     with open(qf, "w") as f:
         f.write("\n".join(query_lines) + "\n")
-    cmd = [REF_RUNNER, "query", "--queries", qf, "--threads", str(threads), "--repeat", str(repeat),
+    e = dict(os.environ)
+    if shim:
+        e.setdefault("XGM_LIB", os.path.join(HERE, "..", "xapiand_b200", "libxgm.so"))
+    if env:
+        e.update(env)
+    cmd = [REF_RUNNER_XGM if shim else REF_RUNNER, "query", "--queries", qf, "--threads", str(threads), "--repeat", str(repeat),
            "--warmup", str(warmup)]
     for d in dbs:
         cmd += ["--db", d]
     if twophase:
         cmd.append("--twophase")
-    df = os.path.join(workdir, "dump.txt")
+    df = os.path.join(workdir, "dump_xgm.txt" if shim else "dump.txt")
     if dump:
         cmd += ["--dump", df]
-    info = json.loads(subprocess.check_output(cmd).decode().strip().splitlines()[-1])
+    info = json.loads(subprocess.check_output(cmd, env=e).decode().strip().splitlines()[-1])
     return info, (parse_dump(df) if dump else None)

@@ -52,6 +52,14 @@ Xapian::KeyMaker* make_key_maker(const std::vector<std::pair<unsigned, bool>>& s
 
 #include "../xapiand_b200/csrc/xgm_corpus.h"
 
+#ifdef XGM_SHIM_RUNNER
+/* linked against oracle/_ref/libxapian_ref_xgm.so: the same reference library with the xgm shim at the
+ * Matcher::get_mset seam (xapiand_b200/shim/xgm_shim.h).  The dump records who answered each query. */
+extern "C" int xgm_shim_last_served(void);
+extern "C" unsigned xgm_shim_last_flags(void);
+extern "C" const char* xgm_shim_last_reason(void);
+#endif
+
 using Clock = std::chrono::steady_clock;
 
 static double now_s() {
@@ -92,6 +100,13 @@ static int cmd_build(const Args& a) {
     uint32_t shard = (uint32_t)strtoul(a.get("--shard", "0").c_str(), nullptr, 10);
     bool values = a.flag("--values");
     bool mvalues = a.flag("--mvalues");
+    /* --mvalues-sparse m0 m1: no slot-0 value where the smallest value is a multiple of m0, no slot-1 value
+     * where it is a multiple of m1 (documents without a value: SerialiseKey's MAX/MIN_STR_CMPVALUE path) */
+    uint32_t sp0 = 0, sp1 = 0;
+    {
+        for (size_t i = 0; i + 2 < a.v.size(); ++i)
+            if (a.v[i] == "--mvalues-sparse") { sp0 = (uint32_t)strtoul(a.v[i + 1].c_str(), nullptr, 10); sp1 = (uint32_t)strtoul(a.v[i + 2].c_str(), nullptr, 10); }
+    }
     uint32_t rfirst = (uint32_t)strtoul(a.get("--range-first", "1").c_str(), nullptr, 10);
     uint32_t rlast = (uint32_t)strtoul(a.get("--range-last", "0").c_str(), nullptr, 10);
     if (rlast == 0 || rlast > N) rlast = N;
@@ -133,8 +148,8 @@ static int cmd_build(const Args& a) {
             /* Xapiand keeps the values of a slot in a std::set of serialised strings and writes
              * StringList::serialise of it (src/database/schema.cc:2958-2959, 5346): sorted, unique */
             ser.erase(std::unique(ser.begin(), ser.end()), ser.end());
-            doc.add_value(0, xgmref::serialise_slot(ser));
-            doc.add_value(1, xgmref::serialise_number((long double)v1));
+            if (!(sp0 && v0[0] % sp0 == 0)) doc.add_value(0, xgmref::serialise_slot(ser));
+            if (!(sp1 && v1 % sp1 == 0)) doc.add_value(1, xgmref::serialise_number((long double)v1));
         }
         Xapian::docid got = db.add_document(doc).did;
         if (got != ++local) die("unexpected docid");
@@ -270,6 +285,9 @@ struct QResult {
     uint32_t lb = 0, est = 0, ub = 0;
     double max_possible = 0, max_attained = 0;
     double seconds = 0;
+    int served = -1;          /* shim runner: 1 = libxgm answered, 0 = the reference matcher did */
+    unsigned flags = 0;
+    std::string reason;
 };
 
 static void setup_enquire(Xapian::Enquire& enq, const QSpec& q) {
@@ -298,6 +316,11 @@ static void collect(const Xapian::MSet& m, QResult& r, bool want_keys) {
     r.ub = m.get_matches_upper_bound();
     r.max_possible = m.get_max_possible();
     r.max_attained = m.get_max_attained();
+#ifdef XGM_SHIM_RUNNER
+    r.served = xgm_shim_last_served();
+    r.flags = xgm_shim_last_flags();
+    r.reason = xgm_shim_last_reason();
+#endif
 }
 
 static int cmd_query(const Args& a) {
@@ -422,8 +445,14 @@ static int cmd_query(const Args& a) {
         if (!f) die("cannot write " + dump);
         for (size_t i = 0; i < res.size(); ++i) {
             const QResult& r = res[i];
-            fprintf(f, "Q %zu %zu %u %u %u %.17g %.17g\n", i, r.items.size(), r.lb, r.est, r.ub,
+            fprintf(f, "Q %zu %zu %u %u %u %.17g %.17g", i, r.items.size(), r.lb, r.est, r.ub,
                     r.max_possible, r.max_attained);
+            if (r.served >= 0) {
+                std::string why = r.reason;
+                for (auto& c : why) if (c == ' ') c = '_';
+                fprintf(f, " S%d F%u %s", r.served, r.flags, why.empty() ? "-" : why.c_str());
+            }
+            fputc('\n', f);
             for (size_t k = 0; k < r.items.size(); ++k) {
                 fprintf(f, "%u %.17g", r.items[k].first, r.items[k].second);
                 if (k < r.sort_keys.size()) {
@@ -490,6 +519,31 @@ static int cmd_export(const Args& a) {
     return 0;
 }
 
+/* ref_runner slots --db DIR: "slot docid hex" of every stored value (Database::valuestream_begin) */
+static int cmd_slots(const Args& a) {
+    Xapian::Database db(a.get("--db"));
+    for (uint32_t s = 0; s < 8; ++s) {
+        if (db.get_value_freq(s) == 0) continue;
+        for (auto v = db.valuestream_begin(s); v != db.valuestream_end(s); ++v) {
+            std::string val = *v;
+            printf("%u %u ", s, v.get_docid());
+            for (unsigned char c : val) printf("%02x", c);
+            printf("\n");
+        }
+    }
+    return 0;
+}
+
+/* ref_runner serialise N...: hex of Xapiand's sortable_serialise (= Serialise::integer / positive / floating) */
+static int cmd_serialise(int argc, char** argv) {
+    for (int i = 2; i < argc; ++i) {
+        std::string s = xgmref::serialise_number(strtold(argv[i], nullptr));
+        for (unsigned char c : s) printf("%02x", c);
+        printf("\n");
+    }
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc < 2) die("usage: ref_runner build|query|export ...");
     Args a;
@@ -500,6 +554,8 @@ int main(int argc, char** argv) {
         if (cmd == "query") return cmd_query(a);
         if (cmd == "export") return cmd_export(a);
         if (cmd == "compact") return cmd_compact(a);
+        if (cmd == "serialise") return cmd_serialise(argc, argv);
+        if (cmd == "slots") return cmd_slots(a);
     } catch (const Xapian::Error& e) {
         die("xapian: " + e.get_description());
     }

@@ -160,6 +160,7 @@ bad:
 }
 
 void orc_index_free(orc_index* ix) {
+    if (ix) free(ix->has1);
     if (!ix) return;
     if (ix->names) for (uint32_t t = 0; t < ix->nterms; ++t) free(ix->names[t]);
     free(ix->names); free(ix->doclen); free(ix->off); free(ix->docids); free(ix->wdfs);
@@ -471,10 +472,31 @@ static int pass_filter(const orc_index* ix, const orc_query* q, uint32_t did) {
 
 static uint64_t sort_value(const orc_index* ix, const orc_query* q, uint32_t did) {
     if (!ix->nvals0) return 0;
+    if (q->sort_keymaker) {
+        /* SerialiseKey::findSmallest / findBiggest, src/multivalue/keymaker.cc:67-92: first / last value of the
+         * slot's StringList, MAX_STR_CMPVALUE / MIN_STR_CMPVALUE when the document has none */
+        switch (q->sort_slot) {
+            case 0: return ix->nvals0[did] ? ix->vals0[3 * (size_t)did] + 1 : q->sort_missing;
+            case 2: return ix->nvals0[did] ? ix->vals0[3 * (size_t)did + ix->nvals0[did] - 1] + 1 : q->sort_missing;
+            default: return (!ix->has1 || ix->has1[did]) ? ix->val1[did] + 1 : q->sort_missing;
+        }
+    }
     switch (q->sort_slot) {
         case 0: return ix->vals0[3 * (size_t)did];
         case 2: return ix->vals0[3 * (size_t)did + (ix->nvals0[did] ? ix->nvals0[did] - 1 : 0)];
         default: return ix->val1[did];
+    }
+}
+
+void orc_index_make_sparse(orc_index* ix, uint32_t mod0, uint32_t mod1) {
+    if (!ix || !ix->nvals0) return;
+    if (!ix->has1) {
+        ix->has1 = (uint8_t*)xcalloc((size_t)ix->lastdocid + 1, 1);
+        memset(ix->has1, 1, (size_t)ix->lastdocid + 1);
+    }
+    for (uint32_t d = 1; d <= ix->lastdocid; ++d) {
+        if (mod0 && ix->nvals0[d] && ix->vals0[3 * (size_t)d] % mod0 == 0) ix->nvals0[d] = 0;
+        if (mod1 && ix->val1[d] % mod1 == 0) ix->has1[d] = 0;
     }
 }
 
@@ -585,8 +607,43 @@ int orc_match(const orc_index* ix, const orc_query* q, orc_mset* out) {
     double max_possible = 0;
     uint32_t tf_min = 0, tf_est = 0, tf_max = 0;
     double dbsize = ix->doccount;
+    uint32_t src_pos = 0xffffffffu; /* place of a weighted range source among the AND's children */
+    double src_w = 0.0;
     if (q->op == ORC_OP_AND) {
         orc_and_order(len, n, order);
+        if (q->filter == ORC_FILTER_MULTI_RANGE && !(q->nfilter || q->nnot || q->nmaybe)) {
+            /* the range source is one more child, sorted in by its termfreq estimate = value_freq */
+            uint32_t vf = 0;
+            if (ix->nvals0) for (uint32_t d = 1; d <= ix->lastdocid; ++d) vf += ix->nvals0[d] != 0;
+            uint32_t* cl = (uint32_t*)xcalloc(n + 1, 4);
+            uint32_t* co = (uint32_t*)xcalloc(n + 1, 4);
+            memcpy(cl, len, n * 4);
+            cl[n] = vf;
+            orc_and_order(cl, n + 1, co);
+            src_w = q->filter_weighted ? (q->filter_factor != 0.0 ? q->filter_factor : 1.0) * 1.0 : 0.0;
+            uint32_t k = 0;
+            for (uint32_t i = 0; i <= n; ++i) { if (co[i] == n) src_pos = k; else order[k++] = co[i]; }
+            for (uint32_t i = 0; i <= n; ++i)
+                max_possible += co[i] == n ? (q->filter_weighted ? src_w * 1.7976931348623157e308 : 0.0) : maxpart[co[i]];
+            #define CH_MIN(i) (co[i] == n ? 0u : cl[co[i]])
+            uint32_t sum = CH_MIN(0);
+            if (sum) {
+                for (uint32_t i = 1; i <= n; ++i) {
+                    uint32_t old = sum;
+                    sum += CH_MIN(i);
+                    if (sum >= old && sum <= ix->doccount) { sum = 0; break; }
+                    sum -= ix->doccount;
+                }
+            }
+            #undef CH_MIN
+            tf_min = sum;
+            tf_max = cl[co[0]];
+            for (uint32_t i = 1; i <= n; ++i) if (cl[co[i]] < tf_max) tf_max = cl[co[i]];
+            double r = cl[co[0]];
+            for (uint32_t i = 1; i <= n; ++i) r = (r * cl[co[i]]) / dbsize;
+            tf_est = ix->doccount ? (uint32_t)(r + 0.5) : 0;
+            free(cl); free(co);
+        } else {
         /* MultiAndPostList::recalc_maxweight matcher/multiandpostlist.cc:161-171: sum in plist order */
         for (uint32_t i = 0; i < n; ++i) max_possible += maxpart[order[i]];
         /* get_termfreq_min/max/est multiandpostlist.cc:55-105 */
@@ -605,6 +662,7 @@ int orc_match(const orc_index* ix, const orc_query* q, orc_mset* out) {
         double r = len[order[0]];
         for (uint32_t i = 1; i < n; ++i) r = (r * len[order[i]]) / dbsize;
         tf_est = ix->doccount ? (uint32_t)(r + 0.5) : 0;
+        }
     } else {
         nprog = orc_or_program(len, n, prog);
         /* OrPostList::recalc_maxweight orpostlist.cc:105-111 (l_max + r_max per node) and
@@ -718,6 +776,7 @@ int orc_match(const orc_index* ix, const orc_query* q, orc_mset* out) {
     uint32_t nweighted = 0; /* leaves with a Weight object: QueryTerm::postlist counts them only when factor != 0 */
     for (uint32_t j = 0; j < n; ++j) nweighted += (!q->factors || q->factors[j] != 0.0) ? 1u : 0u;
     uint32_t total_subqs = nweighted + nm; /* api/queryinternal.cc:1053-1054 */
+    if (q->filter_weighted && q->filter == ORC_FILTER_MULTI_RANGE) ++total_subqs; /* QueryPostingSource::postlist, factor != 0 */
 
     uint64_t* pos = (uint64_t*)xcalloc(n, 8);
     double* stk = (double*)xcalloc(2 * (n + nm) + 2, 8);
@@ -753,8 +812,10 @@ int orc_match(const orc_index* ix, const orc_query* q, orc_mset* out) {
                 doclen = ix->doclen[did];
                 for (uint32_t i = 0; i < n; ++i) {
                     uint32_t j = order[i];
+                    if (q->filter_weighted && src_pos == i) weight += src_w; /* ExternalPostList::get_weight */
                     weight += orc_bm25_sumpart(tw[j], len_factor, q->k1, q->b, q->min_normlen, wl[j][pos[j]], doclen);
                 }
+                if (q->filter_weighted && src_pos == n) weight += src_w;
                 subqs = nweighted;
             } else {
                 /* union in docid order; OrPostList::get_weight matcher/orpostlist.cc:93-103 folds

@@ -39,6 +39,7 @@ typedef struct orc_index {
     uint8_t* nvals0;         /* [lastdocid+1] or NULL */
     uint64_t* vals0;         /* [3*(lastdocid+1)] */
     uint64_t* val1;          /* [lastdocid+1] */
+    uint8_t* has1;           /* [lastdocid+1] slot-1 value present, or NULL = every document has one */
 } orc_index;
 
 /* collection statistics used by Weight::init_ (global over all shards in Xapiand's two-phase
@@ -81,6 +82,19 @@ typedef struct orc_query {
     const uint32_t* not_terms;
     uint32_t nmaybe;
     const uint32_t* maybe_terms;
+    /* Xapiand's range source as a child of the AND (ORC_FILTER_MULTI_RANGE on an AND / single-term base, no
+     * term groups): MultipleValueRange is a ValuePostingSource with termfreq (min, est, max) = (0, value_freq,
+     * value_freq) (src/multivalue/range.cc:457-464, api/postingsource.cc:201-214), sorted into the
+     * MultiAndPostList by that estimate.  filter_weighted: OP_AND(base, source) instead of OP_FILTER — every
+     * match gets filter_factor * 1.0 (range.cc:410-414) at the source's place, max_possible includes
+     * filter_factor * DBL_MAX, and the source is one more of the total subqueries. */
+    int filter_weighted;
+    double filter_factor;
+    /* Xapiand's sorter (Multi_MultiValueKeyMaker with one SerialiseKey): key of a document without a value,
+     * on the oracle's numeric scale where a value v sorts as v + 1: 0 = below everything ("\0", reverse),
+     * UINT64_MAX = above everything ("\xff", forward).  sort_keymaker != 0 selects this scale. */
+    int sort_keymaker;
+    uint64_t sort_missing;
 } orc_query;
 
 typedef struct orc_mset {
@@ -98,6 +112,9 @@ orc_index* orc_index_synthetic(uint32_t N, uint32_t V, uint64_t seed, uint32_t n
                                int with_values);
 orc_index* orc_index_load_flat(const char* path);
 void orc_index_free(orc_index*);
+/* Drop slot-0 values of documents whose smallest value is a multiple of mod0 and slot-1 values that are
+ * multiples of mod1 (0 = keep all) — the rule of `ref_runner build --mvalues-sparse`. */
+void orc_index_make_sparse(orc_index*, uint32_t mod0, uint32_t mod1);
 int orc_term_lookup(const orc_index*, const char* name, uint32_t* id);
 
 void orc_query_defaults(orc_query* q);

@@ -63,6 +63,60 @@ def run_set(tag, ndocs, vocab, queries, nshards=1, twophase=False, values=False,
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def run_mv_set(tag, ndocs, vocab, queries, sparse=(7, 5), seed=12345):
+    """Xapiand's own multivalue classes (oracle/_ref/libxapiand_mv_ref.so = src/multivalue/range.cc, keymaker.cc …
+    compiled from the reference): slots written as StringLists of Serialise::positive keys, MultipleValueRange as
+    OP_FILTER right side or weighted OP_AND child, Multi_MultiValueKeyMaker{SerialiseKey} as the sorter."""
+    import subprocess
+    tmp = tempfile.mkdtemp(prefix="xgm_golden_")
+    try:
+        d = os.path.join(tmp, "db")
+        O.ref_build(d, ndocs, vocab, seed=seed, mvalues=True, sparse=sparse)
+        lines = [O.query_line("TERM" if len(q["terms"]) == 1 else "AND", [name(t) for t in q["terms"]], q["first"],
+                              q["maxitems"], q["check_at_least"], mvr=q.get("mvr"), keysort=q.get("keysort"))
+                 for q in queries]
+        info, res = O.ref_query([d], lines, os.path.join(tmp, "w"))
+        slots = {}
+        for ln in subprocess.check_output([O.REF_RUNNER, "slots", "--db", d]).decode().splitlines():
+            sl, did, hx = (ln.split() + [""])[:3]
+            slots.setdefault(sl, {})[did] = hx
+        nums = sorted({v for q in queries if q.get("mvr") for v in q["mvr"][1:3]})
+        ser = subprocess.check_output([O.REF_RUNNER, "serialise"] + [str(v) for v in nums]).decode().split()
+        fixture = dict(tag=tag, ndocs=ndocs, vocab=vocab, seed=seed, sparse=list(sparse), slots=slots,
+                       serialised=dict(zip(map(str, nums), ser)), queries=[])
+        for q, r in zip(queries, res):
+            e = dict(q)
+            e["docids"] = r.docids
+            e["weights"] = [float(w).hex() for w in r.weights]
+            if r.sort_keys:
+                e["sort_keys"] = r.sort_keys
+            e["percents"] = r.percents
+            e.update(lb=r.lb, est=r.est, ub=r.ub, max_possible=float(r.max_possible).hex(),
+                     max_attained=float(r.max_attained).hex())
+            fixture["queries"].append(e)
+        with open(os.path.join(OUT, f"{tag}.json"), "w") as f:
+            json.dump(fixture, f, separators=(",", ":"))
+        print(tag, len(queries), "queries", os.path.getsize(os.path.join(OUT, f"{tag}.json")), "bytes")
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def mv_queries(rng, n, topranks, ndocs):
+    qs = []
+    for i in range(n):
+        nb = rng.choice([1, 2, 2, 3])
+        q = dict(terms=rng.sample(range(topranks), nb), first=rng.choice([0, 0, 3]), maxitems=rng.choice([5, 10, 100]),
+                 check_at_least=rng.choice([0, 0, ndocs]))
+        lo = rng.randrange(0, 950000)
+        kind = i % 4
+        if kind != 3:  # range source: filter (0, 1) or weighted AND child (2)
+            q["mvr"] = [0, lo, lo + rng.choice([5000, 50000, 300000]), 1 if kind == 2 else 0]
+        if i % 3 != 1:
+            q["keysort"] = [rng.choice([0, 1, 1]), rng.choice([0, 1])]
+        qs.append(q)
+    return qs
+
+
 def mixed(rng, n, topranks, ndocs, big_or_items):
     qs = []
     for i in range(n):
@@ -166,6 +220,9 @@ def bm25_queries(rng, n, topranks, ndocs):
 def main():
     if not O.have_reference():
         raise SystemExit("oracle/_ref not built: run oracle/build_ref.sh (needs /root/reference)")
+    if sys.argv[1:] == ["mv"]:
+        run_mv_set("multivalue_5k", 5000, 2000, mv_queries(random.Random(20260930), 240, 60, 5000))
+        return
     if sys.argv[1:] == ["ops"]:  # only the fixtures added after round 1's first batch
         run_set("ops_6k", 6000, 900, ops_queries(random.Random(20260924), 240, 200, 6000), seed=11)
         run_set("scale_6k", 6000, 900, scale_queries(random.Random(20260925), 200, 200, 6000), seed=11)
@@ -205,6 +262,7 @@ def main():
     run_set("wqf_6k", 6000, 900, wqf_queries(random.Random(20260927), 150, 150, 6000), seed=11)
     run_set("sortmodes_6k", 6000, 900, sortmode_queries(random.Random(20260928), 200, 100, 6000), seed=11, values=True)
     run_set("bm25_6k", 6000, 900, bm25_queries(random.Random(20260929), 200, 150, 6000), seed=11)
+    run_mv_set("multivalue_5k", 5000, 2000, mv_queries(random.Random(20260930), 240, 60, 5000))
 
 
 if __name__ == "__main__":

@@ -24,3 +24,19 @@ def sortable_key_to_int(hexkey: str) -> int:
         return 0
     b = bytes.fromhex(hexkey)
     return int.from_bytes(b.ljust(10, b"\0"), "big")
+
+
+def fixture_query_line(q) -> str:
+    """The oracle/ref_runner query line of a fixture entry (what tests/golden/make_golden.py fed the reference)."""
+    from oracle import oracle as O
+    name = lambda r: f"T{r:06d}"
+    facs, wq = q.get("factors"), q.get("wqf")
+    tnames = [name(t) + ("" if not wq or wq[j] == 1 else f"#{wq[j]}") +
+              ("" if not facs or facs[j] == 1.0 else f"^{facs[j]!r}") for j, t in enumerate(q["terms"])]
+    return O.query_line("TERM" if len(q["terms"]) == 1 else q.get("op", "AND"), tnames, q["first"], q["maxitems"],
+                        q["check_at_least"], vr=q.get("vr"),
+                        sort=(q["sort"] + [q.get("sort_mode", 0)]) if q.get("sort") else None, bm25=q.get("bm25"),
+                        filter_terms=[name(t) for t in q.get("filter_terms", [])],
+                        not_terms=[name(t) for t in q.get("not_terms", [])],
+                        maybe_terms=[name(t) for t in q.get("maybe_terms", [])],
+                        mvr=q.get("mvr"), keysort=q.get("keysort"))

@@ -260,3 +260,46 @@ def test_cuda_matches_reference_more_regimes(tag):
             assert [O.convert_to_percent(w, m.percent_scale_factor) for w in m.weights] == q["percents"], ctx
     assert declined < len(keep) // 4
 
+
+
+def test_cuda_matches_xapiand_multivalue_classes():
+    """SURVEY.md §8 rows a15 / a16 against Xapiand's REAL classes (multivalue_5k fixture: src/multivalue/range.cc,
+    keymaker.cc, serialise_list.h, sortable_serialise.cc compiled from the reference).  The index is built from the
+    slot bytes exactly as Xapiand stores them (xgm_builder_add_value_slot_serialised); range bounds and the
+    missing-value keys go in as value keys of the reference's serialised bytes; MSetIterator::get_sort_key bytes are
+    rebuilt from the device's keys (xgm_sort_key_bytes) and must equal Multi_MultiValueKeyMaker's."""
+    from oracle import oracle as O
+    fx = load("multivalue_5k")
+    orc = O.Index.synthetic(fx["ndocs"], fx["vocab"], fx["seed"])  # the corpus' postings only
+    terms = [(orc.name(t),) + tuple(orc.postings(t)) for t in range(orc.nterms)]
+    last = orc.lastdocid
+    slots = {int(s): [bytes.fromhex(fx["slots"][s].get(str(d), "")) for d in range(last + 1)] for s in fx["slots"]}
+    ix = xgm.Index.from_postings(orc.doclen(), terms, serialised_slots=slots, revision=7)
+    assert ix.info().revision == 7
+    key = lambda v: xgm.value_key(bytes.fromhex(fx["serialised"][str(v)]))[0]
+    qs = []
+    for q in fx["queries"]:
+        kw = dict(first=q["first"], maxitems=q["maxitems"], check_at_least=q["check_at_least"], revision=7)
+        if "mvr" in q:
+            kw.update(filter=xgm.FILTER_MULTI_RANGE, filter_slot=q["mvr"][0], range_lo=key(q["mvr"][1]),
+                      range_hi=key(q["mvr"][2]), filter_weighted=bool(q["mvr"][3]))
+        if "keysort" in q:
+            slot, rev = q["keysort"]
+            kw.update(sort_by=xgm.SORT_VAL_REL, sort_slot=slot, sort_reverse=bool(rev), sort_use_max=bool(rev),
+                      sort_missing_key=xgm.value_key(b"\x00" if rev else b"\xff")[0])
+        qs.append(xgm.Query(xgm.OP_AND, [f"T{t:06d}" for t in q["terms"]], **kw))
+    res = xgm.Searcher(ix, max_batch=len(qs), max_topk=128).search(qs)
+    exact_bounds = 0
+    for i, (q, m) in enumerate(zip(fx["queries"], res)):
+        ctx = f"mv[{i}] {q['terms']} mvr={q.get('mvr')} keysort={q.get('keysort')}"
+        check(m, q, ctx)
+        exact_bounds += not (m.flags & 1)
+        if "keysort" in q:
+            got = [xgm.sort_key_bytes(int(k), bool(q["keysort"][1])).hex() for k in m.sort_keys]
+            assert got == q.get("sort_keys", []), ctx
+        mine = [O.convert_to_percent(w, m.percent_scale_factor) for w in m.weights]
+        assert mine == q["percents"], ctx
+    assert exact_bounds >= len(qs) * 3 // 4
+    # a query that names another revision is refused with XGM_E_STALE (→ Xapian::DatabaseModifiedError)
+    stale = xgm.Searcher(ix, max_batch=1, max_topk=16).search([xgm.Query(xgm.OP_AND, ["T000001"], revision=8)])
+    assert stale[0].status == xgm.E_STALE

@@ -164,3 +164,40 @@ def test_round_estimate_examples():
     assert O.round_estimate(676, 1000, 925) == 900
     assert O.round_estimate(9998, 19159, 18081) == 18000
     assert O.round_estimate(5, 5, 5) == 5
+
+
+def mv_o_query(q):
+    """multivalue_5k fixture → oracle query: Xapiand's MultipleValueRange / Multi_MultiValueKeyMaker shapes."""
+    kw = dict(op=O.OP_AND, terms=q["terms"], first=q["first"], maxitems=q["maxitems"], check_at_least=q["check_at_least"])
+    if "mvr" in q:
+        kw.update(filter=O.FILTER_MULTI_RANGE, range_lo=q["mvr"][1], range_hi=q["mvr"][2], filter_weighted=bool(q["mvr"][3]))
+    if "keysort" in q:
+        slot, rev = q["keysort"]
+        kw.update(sort_by=O.SORT_VAL_REL, sort_slot=1 if slot == 1 else (2 if rev else 0), sort_reverse=bool(rev),
+                  sort_keymaker=True, sort_missing=0 if rev else 2 ** 64 - 1)
+    return O.Query(**kw)
+
+
+def test_oracle_matches_xapiand_multivalue_classes():
+    """SURVEY.md §8 rows a15 / a16 pinned against Xapiand's REAL code: the fixture comes from
+    src/multivalue/range.cc (MultipleValueRange as OP_FILTER right side and as weighted OP_AND child),
+    src/multivalue/keymaker.cc (Multi_MultiValueKeyMaker with a SerialiseKey, forward and reverse, documents
+    without a value) and src/serialise_list.h / src/sortable_serialise.cc slot encodings, compiled from the
+    reference by oracle/build_ref.sh.  Docids, weights, bounds, max_possible / max_attained, percentages."""
+    fx = load("multivalue_5k")
+    ix = O.Index.synthetic(fx["ndocs"], fx["vocab"], fx["seed"], values=True)
+    ix.make_sparse(*fx["sparse"])
+    kinds = set()
+    for i, q in enumerate(fx["queries"]):
+        m = ix.match(mv_o_query(q))
+        check(m, q, f"mv[{i}] {q['terms']} mvr={q.get('mvr')} keysort={q.get('keysort')}")
+        kinds.add((q.get("mvr", [0, 0, 0, -1])[3], tuple(q.get("keysort", ()))))
+        if "keysort" in q:  # same order relation between consecutive sort keys (byte strings vs the oracle's scale)
+            keys = [bytes.fromhex(k) for k in q.get("sort_keys", [])]
+            mine = list(m.sortvals)
+            rev = bool(q["keysort"][1])
+            for a in range(len(keys) - 1):
+                # reverse keys are complemented: ascending bytes = descending values
+                assert (keys[a] < keys[a + 1]) == ((mine[a] > mine[a + 1]) if rev else (mine[a] < mine[a + 1])), i
+                assert (keys[a] == keys[a + 1]) == (mine[a] == mine[a + 1]), i
+    assert len(kinds) >= 10

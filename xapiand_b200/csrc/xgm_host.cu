@@ -416,8 +416,9 @@ extern "C" size_t xgm_value_key_bytes(uint64_t key, unsigned char out[8]) {
  * bytewise from 0xff, '\0' becoming "\xff\0", and followed by "\xff\xff" (:733-743). */
 extern "C" size_t xgm_sort_key_bytes(uint64_t key, int reverse, unsigned char out[20]) {
     unsigned char v[8];
-    const size_t n = xgm_value_key_bytes(key, v);
+    size_t n = xgm_value_key_bytes(key, v);
     size_t o = 0;
+    if (reverse && key == 0) { v[0] = 0; n = 1; } /* MIN_STR_CMPVALUE "\0": a document without a value (keymaker.cc:82-86) */
     if (!reverse) {
         for (size_t i = 0; i < n; ++i) out[o++] = v[i];
         return o;
@@ -1810,7 +1811,7 @@ static void finish_info(const PlannedQuery& pq, const XgmDevResult* dr, const do
         if (dr->flags & 8u) o->flags |= XGM_MSET_BOUNDS_APPROX | XGM_MSET_COUNT_LOWER_BOUND;
         /* with a value-range source in the AND the reference's lower bound / estimate also fold in
          * ValueRangePostList::get_termfreq_est (valuerangepostlist.cc:70-130), which is not restated */
-        if (pq.filter && size == pq.topk && known >= pq.check_at_least) o->flags |= XGM_MSET_BOUNDS_APPROX;
+        if (pq.filter && !pq.mv_source && size == pq.topk && known >= pq.check_at_least) o->flags |= XGM_MSET_BOUNDS_APPROX;
     } else if (pq.check_at_least != 0) {
         lb = est = ub = 0; /* empty result set: !full() branch */
     }
