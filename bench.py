@@ -4,6 +4,7 @@ BM25 top-100 (config C2), at 1/2/4/8 B200.
 
     python bench.py --gpus N --steps K --warmup W            our CUDA path (torchrun for N>1)
     python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU Enquire::get_mset
+    python bench.py --config C3|C5|C4 ...                    the other BASELINE.json configurations (default C2)
 
 A "step" is one pass of the hot path over one batch of BATCH synthetic queries.
   value  — whole-job queries/s with the batch's plan already resident in HBM (device-timed with CUDA
@@ -12,9 +13,11 @@ A "step" is one pass of the hot path over one batch of BATCH synthetic queries.
            buffers: host planning, H2D of the plan, kernels, D2H of the MSets all inside the timed region.
   roofline — decode+intersect+score kernel: algorithmic bytes / its CUDA-event time.
   cpu_baseline — the compiled reference (oracle/_ref) on the box's host cores, rank 0, N=1 only.
+  parity — N=1: the (docid, weight) dump of the compiled reference on the SAME 10M-doc corpus against the CUDA MSets.
 N>1 is strong scaling: the same 10M-doc corpus split into N interleaved docid shards (Xapian's own
-scheme, backends/multi.h:37-70), every query runs on every shard with global statistics, and the
-per-GPU top-k are merged after a single NCCL all-gather (Matcher::merge_mset semantics).
+scheme, backends/multi.h:37-70), every query runs on every shard with global statistics (exchanged per
+batch, inside the e2e region), and the per-GPU top-k are merged after one all-to-all: every rank merges
+and returns the MSets of its 1/N of the batch (Matcher::merge_mset semantics).
 """
 from __future__ import annotations
 
@@ -36,21 +39,76 @@ VOCAB = int(os.environ.get("XGM_BENCH_VOCAB", 1_000_000))
 SEED = 12345
 QSEED = 777
 TOPRANKS = 1000
-NTERMS = 3
-TOPK = 100
-BATCH = int(os.environ.get("XGM_BENCH_BATCH", 4096))
-REF_QUERIES_PER_STEP = int(os.environ.get("XGM_BENCH_REF_QUERIES", 1024))
-METRIC = "queries/sec, 10M-doc 3-term AND BM25 top-100"
 UNIT = "queries/s"
 
+# BASELINE.json's configurations.  C2 is the one `metric` is quoted on and the default;
+# the others are run with --config and their lines kept under profiles/.
+CONFIGS = {
+    "C2": dict(metric="queries/sec, 10M-doc 3-term AND BM25 top-100", op="AND", nterms=3, topk=100, batch=4096,
+               workload="C2: 10M docs, V=1M Zipf(1) terms, 3-term OP_AND, BM25, get_mset(0,100)",
+               kernel="xgm_and_bm3_kernel (decode driver + bitmap intersect + BM25)", ref_queries=1024, parity=1024),
+    "C3": dict(metric="queries/sec, 10M-doc 5-term OR BM25 top-1000", op="OR", nterms=5, topk=1000, batch=512,
+               workload="C3: 10M docs, V=1M Zipf(1) terms, 5-term OP_OR, BM25, get_mset(0,1000)",
+               kernel="xgm_or_kernel (owner-leaf union + tree-order BM25)", ref_queries=256, parity=200),
+    "C5": dict(metric="queries/sec, 10M-doc 2-term AND + multivalue range filter + sort by value, top-100", op="AND",
+               nterms=2, topk=100, batch=4096, values=True,
+               workload=("C5: 10M docs, OP_FILTER(2-term OP_AND, Xapiand MultipleValueRange(slot 0, [lo, lo+1e4])), "
+                         "Multi_MultiValueKeyMaker(slot 1) then relevance, get_mset(0,100)"),
+               kernel="xgm_and_bm3_kernel (decode driver + bitmap intersect + range predicate + BM25)",
+               ref_queries=1024, parity=256),
+    "C4": dict(metric="queries/sec, 100M-doc (8 shards) 3-term AND BM25 top-100", op="AND", nterms=3, topk=100, batch=4096,
+               docs=int(os.environ.get("XGM_BENCH_C4_DOCS", 100_000_000)), shards=8,
+               workload="C4: 100M docs in 8 interleaved shards, 3-term OP_AND, BM25, get_mset(0,100), two-phase statistics",
+               kernel="xgm_and_bm3_kernel (decode driver + bitmap intersect + BM25)", ref_queries=0, parity=0),
+}
+BATCH_ENV = os.environ.get("XGM_BENCH_BATCH")
+REF_Q_ENV = os.environ.get("XGM_BENCH_REF_QUERIES")
 
-def gen_query_terms(step: int, n: int):
+
+def config(name):
+    c = dict(CONFIGS[name])
+    c["name"] = name
+    c.setdefault("docs", NDOCS)
+    c.setdefault("values", False)
+    if BATCH_ENV:
+        c["batch"] = int(BATCH_ENV)
+    if REF_Q_ENV:
+        c["ref_queries"] = int(REF_Q_ENV)
+    return c
+
+
+def gen_queries(cfg, step: int, n: int):
+    """n queries of the configuration: term ranks drawn uniformly from [0, 1000) without repetition
+    (SURVEY.md section 8d); C5 adds a range [lo, lo + 1e4] over slot 0."""
     rng = random.Random(QSEED * 1000003 + step)
-    return [rng.sample(range(TOPRANKS), NTERMS) for _ in range(n)]
+    out = []
+    for _ in range(n):
+        t = rng.sample(range(TOPRANKS), cfg["nterms"])
+        lo = rng.randrange(0, 990000) if cfg["name"] == "C5" else None
+        out.append((t, lo))
+    return out
 
 
 def term_name(r: int) -> str:
     return f"T{r:06d}"
+
+
+def xgm_query(cfg, q, stats=None, check_at_least=0):
+    from xapiand_b200 import xgm
+    terms, lo = q
+    kw = dict(first=0, maxitems=cfg["topk"], check_at_least=check_at_least, stats=stats)
+    if lo is not None:
+        # numeric keys of the synthetic index are order-isomorphic to the serialised bytes the reference compares
+        kw.update(filter=xgm.FILTER_MULTI_RANGE, filter_slot=0, range_lo=lo, range_hi=lo + 10000,
+                  sort_by=xgm.SORT_VAL_REL, sort_slot=1, sort_reverse=False, sort_missing_key=2 ** 64 - 1)
+    return xgm.Query(xgm.OP_AND if cfg["op"] == "AND" else xgm.OP_OR, [term_name(t) for t in terms], **kw)
+
+
+def ref_query_line(cfg, q, check_at_least=0):
+    from oracle import oracle as O
+    terms, lo = q
+    return O.query_line(cfg["op"], [term_name(t) for t in terms], 0, cfg["topk"], check_at_least,
+                        mvr=None if lo is None else (0, lo, lo + 10000, 0), keysort=None if lo is None else (1, 0))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -194,73 +252,133 @@ def measured_peak_gbs():
 # reference arm / cpu baseline: the compiled reference's Enquire::get_mset on host cores
 # ---------------------------------------------------------------------------------------------
 
-def ref_db_dir():
+def ref_db_dir(cfg=None):
     base = os.environ.get("XGM_REF_DB_DIR") or ("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp")
-    return os.path.join(base, f"xgm_refdb_{NDOCS}_{VOCAB}_{SEED}")
+    return os.path.join(base, f"xgm_refdb_mv_{NDOCS}_{VOCAB}_{SEED}")
 
 
 def ref_cores():
+    """Host threads the reference arm may use: the scheduler affinity, capped by the cgroup CPU quota
+    (a container can see 128 CPUs and be allowed 16)."""
     try:
-        return len(os.sched_getaffinity(0))
+        aff = len(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        aff = os.cpu_count() or 1
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = int(q) / int(per)
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    n = aff if quota is None else max(1, min(aff, int(quota)))
+    return n, {"affinity": aff, "cgroup_quota": quota}
 
 
 def build_reference_db():
+    """The 10M-doc glass DB of C2 / C3 / C5, written by the reference's own WritableDatabase: value slots the way
+    Xapiand stores them (--mvalues), so that one DB serves every configuration."""
     from oracle import oracle as O
     if not O.have_reference():
         raise RuntimeError("oracle/_ref missing: the reference was not built (oracle/build_ref.sh)")
-    procs = min(ref_cores(), 128)
-    return O.ref_build_parallel(ref_db_dir(), NDOCS, VOCAB, seed=SEED, procs=procs)
+    procs = min(ref_cores()[0], 128)
+    return O.ref_build_parallel(ref_db_dir(), NDOCS, VOCAB, seed=SEED, procs=procs, mvalues=True)
 
 
-def run_reference_queries(dbs, nqueries: int, steps: int, warmup: int, threads: int):
-    """Each step = nqueries queries of the bench workload, all host threads, timing only get_mset."""
+def run_reference_queries(cfg, dbs, nqueries: int, steps: int, warmup: int, threads: int, dump=False, step0=0,
+                          check_at_least=0):
+    """Each step = nqueries queries of the workload over all host threads.  Every thread opens its own
+    Xapian::Database + Enquire before the first pass (oracle/ref_runner.cc); the wall clock of a pass covers
+    Enquire::set_query + get_mset + reading the MSet."""
     from oracle import oracle as O
-    work = os.path.join(ref_db_dir(), "work")
-    terms = gen_query_terms(0, nqueries)
-    lines = [O.query_line("AND", [term_name(t) for t in q], 0, TOPK) for q in terms]
-    info, _ = O.ref_query(dbs, lines, work, threads=threads, repeat=steps, warmup=max(1, warmup), dump=False)
-    return info
+    work = os.path.join(ref_db_dir(), f"work_{cfg['name']}_{os.getpid()}")
+    lines = [ref_query_line(cfg, q, check_at_least) for q in gen_queries(cfg, step0, nqueries)]
+    return O.ref_query(dbs, lines, work, threads=threads, repeat=steps, warmup=max(1, warmup), dump=dump)
 
 
-def single_thread_baseline(dbs):
-    """SURVEY.md §8(d) asks for the reference at (i) one thread and (ii) all cores: the one-thread leg, on a
+def single_thread_baseline(cfg, dbs):
+    """SURVEY.md section 8(d) asks for the reference at (i) one thread and (ii) all cores: the one-thread leg, on a
     small bounded sample (a few seconds)."""
-    n = int(os.environ.get("XGM_BENCH_REF_QUERIES_1T", 256))
+    n = int(os.environ.get("XGM_BENCH_REF_QUERIES_1T", 256 if cfg["name"] != "C3" else 48))
     try:
-        info = run_reference_queries(dbs, n, 1, 1, 1)
+        info, _ = run_reference_queries(cfg, dbs, n, 1, 1, 1)
         return {"value": info["qps"], "unit": UNIT, "cores": 1, "p50_ms": info["p50_ms"], "p99_ms": info["p99_ms"],
                 "sample": f"1 pass of {n} queries of the same workload, one thread"}
     except Exception as e:  # reported, never required
         return {"value": None, "unit": UNIT, "cores": 1, "sample": f"unavailable: {e}"}
 
 
+def ref_queries_per_step(cfg, cores):
+    """At least 64 queries per thread and step, so that thread start-up and the slowest query's tail do not
+    dominate a step."""
+    return max(cfg["ref_queries"], 64 * cores)
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    cfg = config(args.config)
+    if cfg["name"] == "C4":
+        print(json.dumps({"impl": "reference", "unavailable": "C4 (100M docs) reference DB is not built inside bench.py"}))
+        return 0
     t0 = time.time()
     binfo = build_reference_db()
-    cores = ref_cores()
-    info = run_reference_queries(binfo["dbs"], REF_QUERIES_PER_STEP, args.steps, args.warmup, cores)
+    cores, cinfo = ref_cores()
+    nq = ref_queries_per_step(cfg, cores) if not REF_Q_ENV else cfg["ref_queries"]
+    info, _ = run_reference_queries(cfg, binfo["dbs"], nq, args.steps, args.warmup, cores)
     qps = info["qps"]
     ms_per_step = info["wall_s"] / args.steps * 1e3
-    sample = (f"{REF_QUERIES_PER_STEP} queries/step of the same workload on the full {NDOCS}-doc glass DB "
+    sample = (f"{nq} queries/step of the same workload on the full {NDOCS}-doc glass DB "
               f"(built by {binfo['procs']} parallel WritableDatabase writers + Database::compact), "
-              f"{cores} threads each with its own Xapian::Database+Enquire, timing Enquire::get_mset only")
-    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus,
+              f"{cores} threads each with its own Xapian::Database+Enquire opened before the timed passes")
+    line = {"impl": "reference", "metric": cfg["metric"], "value": qps, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2: 10M docs, V=1M Zipf(1) terms, 3-term OP_AND, BM25, get_mset(0,100)",
-                       "docs": NDOCS, "vocab": VOCAB, "queries_per_step": REF_QUERIES_PER_STEP, "topk": TOPK},
+            "config": {"workload": cfg["workload"], "docs": NDOCS, "vocab": VOCAB, "queries_per_step": nq,
+                       "topk": cfg["topk"]},
             "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample,
-                             "p50_ms": info["p50_ms"], "p99_ms": info["p99_ms"],
-                             "single_thread": single_thread_baseline(binfo["dbs"])},
+                             "cores_detail": cinfo, "p50_ms": info["p50_ms"], "p99_ms": info["p99_ms"],
+                             "single_thread": single_thread_baseline(cfg, binfo["dbs"])},
             "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "setup_s": round(time.time() - t0, 1)}
     print(json.dumps(line))
     return 0
+
+
+def parity_against_reference(cfg, dbs, searcher, cores):
+    """the (docid, %.17g weight) dump of the compiled reference on the bench corpus itself
+    against the CUDA MSets of the same queries — docids identical in order, weights bit-equal."""
+    import struct
+    from xapiand_b200 import xgm
+    n = cfg["parity"]
+    if n == 0:
+        return None
+    out = {"checked": 0, "mismatches": 0, "bounds_approx": 0, "declined": 0, "against": "compiled reference, full corpus"}
+    legs = [0] if cfg["name"] != "C3" else [0, NDOCS]  # C3 also with check_at_least = N (SURVEY.md section 8d)
+    for cal in legs:
+        qs = gen_queries(cfg, 12345, n)
+        _, ref = run_reference_queries(cfg, dbs, n, 1, 0, cores, dump=True, step0=12345, check_at_least=cal)
+        res = searcher.search([xgm_query(cfg, q, check_at_least=cal) for q in qs])
+        for r, m in zip(ref, res):
+            out["checked"] += 1
+            if m.status != 0:
+                out["declined"] += 1
+                continue
+            same = list(m.docids) == r.docids and all(struct.pack("<d", a) == struct.pack("<d", b) for a, b in zip(m.weights, r.weights))
+            same = same and m.matches_upper_bound == r.ub
+            if not (m.flags & 1):
+                same = same and (m.matches_lower_bound, m.get_matches_estimated()) == (r.lb, r.est)
+            else:
+                out["bounds_approx"] += 1
+            out["mismatches"] += 0 if same else 1
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -281,6 +399,8 @@ def ours(args):
     import torch.distributed as dist
     from xapiand_b200 import xgm
 
+    cfg = config(args.config)
+    BATCH, TOPK = cfg["batch"], cfg["topk"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -289,6 +409,10 @@ def ours(args):
             raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libxgm has no CPU path")
+    if cfg["name"] == "C4" and world != cfg["shards"]:
+        raise SystemExit(f"--config C4 is the {cfg['shards']}-shard configuration: launch it with --gpus {cfg['shards']}")
+    if BATCH % world:
+        raise SystemExit("the batch must divide evenly over the ranks")
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -299,55 +423,78 @@ def ours(args):
         torch.cuda.synchronize()
 
     t_setup = time.time()
-    ix = xgm.Index.synthetic(NDOCS, VOCAB, seed=SEED, nshards=world, shard=rank, device=local_rank)
+    threads = max(4, (os.cpu_count() or 8) // max(1, world))
+    ix = xgm.Index.synthetic(cfg["docs"], VOCAB, seed=SEED, nshards=world, shard=rank, values=cfg["values"],
+                             device=local_rank, host_threads=min(64, threads))
     info = ix.info()
     build_s = time.time() - t_setup
+    L = xgm.lib()
 
-    # ---- global statistics (phase 1 of Xapiand's two-phase scheme, handler.cc:1532-1538) ----
-    def make_batch(step: int):
-        terms = gen_query_terms(step, BATCH)
-        stats_list = None
-        if world > 1:
-            uniq = sorted({t for q in terms for t in q})
-            local_tf = torch.tensor([ix.term_stats(term_name(t)).termfreq for t in uniq], dtype=torch.int64, device="cuda")
-            totals = torch.tensor([info.doccount, info.total_length], dtype=torch.int64, device="cuda")
-            dist.all_reduce(local_tf)
-            dist.all_reduce(totals)
-            gtf = dict(zip(uniq, local_tf.tolist()))
-            coll, tlen = totals.tolist()
-            stats_list = [(coll, tlen, [gtf[t] for t in q]) for q in terms]
-        qs = [xgm.Query(xgm.OP_AND, [term_name(t) for t in q], first=0, maxitems=TOPK,
-                        stats=None if stats_list is None else stats_list[i]) for i, q in enumerate(terms)]
-        return xgm.QueryBatch(qs)
+    # ---- batches: queries marshalled once; for N > 1 their global statistics are filled in per step ----
+    nbatches = max(args.warmup, 3) + args.steps + 2
+    raw = [gen_queries(cfg, i, BATCH) for i in range(nbatches)]
+    batches = [xgm.QueryBatch([xgm_query(cfg, q) for q in qs]) for qs in raw]
+    if world > 1:
+        # phase 1 of Xapiand's two-phase scheme (src/database/handler.cc:1532-1538, weightinternal.cc:54-72) per batch:
+        # local termfreq of every distinct query term (one C call), ONE all-reduce of (termfreqs, doccount,
+        # total_length), then the sums go into the batch's statistics blocks.  All of it is inside the e2e region.
+        names = [term_name(r) for r in range(TOPRANKS)]
+        name_arr = [n.encode() for n in names]
+        term_idx = [np.array([q[0] for q in qs], np.int64) for qs in raw]
+        uniq = [np.unique(t) for t in term_idx]
+        for b in batches:
+            b.attach_global_stats()
+        stat_buf = torch.zeros(TOPRANKS + 2, dtype=torch.int64, device="cuda")
+        stat_host = torch.zeros(TOPRANKS + 2, dtype=torch.int64).pin_memory()
+
+        def exchange_stats(bi: int):
+            u = uniq[bi]
+            tf = ix.term_freqs([name_arr[i] for i in u])
+            stat_host.zero_()
+            stat_host[:TOPRANKS][torch.from_numpy(u)] = torch.from_numpy(tf.astype(np.int64))
+            stat_host[TOPRANKS] = int(info.doccount)
+            stat_host[TOPRANKS + 1] = int(info.total_length)
+            stat_buf.copy_(stat_host, non_blocking=True)
+            dist.all_reduce(stat_buf)
+            g = stat_buf.cpu().numpy()
+            batches[bi].set_global_stats(int(g[TOPRANKS]), int(g[TOPRANKS + 1]), g[:TOPRANKS][term_idx[bi]].astype(np.uint32))
+    else:
+        def exchange_stats(bi: int):
+            return None
 
     NSEARCH = 3  # batches in flight in the end-to-end loop (host planning / GPU / result scatter overlap)
     searchers = [xgm.Searcher(ix, max_batch=BATCH, max_topk=TOPK) for _ in range(NSEARCH)]
     streams = [torch.cuda.ExternalStream(s.stream(), device=torch.device("cuda", local_rank)) for s in searchers]
-    L = xgm.lib()
 
-    # merge buffers for N > 1: ONE all-gather of each GPU's result slab (weights | docids | counts of its
-    # per-query top-k), then the merge kernel (Matcher::merge_mset) on every rank
+    # ---- N > 1: the merge.  Rank r owns queries [r*BATCH/N, (r+1)*BATCH/N): one all-to-all moves every shard's
+    # top-k of those queries to r (three regions of the result slab: weights | docids | records), r merges them
+    # (Matcher::merge_mset, unshard included) and copies ITS slice of the merged MSets to the host. ----
+    QL = BATCH // world
     if world > 1:
-        gathered = []
+        xbuf = []
         for s in searchers:
             base, nbytes, off_d, off_c, stride = s.device_slab()
-            local = torch.as_tensor(CudaArray(base, (nbytes,), "|u1"), device="cuda")
-            g = torch.empty(world * nbytes, dtype=torch.uint8, device="cuda")
-            ow = torch.empty(BATCH * TOPK, dtype=torch.float64, device="cuda")
-            od = torch.empty(BATCH * TOPK, dtype=torch.int32, device="cuda")
-            on = torch.empty(BATCH, dtype=torch.int32, device="cuda")
-            gathered.append((local, g, nbytes, off_d, off_c, ow, od, on, stride))
-        host_out = [(torch.empty(BATCH * TOPK, dtype=torch.float64).pin_memory(),
-                     torch.empty(BATCH * TOPK, dtype=torch.int32).pin_memory(),
-                     torch.empty(BATCH, dtype=torch.int32).pin_memory()) for _ in searchers]
+            assert stride == TOPK
+            lw = torch.as_tensor(CudaArray(base, (BATCH * TOPK * 8,), "|u1"), device="cuda")
+            ld = torch.as_tensor(CudaArray(base + off_d, (BATCH * TOPK * 4,), "|u1"), device="cuda")
+            li = torch.as_tensor(CudaArray(base + off_c, (BATCH * 32,), "|u1"), device="cuda")
+            gw, gd, gi = torch.empty_like(lw), torch.empty_like(ld), torch.empty_like(li)
+            ow = torch.empty(QL * TOPK, dtype=torch.float64, device="cuda")
+            od = torch.empty(QL * TOPK, dtype=torch.int32, device="cuda")
+            on = torch.empty(QL, dtype=torch.int32, device="cuda")
+            xbuf.append((lw, ld, li, gw, gd, gi, ow, od, on))
+        host_out = [(torch.empty(QL * TOPK, dtype=torch.float64).pin_memory(),
+                     torch.empty(QL * TOPK, dtype=torch.int32).pin_memory(),
+                     torch.empty(QL, dtype=torch.int32).pin_memory()) for _ in searchers]
 
     def merge_step(si: int, to_host: bool):
-        """all-gather + merge on the searcher's stream; optionally copy the merged MSets to the host."""
-        local, g, nbytes, off_d, off_c, ow, od, on, stride = gathered[si]
+        lw, ld, li, gw, gd, gi, ow, od, on = xbuf[si]
         with torch.cuda.stream(streams[si]):
-            dist.all_gather_into_tensor(g, local)
-            st = L.xgm_merge_topk_device_slab(g.data_ptr(), nbytes, off_d, off_c, world, BATCH, stride, TOPK,
-                                              ow.data_ptr(), od.data_ptr(), on.data_ptr(), searchers[si].stream())
+            dist.all_to_all_single(gw, lw)
+            dist.all_to_all_single(gd, ld)
+            dist.all_to_all_single(gi, li)
+            st = L.xgm_merge_topk_device(gw.data_ptr(), gd.data_ptr(), gi.data_ptr(), world, QL, TOPK, TOPK,
+                                         ow.data_ptr(), od.data_ptr(), on.data_ptr(), searchers[si].stream())
             if st != 0:
                 raise RuntimeError(L.xgm_last_error().decode())
             if to_host:
@@ -357,14 +504,17 @@ def ours(args):
                 hn.copy_(on, non_blocking=True)
 
     # ---- warm-up: W steps through the full API (also makes the plan of batch 0 resident) ----
-    batches = [make_batch(i) for i in range(max(args.warmup, 1) + args.steps + 1)]
-    for w in range(max(args.warmup, 3)):
+    W = max(args.warmup, 3)
+    for w in range(W):
         for si, srch in enumerate(searchers):  # every searcher (staging buffers, worker thread) is warmed up
-            srch.submit(batches[w % len(batches)], background=True)
+            bi = w % nbatches
+            exchange_stats(bi)
+            srch.submit(batches[bi], background=True)
             if world > 1:
                 srch.launched()
                 merge_step(si, True)
             srch.wait_raw()
+    exchange_stats(0)
     if world > 1:  # the device-resident loop alternates between two searchers holding the same resident plan
         searchers[1].submit(batches[0])
         searchers[1].wait_raw()
@@ -373,6 +523,7 @@ def ours(args):
     bad = sum(1 for i in range(BATCH) if inf0[i].status != 0)
     if bad:
         raise SystemExit(f"{bad} queries of the bench batch were not answered on the device")
+    approx0 = sum(1 for i in range(BATCH) if inf0[i].flags & 1)
     st0 = searchers[0].last_stats()
     barrier()
 
@@ -385,12 +536,12 @@ def ours(args):
     sampler.start()
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
-    match_ms = []
+    match_ms, topk_ms = [], []
     barrier()
     sampler.begin()
     ev0.record(streams[0])
     for k in range(args.steps):
-        # N > 1: the all-gather + merge of step k (searcher k%2's stream) overlaps the kernels of step k+1
+        # N > 1: the exchange + merge of step k (searcher k%2's stream) overlaps the kernels of step k+1
         # (the index's compute stream), consecutive steps being independent batches
         si = k % 2 if world > 1 else 0
         searchers[si].replay()
@@ -408,7 +559,19 @@ def ours(args):
     # per-launch time of the dominant kernel: K more replays, reading each launch's own events
     for k in range(args.steps):
         searchers[0].replay()
-        match_ms.append(searchers[0].last_stats().match_kernel_ms)
+        ls = searchers[0].last_stats()
+        match_ms.append(ls.match_kernel_ms)
+        topk_ms.append(ls.topk_kernel_ms)
+    xchg_ms = None
+    if world > 1:  # the exchange + merge alone, for the "what bounds the step" note
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(streams[0])
+        for k in range(args.steps):
+            merge_step(0, False)
+        e1.record(streams[0])
+        torch.cuda.synchronize()
+        xchg_ms = e0.elapsed_time(e1) / args.steps
     torch.cuda.synchronize()
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -421,16 +584,20 @@ def ours(args):
     sampler.begin()
     t0 = time.perf_counter()
     inflight = []
-    h2d = d2h = 0
     prev = None
+    stats_s = 0.0
     for k in range(args.steps):
         si = k % NSEARCH
+        bi = W + 1 + k
         if len(inflight) == NSEARCH:
             searchers[inflight.pop(0)].wait_raw()
+        ts = time.perf_counter()
+        exchange_stats(bi)  # N > 1: phase-1 statistics of THIS batch (lookups + all-reduce + fill-in)
+        stats_s += time.perf_counter() - ts
         # the searcher's worker thread plans + enqueues batch k while this thread scatters an earlier one
-        searchers[si].submit(batches[1 + k], background=True)
+        searchers[si].submit(batches[bi], background=True)
         if world > 1 and prev is not None:
-            # all-gather + merge of the previous batch: its kernels were enqueued while we were busy above
+            # exchange + merge of the previous batch: its kernels were enqueued while we were busy above
             searchers[prev].launched()
             merge_step(prev, True)
         prev = si
@@ -452,15 +619,15 @@ def ours(args):
     bs = searchers[pending].last_stats()
     h2d, d2h = int(bs.h2d_bytes), int(bs.d2h_bytes)
     if world > 1:
-        d2h += BATCH * TOPK * 12 + BATCH * 4
+        h2d += (TOPRANKS + 2) * 8
+        d2h += QL * TOPK * 12 + QL * 4 + (TOPRANKS + 2) * 8
     clocks = sampler.stop()
     e2e_value = BATCH * args.steps / e2e_s
 
     # ---- p50 latency at batch = 1 through the C-ABI (rank-local) ----
     lat = []
     one = xgm.Searcher(ix, max_batch=1, max_topk=TOPK)
-    singles = [xgm.QueryBatch([xgm.Query(xgm.OP_AND, [term_name(t) for t in q], maxitems=TOPK)])
-               for q in gen_query_terms(999, 200)]
+    singles = [xgm.QueryBatch([xgm_query(cfg, q)]) for q in gen_queries(cfg, 999, 200)]
     for b in singles[:20]:
         one.submit(b); one.wait_raw()
     for b in singles:
@@ -475,50 +642,66 @@ def ours(args):
     alg_bytes = int(st0.algorithmic_bytes)
     kern_ms = statistics.mean(match_ms)
     achieved = alg_bytes / 1e9 / (kern_ms / 1e3)
-    launches_per_step = int(st0.kernel_launches) + (1 if world > 1 else 0)
+    launches_per_step = int(st0.kernel_launches) + (4 if world > 1 else 0)
 
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_and_bm_kernel.json")
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", f"r2_{cfg['name'].lower()}_match_kernel.json")
     if os.path.exists(tp) and world == 1:
         try:
             prof = json.load(open(tp))
-            if prof.get("queries_per_launch") == BATCH:
+            # the capture is only a cross-reference while the kernel source is the one it was taken from
+            import hashlib
+            src = open(os.path.join(ROOT, "xapiand_b200", "csrc", "xgm_kernels.cu"), "rb").read()
+            if prof.get("queries_per_launch") == BATCH and prof.get("kernels_sha16") == hashlib.sha256(src).hexdigest()[:16]:
                 traffic = prof["dram_bytes_read"] + prof["dram_bytes_write"]
+                traffic_src = f"profiles/{os.path.basename(tp)} (ncu dram__bytes_read+write of one launch, same kernel source hash)"
         except Exception:
             pass
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2: 10M docs, V=1M Zipf(1) terms, 3-term OP_AND, BM25, get_mset(0,100)",
-                       "docs": NDOCS, "vocab": VOCAB, "queries_per_step": BATCH, "topk": TOPK,
-                       "shards": world, "shard_docs": int(info.doccount),
+    step_parts = {"match_kernel_ms": kern_ms, "topk_kernel_ms": statistics.mean(topk_ms), "host_plan_ms": float(bs.host_plan_ms),
+                  "host_scatter_ms": float(bs.host_wait_ms)}
+    if world > 1:
+        step_parts.update(exchange_merge_ms=xchg_ms, stats_exchange_ms=stats_s / args.steps * 1e3)
+    bound = max(step_parts, key=lambda k: step_parts[k] or 0.0)
+    line = {"metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": W, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if cfg["name"] != "C4" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "docs": cfg["docs"], "vocab": VOCAB, "queries_per_step": BATCH,
+                       "topk": TOPK, "shards": world, "shard_docs": int(info.doccount),
                        "cache": "inputs larger than L2: one step streams %.0f MB of posting columns (L2 = 126 MB)" % (alg_bytes / 1e6),
                        "index_bytes": int(info.bytes_docids + info.bytes_wdfs + info.bytes_headers + info.bytes_doclen),
-                       "index_build_s": round(build_s, 1)},
+                       "index_build_s": round(build_s, 1),
+                       "value_is": "device-resident replay of one planned batch (kernel throughput); e2e is the end-to-end number"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s / args.steps * 1e3, "p50_ms_batch1": lat[len(lat) // 2],
-                    "p99_ms_batch1": lat[int(len(lat) * 0.99)]},
+                    "p99_ms_batch1": lat[int(len(lat) * 0.99)], "distinct_batches": args.steps,
+                    "includes": "host planning, H2D of the plan, kernels, D2H of the MSets, result scatter" +
+                                ("; per batch the phase-1 statistics exchange, the all-to-all and the merge" if world > 1 else "")},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "xgm_and_bm_kernel (decode driver + bitmap intersect + BM25)",
+            "roofline": {"bound": "hbm", "kernel": cfg["kernel"],
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "traffic_source": "profiles/r1_and_bm_kernel.json (ncu dram__bytes_read+write of one launch)" if traffic else None,
+                         "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms_per_launch": kern_ms},
+            "step_breakdown_ms": step_parts, "step_bound_by": bound,
+            "bounds_approx_fraction": approx0 / BATCH,
             "clocks": clocks}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             binfo = build_reference_db()
-            cores = ref_cores()
-            cinfo = run_reference_queries(binfo["dbs"], REF_QUERIES_PER_STEP, 3, 1, cores)
+            cores, cdet = ref_cores()
+            nq = ref_queries_per_step(cfg, cores) if not REF_Q_ENV else cfg["ref_queries"]
+            cinfo, _ = run_reference_queries(cfg, binfo["dbs"], nq, 3, 1, cores)
             line["cpu_baseline"] = {
-                "value": cinfo["qps"], "unit": UNIT, "cores": cores, "kind": "reference",
-                "sample": (f"3 passes of {REF_QUERIES_PER_STEP} queries of the same workload on the full {NDOCS}-doc "
-                           f"glass DB, {cores} threads (one Xapian::Database+Enquire each), timing get_mset only"),
+                "value": cinfo["qps"], "unit": UNIT, "cores": cores, "kind": "reference", "cores_detail": cdet,
+                "sample": (f"3 passes of {nq} queries of the same workload on the full {NDOCS}-doc "
+                           f"glass DB, {cores} threads (one Xapian::Database+Enquire each, opened before the timed passes)"),
                 "p50_ms": cinfo["p50_ms"], "p99_ms": cinfo["p99_ms"],
-                "single_thread": single_thread_baseline(binfo["dbs"])}
+                "single_thread": single_thread_baseline(cfg, binfo["dbs"])}
+            if not args.no_parity:
+                line["parity"] = parity_against_reference(cfg, binfo["dbs"], xgm.Searcher(ix, max_batch=256, max_topk=TOPK), cores)
         except Exception as e:  # the baseline is reported, never required for the GPU numbers
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": ref_cores(), "kind": "reference",
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": ref_cores()[0], "kind": "reference",
                                     "sample": f"unavailable: {e}"}
     if rank == 0:
         print(json.dumps(line))
@@ -534,6 +717,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the dump diff against the compiled reference")
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS), help="BASELINE.json configuration (default C2)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

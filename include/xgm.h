@@ -124,6 +124,10 @@ typedef struct xgm_term_stats {
 } xgm_term_stats;
 /* Returns XGM_OK with termfreq == 0 for an unknown term (like Database::get_termfreq). */
 xgm_status xgm_term_stats_get(const xgm_index*, const char* term, uint32_t term_len, xgm_term_stats* out);
+/* termfreq of n terms in one call (0 for unknown terms): phase 1 of Xapiand's two-phase scheme looks up every
+ * query term of a batch on every shard before the sums are exchanged (src/database/handler.cc:1532-1538). */
+xgm_status xgm_term_stats_many(const xgm_index*, uint32_t n, const char* const* terms, const uint32_t* term_lens,
+                               uint32_t* termfreq);
 /* Round-trip check: decode a term's posting list on the device back into flat arrays (capacity n). */
 xgm_status xgm_index_decode_term(const xgm_index*, uint32_t term_id, uint32_t* docids, uint32_t* wdfs,
                                  uint32_t capacity, uint32_t* n);
@@ -204,9 +208,10 @@ typedef struct xgm_query {
      * (api/postingsource.cc:208).  0 = the source only filters (OP_FILTER right side). */
     uint32_t filter_weighted, reserved2;
     double filter_factor;        /* used when filter_weighted; 0 is treated as 1.0 */
-    uint64_t sort_missing_key;   /* key of a document without a value in sort_slot: 0 for Enquire::set_sort_by_value*
-                                    (empty string), xgm_value_key("\xff") / ("\0") for Xapiand's SerialiseKey forward /
-                                    reverse (MAX_STR_CMPVALUE / MIN_STR_CMPVALUE, src/multivalue/keymaker.h:53-54) */
+    uint64_t sort_missing_key;   /* key of a document without a value in sort_slot: 0 (the empty string) for
+                                    Enquire::set_sort_by_value* and for Xapiand's SerialiseKey in reverse — its
+                                    MIN_STR_CMPVALUE is std::string("\x00"), i.e. empty (src/multivalue/keymaker.h:54) —
+                                    and xgm_value_key("\xff") for SerialiseKey forward (MAX_STR_CMPVALUE, keymaker.h:53) */
 } xgm_query;
 
 /* One query's result: the fields of MSet::Internal (src/xapian/api/msetinternal.h:58-99). */

@@ -286,7 +286,7 @@ def test_cuda_matches_xapiand_multivalue_classes():
         if "keysort" in q:
             slot, rev = q["keysort"]
             kw.update(sort_by=xgm.SORT_VAL_REL, sort_slot=slot, sort_reverse=bool(rev), sort_use_max=bool(rev),
-                      sort_missing_key=xgm.value_key(b"\x00" if rev else b"\xff")[0])
+                      sort_missing_key=xgm.value_key(b"" if rev else b"\xff")[0])
         qs.append(xgm.Query(xgm.OP_AND, [f"T{t:06d}" for t in q["terms"]], **kw))
     res = xgm.Searcher(ix, max_batch=len(qs), max_topk=128).search(qs)
     exact_bounds = 0

@@ -62,6 +62,7 @@ struct XgmKernelParams {
     uint32_t* out_d;
     uint64_t* out_k;
     XgmDevResult* out_info;
+    XgmRaise* raise_log;          /* [nq][XGM_RAISE_LOG] */
 };
 
 cudaError_t xgm_launch_and(const XgmKernelParams& p, int grid, cudaStream_t s);

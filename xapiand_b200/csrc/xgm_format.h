@@ -70,7 +70,7 @@ struct XgmDevQuery {
     double src_weight;                  /* weighted value-range source: factor * 1.0 added to every match ... */
     uint32_t src_pos;                   /* ... before the weight of required list src_pos (MultiAndPostList order);
                                            nterms = after all; XGM_NO_SRC = the source only filters */
-    uint32_t pad1;
+    uint32_t log_raises;                /* record the matches that attain the running maximum weight (XGM_RAISE_LOG) */
     XgmDevTerm terms[XGM_DEV_MAX_TERMS]; /* AND: ascending termfreq (MultiAndPostList order) */
 };
 
@@ -90,7 +90,16 @@ struct XgmQState {
     uint32_t pool_off;         /* second pass: this query's slice of the overflow pool (entries) */
     uint32_t pool_cap;         /* exact number of matches at or above b* (from the completed histogram) */
     uint32_t skipped;          /* OR: whole work items were skipped by MaxScore (match count is a lower bound) */
-    uint32_t pad;
+    uint32_t nraise;           /* entries appended to the query's raise log (see XGM_RAISE_LOG) */
 };
+
+/* ProtoMSet::update_max_weight (matcher/protomset.h:174-183) remembers how many subqueries matched the
+ * best-weighted document — the numerator of percent_scale_factor.  When that number varies per document (OR,
+ * AND_MAYBE) and the MSet is NOT ordered by weight, the best-weighted document need not be among the results,
+ * so queries that ask for it (XgmDevQuery::log_raises) log every match that attains the running maximum:
+ * {weight bits, docid, matching subqueries}.  The running maximum only rises, so the log stays short
+ * (~ln(matches) entries); a query whose log overflows is declined. */
+#define XGM_RAISE_LOG 64u
+struct XgmRaise { unsigned long long wbits; uint32_t docid, subqs; };
 
 #endif

@@ -13,6 +13,7 @@
 #include <chrono>
 #include <cstring>
 #include <condition_variable>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -418,7 +419,6 @@ extern "C" size_t xgm_sort_key_bytes(uint64_t key, int reverse, unsigned char ou
     unsigned char v[8];
     size_t n = xgm_value_key_bytes(key, v);
     size_t o = 0;
-    if (reverse && key == 0) { v[0] = 0; n = 1; } /* MIN_STR_CMPVALUE "\0": a document without a value (keymaker.cc:82-86) */
     if (!reverse) {
         for (size_t i = 0; i < n; ++i) out[o++] = v[i];
         return o;
@@ -766,6 +766,17 @@ extern "C" xgm_status xgm_term_stats_get(const xgm_index* ix, const char* term, 
     return XGM_OK;
 }
 
+extern "C" xgm_status xgm_term_stats_many(const xgm_index* ix, uint32_t n, const char* const* terms, const uint32_t* lens,
+                                          uint32_t* termfreq) {
+    if (!ix || (n && (!terms || !termfreq))) return fail(XGM_E_INVALID, "null argument");
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t id;
+        const uint32_t len = lens ? lens[i] : (uint32_t)strlen(terms[i]);
+        termfreq[i] = lookup_term(ix, terms[i], len, &id) ? ix->terms[id].termfreq : 0u;
+    }
+    return XGM_OK;
+}
+
 static void fill_index_params(const xgm_index* ix, XgmKernelParams& p) {
     memset(&p, 0, sizeof(p));
     p.hdr = ix->d_hdr; p.docs = ix->d_docs; p.tfs = ix->d_tfs; p.doclen = ix->d_doclen; p.lastdocid = ix->lastdocid;
@@ -796,6 +807,74 @@ extern "C" xgm_status xgm_index_decode_term(const xgm_index* ix, uint32_t term_i
     return XGM_OK;
 }
 
+/* ------------------------------------------------------------------ planner pool */
+
+/* Query planning is independent per query; large batches are split over a few helper threads.  The helpers
+ * live as long as the process (one pool, shared by all searchers): spawning threads per batch cost more than
+ * the planning itself once several searchers and several ranks per box were submitting at the same time. */
+class PlannerPool {
+  public:
+    static PlannerPool& get() { static PlannerPool p; return p; }
+    /* run fn(part) for part in [0, nparts) on the pool (the caller takes parts too); returns when all are done */
+    void run(int nparts, const std::function<void(int)>& fn) {
+        if (nparts <= 1 || nthreads_ == 0) { for (int i = 0; i < nparts; ++i) fn(i); return; }
+        std::unique_lock<std::mutex> lk(mu_);
+        run_cv_.wait(lk, [&] { return !busy_; }); /* one batch at a time */
+        busy_ = true; fn_ = &fn; nparts_ = nparts; next_ = 0; done_ = 0; ++gen_;
+        lk.unlock();
+        cv_.notify_all();
+        work();
+        lk.lock();
+        done_cv_.wait(lk, [&] { return done_ == nparts_; });
+        busy_ = false; fn_ = nullptr;
+        lk.unlock();
+        run_cv_.notify_one();
+    }
+    int threads() const { return nthreads_ + 1; }
+
+  private:
+    PlannerPool() {
+        int t = std::min(default_threads(), 8);
+        if (const char* e = getenv("XGM_HOST_THREADS")) t = std::max(1, atoi(e));
+        nthreads_ = t - 1;
+        for (int i = 0; i < nthreads_; ++i) std::thread([this] { loop(); }).detach();
+    }
+    void work() {
+        for (;;) {
+            int i;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (!fn_ || next_ >= nparts_) return;
+                i = next_++;
+            }
+            (*fn_)(i);
+            bool last;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                last = ++done_ == nparts_;
+            }
+            if (last) done_cv_.notify_all();
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+            }
+            work();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_, run_cv_;
+    const std::function<void(int)>* fn_ = nullptr;
+    int nthreads_ = 0, nparts_ = 0, next_ = 0, done_ = 0;
+    uint64_t gen_ = 0;
+    bool busy_ = false;
+};
+
 /* ------------------------------------------------------------------ searcher */
 
 struct PlannedQuery {
@@ -812,6 +891,7 @@ struct PlannedQuery {
     bool mv_source = false;  /* a Xapiand range source is a child of the AND: its termfreq estimates are restated */
     bool count_only = false; /* first >= every possible match count: the MSet is empty, only counts matter */
     bool aux_subqs = false;  /* the number of matching weighted leaves varies per document (OR, AND_MAYBE) */
+    bool log_raises = false; /* … and the MSet is not ordered by weight: subqueries of the best-weighted document come from the raise log */
 };
 
 struct xgm_searcher {
@@ -830,6 +910,10 @@ struct xgm_searcher {
     uint32_t* h_out_d = nullptr;
     uint64_t* h_out_k = nullptr;
     XgmDevResult* h_info = nullptr;
+    XgmRaise* h_raise = nullptr;  /* pinned: raise logs of the batch (copied only when a query asked for them) */
+    XgmRaise* d_raise = nullptr;
+    XgmQState* h_qstate = nullptr; /* pinned: per-query state after the batch (raise-log lengths) */
+    bool any_raise = false;
     size_t items_cap = 0, items_or_cap = 0, items_bm_cap = 0;
     uint32_t keep_cap = 0;
     size_t ctrl_bytes = 0;
@@ -917,7 +1001,7 @@ extern "C" void xgm_searcher_free(xgm_searcher* s) {
     cudaSetDevice(s->ix->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFreeHost(s->h_queries); cudaFreeHost(s->h_items); cudaFreeHost(s->h_items_or); cudaFreeHost(s->h_items_bm); cudaFreeHost(s->h_out_w); cudaFreeHost(s->h_out_d);
-    cudaFreeHost(s->h_out_k); cudaFreeHost(s->h_info);
+    cudaFreeHost(s->h_out_k); cudaFreeHost(s->h_info); cudaFreeHost(s->h_raise); cudaFree(s->d_raise); cudaFreeHost(s->h_qstate);
     cudaFree(s->d_queries); cudaFree(s->d_items); cudaFree(s->d_items_or); cudaFree(s->d_items_bm); cudaFree(s->d_exp[0]); cudaFree(s->d_exp[1]); cudaFree(s->d_exp[2]);
     for (int w = 0; w < 3; ++w) { if (s->h_levels[w]) cudaFreeHost(s->h_levels[w]); cudaFree(s->d_levels[w]); } cudaFree(s->d_ctrl); cudaFree(s->d_match_w); cudaFree(s->d_match_d);
     cudaFree(s->d_match_k); cudaFree(s->d_pool_w); cudaFree(s->d_pool_d); cudaFree(s->d_pool_k); cudaFree(s->d_slab); cudaFree(s->d_out_k);
@@ -1006,6 +1090,9 @@ extern "C" xgm_status xgm_searcher_new(const xgm_index* ix, uint32_t max_batch, 
     CUDA_TRY(cudaMallocHost(&s->h_out_w, ns * 8)); CUDA_TRY(cudaMallocHost(&s->h_out_d, ns * 4));
     CUDA_TRY(cudaMallocHost(&s->h_out_k, ns * 8)); CUDA_TRY(cudaMallocHost(&s->h_info, nq * sizeof(XgmDevResult)));
     CUDA_TRY(cudaMalloc(&s->d_queries, nq * sizeof(XgmDevQuery)));
+    CUDA_TRY(cudaMallocHost(&s->h_raise, nq * XGM_RAISE_LOG * sizeof(XgmRaise)));
+    CUDA_TRY(cudaMallocHost(&s->h_qstate, nq * sizeof(XgmQState)));
+    CUDA_TRY(cudaMalloc(&s->d_raise, nq * XGM_RAISE_LOG * sizeof(XgmRaise)));
     s->ctrl_bytes = 64 + nq * sizeof(XgmQState) + nq * XGM_NBINS * 4;
     CUDA_TRY(cudaMalloc(&s->d_ctrl, s->ctrl_bytes));
     CUDA_TRY(cudaMalloc(&s->d_match_w, nm * 8)); CUDA_TRY(cudaMalloc(&s->d_match_d, nm * 4)); CUDA_TRY(cudaMalloc(&s->d_match_k, nm * 8));
@@ -1158,7 +1245,7 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
                              std::vector<XgmWorkItem>& items_bm, uint32_t blocks_per_item) {
     const xgm_index* ix = s->ix;
     pq = PlannedQuery();
-    memset(&dq, 0, sizeof(dq));
+    memset(&dq, 0, offsetof(XgmDevQuery, terms)); /* the term slots in use are written in full by put_term */
     if (q.nterms == 0 || q.nterms > XGM_MAX_TERMS) { pq.status = XGM_E_UNIMPLEMENTED; return XGM_OK; }
     if (q.op != XGM_OP_AND && q.op != XGM_OP_OR) { pq.status = XGM_E_UNIMPLEMENTED; return XGM_OK; }
     const uint32_t nfilter = q.nfilter, nnot = q.nnot, nmaybe = q.nmaybe, ngroups = q.nfilter + q.nnot + q.nmaybe;
@@ -1294,7 +1381,8 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
         auto put_term = [&](uint32_t slot, uint32_t j, bool weighted) {
             dq.terms[slot].termweight = weighted ? tw[j] : 0.0; /* a boolean leaf contributes +0.0: sums unchanged */
             dq.terms[slot].maxpart = weighted ? maxpart[j] : 0.0;
-            dq.terms[slot].bm_off = XGM_NO_BITMAP;
+            dq.terms[slot].bm_off = XGM_NO_BITMAP; dq.terms[slot].rk_off = 0;
+            dq.terms[slot].blk_begin = 0; dq.terms[slot].nblocks = 0;
             if (ids[j] != 0xffffffffu) {
                 const TermInfo& tinf = ix->terms[ids[j]];
                 dq.terms[slot].blk_begin = tinf.blk_begin; dq.terms[slot].nblocks = tinf.nblocks;
@@ -1465,7 +1553,8 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
             uint32_t j = order[i];
             dq.terms[i].termweight = tw[j];
             dq.terms[i].maxpart = maxpart[j];
-            dq.terms[i].bm_off = XGM_NO_BITMAP;
+            dq.terms[i].bm_off = XGM_NO_BITMAP; dq.terms[i].rk_off = 0;
+            dq.terms[i].blk_begin = 0; dq.terms[i].nblocks = 0;
             if (ids[j] != 0xffffffffu) {
                 const TermInfo& tinf = ix->terms[ids[j]];
                 dq.terms[i].blk_begin = tinf.blk_begin; dq.terms[i].nblocks = tinf.nblocks;
@@ -1491,6 +1580,10 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
         dq.bucket_scale = (double)XGM_NBINS / ((double)(ix->slot_max[q.sort_slot] - ix->slot_min[q.sort_slot]) + 1.0);
     }
 
+    /* percent_scale_factor needs the number of subqueries matching the best-WEIGHTED document: when that varies
+     * per document and the order is not by weight alone, have the kernels log the running-maximum matches */
+    dq.log_raises = ((dq.route == 1 && n > 1) || pq.aux_subqs) && q.sort_by != XGM_SORT_REL ? 1u : 0u;
+    pq.log_raises = dq.log_raises != 0;
     if (cal == 0) { pq.on_device = false; return XGM_OK; } /* bounds only, matcher.cc:437-461 */
     if (dq.route == 0 && any_absent) { pq.on_device = false; return XGM_OK; } /* AND with an absent term: empty */
     pq.on_device = true;
@@ -1597,10 +1690,7 @@ static xgm_status submit_impl(xgm_searcher* s, const xgm_query* queries, uint32_
     /* Planning (term lookup, Weight::init_, evaluation order, work items) is independent per query:
      * large batches are planned by a few host threads, each into its own work lists. */
     int T = 1;
-    if (nq >= 512) {
-        T = std::min(default_threads(), 8);
-        if (const char* e = getenv("XGM_HOST_THREADS")) T = std::max(1, atoi(e));
-    }
+    if (nq >= 512) T = PlannerPool::get().threads();
     if (T <= 1) {
         for (uint32_t i = 0; i < nq; ++i) {
             xgm_status st = plan_query(s, queries[i], i, s->plan[i], s->h_queries[i], items, items_or, items_bm, bpi);
@@ -1609,17 +1699,14 @@ static xgm_status submit_impl(xgm_searcher* s, const xgm_query* queries, uint32_
     } else {
         std::vector<std::vector<XgmWorkItem>> ti(T), tio(T), tib(T);
         std::vector<xgm_status> tst(T, XGM_OK);
-        std::vector<std::thread> th;
-        for (int t = 0; t < T; ++t)
-            th.emplace_back([&, t]() {
-                uint32_t a = (uint32_t)((uint64_t)nq * t / T), b = (uint32_t)((uint64_t)nq * (t + 1) / T);
-                tib[t].reserve((size_t)(b - a));
-                for (uint32_t i = a; i < b; ++i) {
-                    xgm_status st = plan_query(s, queries[i], i, s->plan[i], s->h_queries[i], ti[t], tio[t], tib[t], bpi);
-                    if (st != XGM_OK) { tst[t] = st; return; }
-                }
-            });
-        for (auto& x : th) x.join();
+        PlannerPool::get().run(T, [&](int t) {
+            uint32_t a = (uint32_t)((uint64_t)nq * t / T), b = (uint32_t)((uint64_t)nq * (t + 1) / T);
+            tib[t].reserve((size_t)(b - a));
+            for (uint32_t i = a; i < b; ++i) {
+                xgm_status st = plan_query(s, queries[i], i, s->plan[i], s->h_queries[i], ti[t], tio[t], tib[t], bpi);
+                if (st != XGM_OK) { tst[t] = st; return; }
+            }
+        });
         for (int t = 0; t < T; ++t) {
             if (tst[t] != XGM_OK) return fail(tst[t], "query planning failed");
             items.insert(items.end(), ti[t].begin(), ti[t].end());
@@ -1752,6 +1839,9 @@ static xgm_status submit_impl(xgm_searcher* s, const xgm_query* queries, uint32_
     p.pool_total = s->pool_total; p.pool_w = s->d_pool_w; p.pool_d = s->d_pool_d; p.pool_k = s->d_pool_k;
     p.match_w = s->d_match_w; p.match_d = s->d_match_d; p.match_k = s->d_match_k;
     p.out_stride = s->max_topk; p.out_w = s->d_out_w; p.out_d = s->d_out_d; p.out_k = s->d_out_k; p.out_info = s->d_info;
+    p.raise_log = s->d_raise;
+    s->any_raise = false;
+    for (uint32_t i = 0; i < nq; ++i) s->any_raise |= s->plan[i].log_raises;
     CUDA_TRY(cudaMemcpyAsync(s->d_queries, s->h_queries, (size_t)nq * sizeof(XgmDevQuery), cudaMemcpyHostToDevice, s->stream));
     if (s->nseg[0])
         CUDA_TRY(cudaMemcpyAsync(s->d_items, s->h_items, (size_t)s->nseg[0] * sizeof(XgmWorkItem), cudaMemcpyHostToDevice, s->stream));
@@ -1770,6 +1860,10 @@ static xgm_status submit_impl(xgm_searcher* s, const xgm_query* queries, uint32_
     CUDA_TRY(cudaMemcpyAsync(s->h_out_w, s->d_out_w, ns * 8, cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaMemcpyAsync(s->h_out_d, s->d_out_d, ns * 4, cudaMemcpyDeviceToHost, s->stream));
     if (s->any_sort) CUDA_TRY(cudaMemcpyAsync(s->h_out_k, s->d_out_k, ns * 8, cudaMemcpyDeviceToHost, s->stream));
+    if (s->any_raise) {
+        CUDA_TRY(cudaMemcpyAsync(s->h_raise, s->d_raise, (size_t)nq * XGM_RAISE_LOG * sizeof(XgmRaise), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(s->h_qstate, s->d_ctrl + 64, (size_t)nq * sizeof(XgmQState), cudaMemcpyDeviceToHost, s->stream));
+    }
     s->pending = true;
     s->stats.host_plan_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_submit0).count();
     if (getenv("XGM_DEBUG_TIMING"))
@@ -1782,7 +1876,7 @@ static xgm_status submit_impl(xgm_searcher* s, const xgm_query* queries, uint32_
 }
 
 static void finish_info(const PlannedQuery& pq, const XgmDevResult* dr, const double* w, const uint64_t* keys, bool is_or,
-                        xgm_mset_info* o) {
+                        xgm_mset_info* o, const XgmRaise* raises = nullptr, uint32_t nraise = 0) {
     memset(o, 0, sizeof(*o));
     o->first = pq.first;
     o->status = pq.status;
@@ -1825,6 +1919,16 @@ static void finish_info(const PlannedQuery& pq, const XgmDevResult* dr, const do
         /* AND: every leaf matches; OR sorted by relevance: leaves matching the best document */
         uint32_t subqs = dr->max_subqs;
         if (is_or && pq.sort_by == XGM_SORT_REL && keys) subqs = (uint32_t)keys[0];
+        if (pq.log_raises) {
+            /* ProtoMSet::update_max_weight: the FIRST document in docid order that attains the maximum */
+            if (!raises || nraise > XGM_RAISE_LOG) { o->status = XGM_E_UNIMPLEMENTED; return; }
+            unsigned long long mb;
+            memcpy(&mb, &max_w, 8);
+            uint32_t best = 0xffffffffu;
+            for (uint32_t i = 0; i < nraise; ++i)
+                if (raises[i].wbits == mb && raises[i].docid < best) { best = raises[i].docid; subqs = raises[i].subqs; }
+            if (best == 0xffffffffu) { o->status = XGM_E_UNIMPLEMENTED; return; }
+        }
         /* a value-range / posting-source filter counts as a matching subquery (ValueRangePostList /
          * ExternalPostList::count_matching_subqs return 1) without being one of the total weighted leaves
          * (api/queryinternal.cc:1097-1098) */
@@ -1911,7 +2015,8 @@ extern "C" xgm_status xgm_search_wait(xgm_searcher* s, uint32_t* docids, double*
         const size_t off = (size_t)i * s->max_topk;
         if (pq.status == XGM_OK && pq.on_device && (s->h_info[i].flags & 16u)) s->stats.second_pass_queries++;
         finish_info(pq, &s->h_info[i], s->h_out_w + off, s->any_sort ? s->h_out_k + off : nullptr,
-                    s->h_queries[i].route == 1 || pq.aux_subqs, &info[i]);
+                    s->h_queries[i].route == 1 || pq.aux_subqs, &info[i],
+                    s->any_raise ? s->h_raise + (size_t)i * XGM_RAISE_LOG : nullptr, s->any_raise ? s->h_qstate[i].nraise : 0u);
         if (pq.status == XGM_OK && pq.on_device) s->stats.algorithmic_bytes += 4ull * s->h_info[i].exact;
         uint32_t n = info[i].n;
         if (n > stride) return fail(XGM_E_INVALID, "stride %u too small for %u results", stride, n);

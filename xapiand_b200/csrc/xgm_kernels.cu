@@ -256,6 +256,16 @@ __device__ __forceinline__ uint32_t match_bucket(const XgmDevQuery* q, double w,
     return q->sort_reverse ? b : (XGM_NBINS - 1 - b);
 }
 
+/* A match whose weight is at least the running maximum: append it to the query's raise log (format.h) */
+__device__ __forceinline__ void log_raise(const XgmKernelParams& p, uint32_t qi, unsigned long long wb, uint32_t did, uint32_t subqs) {
+    const uint32_t slot = atomicAdd(&p.qstate[qi].nraise, 1u);
+    if (slot < XGM_RAISE_LOG) {
+        XgmRaise r;
+        r.wbits = wb; r.docid = did; r.subqs = subqs;
+        p.raise_log[(size_t)qi * XGM_RAISE_LOG + slot] = r;
+    }
+}
+
 /* Warp-wide: lanes hold up to 4 matches each (mask `alive`), weight acc[k], docid c[k], aux[k]
  * (number of matching leaves). Counts every match, keeps those not yet prunable. */
 __device__ __noinline__ void emit_matches_impl(const XgmKernelParams& p, const XgmDevQuery* q, uint32_t qi, uint32_t lane,
@@ -300,14 +310,23 @@ __device__ __noinline__ void emit_matches_impl(const XgmKernelParams& p, const X
     }
     const uint32_t nkeep = __shfl_sync(FULL, incl, 31);
     uint32_t base = 0;
+    unsigned long long oldmax = ~0ull;
     if (lane == 0) {
         if (p.pass == 0) {
             atomicAdd(&st->total, nall);
-            atomicMax(&st->maxw, mb);
+            oldmax = atomicMax(&st->maxw, mb);
         }
         if (nkeep) base = atomicAdd(&st->stored, nkeep);
     }
     base = __shfl_sync(FULL, base, 0);
+    if (q->log_raises && p.pass == 0) {
+        oldmax = __shfl_sync(FULL, oldmax, 0);
+        if (mb >= oldmax) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if ((alive >> k & 1u) && (unsigned long long)__double_as_longlong(acc[k]) == mb) log_raise(p, qi, mb, c[k], aux[k]);
+        }
+    }
     if (nkeep == 0) return;
     uint32_t idx = base + (incl - n);
     if (p.pass == 0) {
@@ -1051,7 +1070,9 @@ __device__ __forceinline__ void emit_match_lanes(const XgmKernelParams& p, uint3
         XgmQState* st = &p.qstate[qi];
         if (p.pass == 0) {
             atomicAdd(&st->total, 1u);
-            atomicMax(&st->maxw, (unsigned long long)__double_as_longlong(w));
+            const unsigned long long wb = (unsigned long long)__double_as_longlong(w);
+            const unsigned long long oldmax = atomicMax(&st->maxw, wb);
+            if (q->log_raises && wb >= oldmax) log_raise(p, qi, wb, d, aux);
         }
         const uint64_t key = q->sort_by != 0 ? doc_sort_key(p, q, d) : 0ull;
         const uint32_t bkt = match_bucket(q, w, key);

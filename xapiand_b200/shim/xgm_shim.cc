@@ -414,7 +414,9 @@ bool xgm_shim_try_get_mset(const Xapian::Database& db, const Xapian::Query& quer
         if (a.sort_val_reverse) return decline("reversed key sort");
         keymaker = true;
         sort_slot = (uint32_t)slot; sort_reverse = rev != 0; sort_use_max = rev != 0;
-        L.xgm_value_key(rev ? "\0" : "\xff", 1, &sort_missing); /* MIN / MAX_STR_CMPVALUE, keymaker.h:53-54 */
+        /* a document without a value sorts as MAX_STR_CMPVALUE "\xff" (forward) or MIN_STR_CMPVALUE (reverse) —
+         * std::string("\x00"), which is the EMPTY string (keymaker.h:53-54, keymaker.cc:67-92) */
+        if (rev) sort_missing = 0; else L.xgm_value_key("\xff", 1, &sort_missing);
     }
     if (sort_by != XGM_SORT_REL && sort_slot >= 8) return decline("sort slot");
     /* ---- the query ---- */

@@ -34,7 +34,7 @@ EXPORTS = [
     "xgm_searcher_stream", "xgm_search_last_stats", "xgm_unshard", "xgm_merge_msets", "xgm_merge_topk_device",
     "xgm_merge_topk_device_slab",
     "xgm_builder_add_value_slot_serialised", "xgm_builder_set_revision", "xgm_index_value_freq",
-    "xgm_value_key", "xgm_value_key_bytes", "xgm_sort_key_bytes",
+    "xgm_value_key", "xgm_value_key_bytes", "xgm_sort_key_bytes", "xgm_term_stats_many",
 ]
 
 
@@ -134,6 +134,7 @@ def lib():
     L.xgm_index_close.restype = None
     L.xgm_index_info_get.argtypes = [C.c_void_p, C.POINTER(IndexInfo)]
     L.xgm_term_stats_get.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.POINTER(TermStats)]
+    L.xgm_term_stats_many.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p]
     L.xgm_index_decode_term.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
                                         C.POINTER(C.c_uint32)]
     L.xgm_searcher_new.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
@@ -256,6 +257,31 @@ class QueryBatch:
             cq.sort_reverse, cq.sort_use_max = int(q.sort_reverse), int(q.sort_use_max)
             cq.revision, cq.filter_weighted, cq.filter_factor = q.revision, int(q.filter_weighted), float(q.filter_factor)
             cq.sort_missing_key = q.sort_missing_key
+
+
+def _attach_global_stats(self):
+    """Give every query of the batch an xgm_stats block backed by ONE (nq, MAX_TERMS) uint32 matrix, so that the
+    global statistics of a batch (phase 1 of the two-phase scheme) can be filled in with two vectorised writes
+    after the all-reduce instead of re-marshalling the queries."""
+    self.gtf = np.zeros((self.n, MAX_TERMS), np.uint32)
+    self.cstats = (CStats * self.n)()
+    view = np.frombuffer(self.cstats, dtype=[("coll", "<u4"), ("pad", "<u4"), ("tlen", "<u8"), ("ptr", "<u8")])
+    view["ptr"] = self.gtf.ctypes.data + np.arange(self.n, dtype=np.uint64) * (MAX_TERMS * 4)
+    self._stats_view = view
+    base = C.addressof(self.cstats)
+    for i in range(self.n):
+        self.arr[i].stats = C.cast(base + i * C.sizeof(CStats), C.POINTER(CStats))
+
+
+def _set_global_stats(self, collection_size: int, total_length: int, termfreqs: np.ndarray):
+    """termfreqs: (nq, k) global termfreq per query term, in query order."""
+    self._stats_view["coll"] = collection_size
+    self._stats_view["tlen"] = total_length
+    self.gtf[:, :termfreqs.shape[1]] = termfreqs
+
+
+QueryBatch.attach_global_stats = _attach_global_stats
+QueryBatch.set_global_stats = _set_global_stats
 
 
 @dataclass
@@ -399,6 +425,15 @@ class Index:
         o = TermStats()
         _check(lib().xgm_term_stats_get(self._h, t, len(t), C.byref(o)))
         return o
+
+    def term_freqs(self, names: Sequence[Union[str, bytes]]) -> np.ndarray:
+        """Local termfreq of many terms in one C call (xgm_term_stats_many)."""
+        bs = [t.encode() if isinstance(t, str) else bytes(t) for t in names]
+        arr = (C.c_char_p * len(bs))(*bs)
+        lens = np.array([len(b) for b in bs], np.uint32)
+        out = np.zeros(len(bs), np.uint32)
+        _check(lib().xgm_term_stats_many(self._h, len(bs), arr, _ptr(lens), _ptr(out)))
+        return out
 
     def decode_term(self, term_id: int):
         n = C.c_uint32()
