@@ -204,3 +204,19 @@ def test_background_submit_matches_synchronous(edge):
             assert [float(x).hex() for x in a.weights] == [float(x).hex() for x in m.weights], (b, i)
             assert (a.matches_lower_bound, a.matches_estimated_raw, a.matches_upper_bound) == \
                    (m.matches_lower_bound, m.matches_estimated_raw, m.matches_upper_bound), (b, i)
+
+
+def test_process_exits_after_a_large_batch():
+    """Batches of >= 512 queries are planned on the library's helper threads, which stay parked for the life of
+    the process: the host program must still exit (a static pool object whose condition variable was destroyed
+    at exit() once blocked every Python process that had submitted a large batch)."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from xapiand_b200 import xgm\n"
+            "ix = xgm.Index.synthetic(20000, 3000)\n"
+            "s = xgm.Searcher(ix, max_batch=640, max_topk=16)\n"
+            "r = s.search([xgm.Query(xgm.OP_AND, [i % 50, 50 + i % 40], maxitems=10) for i in range(600)])\n"
+            "print(sum(m.status == 0 for m in r))\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=180)
+    assert p.returncode == 0 and p.stdout.strip() == "600", p.stderr[-500:]

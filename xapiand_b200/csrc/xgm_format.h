@@ -70,6 +70,8 @@ struct XgmDevQuery {
     double src_weight;                  /* weighted value-range source: factor * 1.0 added to every match ... */
     uint32_t src_pos;                   /* ... before the weight of required list src_pos (MultiAndPostList order);
                                            nterms = after all; XGM_NO_SRC = the source only filters */
+    uint32_t or_fast;                   /* OR: every leaf has a membership bitmap and there are at most 5 → xgm_or3_kernel */
+    uint32_t pad2;
     uint32_t log_raises;                /* record the matches that attain the running maximum weight (XGM_RAISE_LOG) */
     XgmDevTerm terms[XGM_DEV_MAX_TERMS]; /* AND: ascending termfreq (MultiAndPostList order) */
 };

@@ -814,7 +814,9 @@ extern "C" xgm_status xgm_index_decode_term(const xgm_index* ix, uint32_t term_i
  * the planning itself once several searchers and several ranks per box were submitting at the same time. */
 class PlannerPool {
   public:
-    static PlannerPool& get() { static PlannerPool p; return p; }
+    /* never destroyed: its helper threads are detached and wait on the condition variable for the life of the
+     * process (destroying a condition variable that has waiters blocks in glibc — at exit() of the host program) */
+    static PlannerPool& get() { static PlannerPool* p = new PlannerPool(); return *p; }
     /* run fn(part) for part in [0, nparts) on the pool (the caller takes parts too); returns when all are done */
     void run(int nparts, const std::function<void(int)>& fn) {
         if (nparts <= 1 || nthreads_ == 0) { for (int i = 0; i < nparts; ++i) fn(i); return; }
@@ -957,7 +959,8 @@ struct xgm_searcher {
     uint32_t nq = 0, nitems = 0, nitems_or = 0, nitems_bm = 0;
     bool pending = false, any_sort = false;
     xgm_batch_stats stats{};
-    int grid = 0, grid_or = 0, grid_and2 = 0, grid_bm = 0;
+    int grid = 0, grid_or = 0, grid_or3 = 0, grid_and2 = 0, grid_bm = 0;
+    bool any_or_fast = false, any_or_slow = false;
     int and_version = 1; /* 1 = warp-autonomous kernel, 2 = chunked CTA kernel (XGM_AND_KERNEL env) */
     XgmKernelParams params;
     /* xgm_search_submit_async: a worker thread plans and enqueues the batch while the caller scatters the
@@ -1067,7 +1070,7 @@ extern "C" xgm_status xgm_searcher_new(const xgm_index* ix, uint32_t max_batch, 
     s->ix = ix; s->max_batch = max_batch; s->max_topk = max_topk;
     /* candidates a query may buffer before its pruning threshold settles (~k(1+ln(M/k)) arrive above
      * a rising threshold) and how many of them the top-k kernel can hold in shared memory */
-    s->match_cap = std::max<uint32_t>(8192, 16 * max_topk);
+    s->match_cap = std::min<uint32_t>(65536, std::max<uint32_t>(8192, 32 * max_topk));
     s->keep_cap = 2048; /* a power of two (the top-k kernel sorts in place): 2048, 4096 or 8192 */
     while (s->keep_cap < 8192 && s->keep_cap < 8 * max_topk) s->keep_cap <<= 1;
     if (s->keep_cap > s->match_cap) s->keep_cap = s->match_cap;
@@ -1124,6 +1127,9 @@ extern "C" xgm_status xgm_searcher_new(const xgm_index* ix, uint32_t max_batch, 
     occ = xgm_or_occupancy_blocks_per_sm();
     if (occ < 1) occ = 1;
     s->grid_or = ix->sm_count * occ;
+    occ = xgm_or3_occupancy_blocks_per_sm();
+    if (occ < 1) occ = 1;
+    s->grid_or3 = ix->sm_count * occ;
     occ = xgm_and_bm_occupancy_blocks_per_sm();
     if (occ < 1) occ = 1;
     s->grid_bm = ix->sm_count * occ;
@@ -1598,6 +1604,9 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
         wi.query = qi; wi.b0 = dq.terms[0].nblocks; wi.b1 = 0; wi.pad = 0;
         if (wi.b0) dst.push_back(wi);
     } else {
+        bool fastor = n <= 5 && !(getenv("XGM_OR_KERNEL") && atoi(getenv("XGM_OR_KERNEL")) == 1);
+        for (uint32_t leaf = 0; leaf < n; ++leaf) fastor = fastor && dq.terms[leaf].bm_off != XGM_NO_BITMAP;
+        dq.or_fast = fastor ? 1u : 0u;
         for (uint32_t leaf = 0; leaf < n; ++leaf) {
             XgmWorkItem wi;
             wi.query = qi; wi.b0 = dq.terms[leaf].nblocks; wi.b1 = 0; wi.pad = leaf;
@@ -1651,7 +1660,8 @@ static xgm_status launch_batch(xgm_searcher* s) {
     };
     if (s->nitems_bm) { CUDA_TRY(xgm_launch_and_bm(p, s->grid_bm, cs)); s->stats.kernel_launches++; }
     if (s->nitems) { CUDA_TRY(launch_and(p)); s->stats.kernel_launches++; }
-    if (s->nitems_or) { CUDA_TRY(xgm_launch_or(p, s->grid_or, cs)); s->stats.kernel_launches++; }
+    if (s->nitems_or && s->any_or_fast) { CUDA_TRY(xgm_launch_or3(p, s->grid_or3, cs)); s->stats.kernel_launches++; }
+    if (s->nitems_or && s->any_or_slow) { CUDA_TRY(xgm_launch_or(p, s->grid_or, cs)); s->stats.kernel_launches++; }
     CUDA_TRY(cudaEventRecord(s->ev1, cs));
     CUDA_TRY(xgm_launch_topk(p, s->nq, cs));
     s->stats.kernel_launches++;
@@ -1660,7 +1670,8 @@ static xgm_status launch_batch(xgm_searcher* s) {
     p2.pass = 1;
     if (s->nitems_bm) { CUDA_TRY(xgm_launch_and_bm(p2, s->grid_bm, cs)); s->stats.kernel_launches++; }
     if (s->nitems) { CUDA_TRY(launch_and(p2)); s->stats.kernel_launches++; }
-    if (s->nitems_or) { CUDA_TRY(xgm_launch_or(p2, s->grid_or, cs)); s->stats.kernel_launches++; }
+    if (s->nitems_or && s->any_or_fast) { CUDA_TRY(xgm_launch_or3(p2, s->grid_or3, cs)); s->stats.kernel_launches++; }
+    if (s->nitems_or && s->any_or_slow) { CUDA_TRY(xgm_launch_or(p2, s->grid_or, cs)); s->stats.kernel_launches++; }
     CUDA_TRY(xgm_launch_topk(p2, s->nq, cs));
     s->stats.kernel_launches++;
     CUDA_TRY(cudaEventRecord(s->ev2, cs));
@@ -1842,6 +1853,9 @@ static xgm_status submit_impl(xgm_searcher* s, const xgm_query* queries, uint32_
     p.raise_log = s->d_raise;
     s->any_raise = false;
     for (uint32_t i = 0; i < nq; ++i) s->any_raise |= s->plan[i].log_raises;
+    s->any_or_fast = s->any_or_slow = false;
+    for (uint32_t i = 0; i < nq; ++i)
+        if (s->h_queries[i].route == 1 && s->plan[i].on_device) { if (s->h_queries[i].or_fast) s->any_or_fast = true; else s->any_or_slow = true; }
     CUDA_TRY(cudaMemcpyAsync(s->d_queries, s->h_queries, (size_t)nq * sizeof(XgmDevQuery), cudaMemcpyHostToDevice, s->stream));
     if (s->nseg[0])
         CUDA_TRY(cudaMemcpyAsync(s->d_items, s->h_items, (size_t)s->nseg[0] * sizeof(XgmWorkItem), cudaMemcpyHostToDevice, s->stream));

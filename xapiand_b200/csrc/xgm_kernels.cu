@@ -1063,13 +1063,13 @@ __device__ __noinline__ void raise_bstar_warp(const XgmKernelParams& p, uint32_t
 /* Per-lane emission of one match (lanes of a flush belong to different queries): count it, keep it unless
  * its bucket is already below the query's pruning bucket.  Warp-converged call. */
 __device__ __forceinline__ void emit_match_lanes(const XgmKernelParams& p, uint32_t lane, bool alive, uint32_t qi, double w,
-                                                 uint32_t d, uint32_t aux) {
+                                                 uint32_t d, uint32_t aux, bool count = true) {
     bool crossed = false;
     if (alive) {
         const XgmDevQuery* q = &p.queries[qi];
         XgmQState* st = &p.qstate[qi];
         if (p.pass == 0) {
-            atomicAdd(&st->total, 1u);
+            if (count) atomicAdd(&st->total, 1u); /* the OR kernel counts the documents it owns, scored or not */
             const unsigned long long wb = (unsigned long long)__double_as_longlong(w);
             const unsigned long long oldmax = atomicMax(&st->maxw, wb);
             if (q->log_raises && wb >= oldmax) log_raise(p, qi, wb, d, aux);
@@ -1715,6 +1715,7 @@ __global__ void __launch_bounds__(OR_WARPS * 32) xgm_or_kernel(XgmKernelParams p
         const XgmWorkItem wi = p.items_or[item];
         if (p.pass != 0 && p.qstate[wi.query].rerun == 0) continue;
         const XgmDevQuery* q = &p.queries[wi.query];
+        if (q->or_fast != 0) continue; /* answered by xgm_or3_kernel */
         const uint32_t nterms = q->nterms;
         const uint32_t drv = wi.pad; /* driver leaf (position in ascending-termfreq order) */
         uint32_t my_begin = 0, my_nblk = 0, my_cur = 0;
@@ -1861,6 +1862,256 @@ __global__ void __launch_bounds__(OR_WARPS * 32) xgm_or_kernel(XgmKernelParams p
             __syncwarp();
         }
     }
+}
+
+/* ------------------------------------------------------------------ OR kernel, bitmap leaves + queued scoring */
+
+/* Same contract as xgm_or_kernel for queries whose leaves ALL have membership bitmaps and number at most five
+ * (BASELINE config C3), organised like xgm_and_bm3_kernel.  Per iteration a warp decodes one block of the
+ * owner leaf (bulk copies of the next blocks in flight), issues the bitmap probes of all other leaves for its
+ * 128 docids together (up to 16 independent loads per lane) and builds every document's presence mask from the
+ * bits.  Ownership (no rarer leaf holds the document) and MaxScore are then register work: the bound of a
+ * presence mask comes from a 32-entry table held one entry per lane (one shuffle per posting).  Documents that
+ * survive are queued with their presence mask and scored 32 at a time, one per lane: wdf of the owner from its
+ * block, of the other leaves through their rank directories, then the reference's OrPostList tree as a postfix
+ * program (orpostlist.cc:93-103).  The queue lives as long as the warp, so scoring always runs on full warps. */
+#define OR3_WARPS 8
+#define OR3_QCAP 160 /* < 32 left over + up to 128 new candidates per iteration */
+#define OR3_MAX_LEAVES 5
+
+struct __align__(16) Or3Scratch {
+    uint32_t dstage[4][STAGE_WORDS];
+    uint32_t qdid[OR3_QCAP];
+    uint32_t qsrc[OR3_QCAP]; /* index of the owner block's header in hdr[] */
+    uint32_t qqi[OR3_QCAP];  /* query | position in the block << 25 */
+    uint32_t qpm[OR3_QCAP];  /* presence mask | owner leaf << 16 */
+    uint64_t dbar[4];
+};
+
+template <int MINB>
+__global__ void __launch_bounds__(OR3_WARPS * 32, MINB) xgm_or3_kernel(const __grid_constant__ XgmKernelParams p) {
+    extern __shared__ __align__(16) unsigned char or3_raw[];
+    Or3Scratch* scratch = reinterpret_cast<Or3Scratch*>(or3_raw);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    Or3Scratch& ws = scratch[warp];
+    if (lane < 4) mbar_init(&ws.dbar[lane], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    uint32_t phases = 0;
+    const XgmBlockHdr* __restrict__ hdr = p.hdr;
+    const uint32_t stage_base = smem_u32(ws.dstage[0]);
+    const uint32_t bar_base = stage_base + (uint32_t)offsetof(Or3Scratch, dbar);
+    if (p.pass != 0 && *reinterpret_cast<volatile uint32_t*>(p.work_counter + 4) == 0) return;
+    uint32_t qn = 0; /* warp-uniform queue length */
+    bool done = false;
+    /* current work item: blocks [db, it_b1) of leaf it_drv of query it_query are left */
+    uint32_t it_query = 0, it_b1 = 0, db = 0, it_drv = 0, drv_begin = 0, nterms = 0, ubbkt = 0;
+    uint32_t total_acc = 0; /* documents this lane owns in the current item (exact match count) */
+    bool can_prune = false;
+    const XgmDevQuery* q = p.queries;
+    const uint32_t* bmp[OR3_MAX_LEAVES];
+#pragma unroll
+    for (int j = 0; j < OR3_MAX_LEAVES; ++j) bmp[j] = p.bitmaps;
+
+    auto issue = [&](uint32_t blk) { /* stage owner block blk into buffer blk & 3 */
+        const uint32_t b = blk & 3u;
+        const uint4 h = __ldg(reinterpret_cast<const uint4*>(hdr + drv_begin + blk));
+        const uint32_t bits = XGM_HDR_DOC_BITS(h.w);
+        __syncwarp();
+        if (bits != 0 && lane == 0) {
+            mbar_expect_tx_a(bar_base + b * 8u, bits * 16u);
+            bulk_g2s_a(stage_base + b * (STAGE_WORDS * 4u), p.docs + h.y, bits * 16u, bar_base + b * 8u);
+        }
+    };
+
+    for (;;) {
+        /* ---- score queued documents (one per lane) and emit them ---- */
+        if (qn >= 32 || (done && qn != 0)) {
+            __syncwarp();
+            const uint32_t count = min(qn, 32u);
+            qn -= count;
+            const bool alive = lane < count;
+            const uint32_t d = alive ? ws.qdid[qn + lane] : 0u;
+            const uint32_t src = alive ? ws.qsrc[qn + lane] : 0u;
+            const uint32_t qp = alive ? ws.qqi[qn + lane] : 0u;
+            const uint32_t pmd = alive ? ws.qpm[qn + lane] : 0u;
+            const uint32_t qi = qp & 0x1ffffffu, pos = qp >> 25, pm = pmd & 0xffffu, drv = pmd >> 16;
+            double acc = 0.0;
+            if (alive) {
+                const XgmDevQuery* mq = &p.queries[qi];
+                const uint32_t dlen = __ldg(&p.doclen[d]);
+                /* weight = fold of the tree over the leaves present (OrPostList::get_weight, orpostlist.cc:93-103) */
+                double stk[OR3_MAX_LEAVES + 1];
+                uint32_t has = 0;
+                int sp = 0;
+                const uint32_t plen = mq->prog_len;
+                for (uint32_t i = 0; i < plen; ++i) {
+                    const int op = mq->prog[i];
+                    if (op >= 0) {
+                        if (pm >> op & 1u) {
+                            uint32_t tf;
+                            if ((uint32_t)op == drv) {
+                                const XgmBlockHdr hh = hdr[src];
+                                tf = unpack_gl(p.tfs, hh.tf_off, pos, XGM_HDR_TF_BITS(hh.meta));
+                            } else {
+                                const uint32_t r = bitmap_rank(p, mq->terms[op], d);
+                                const XgmBlockHdr bh = hdr[mq->terms[op].blk_begin + (r >> 7)];
+                                tf = unpack_gl(p.tfs, bh.tf_off, r & 127u, XGM_HDR_TF_BITS(bh.meta));
+                            }
+                            const double v = bm25_sumpart(mq->terms[op].termweight, mq, tf, dlen);
+                            /* static indexing keeps the stack in registers */
+                            if (sp == 0) stk[0] = v; else if (sp == 1) stk[1] = v; else if (sp == 2) stk[2] = v;
+                            else if (sp == 3) stk[3] = v; else if (sp == 4) stk[4] = v; else stk[5] = v;
+                            has |= 1u << sp;
+                        } else {
+                            has &= ~(1u << sp);
+                        }
+                        ++sp;
+                    } else {
+                        --sp;
+                        const bool hl = has >> (sp - 1) & 1u, hr = has >> sp & 1u;
+                        const double r = sp == 1 ? stk[1] : sp == 2 ? stk[2] : sp == 3 ? stk[3] : sp == 4 ? stk[4] : stk[5];
+                        const double l = sp == 1 ? stk[0] : sp == 2 ? stk[1] : sp == 3 ? stk[2] : sp == 4 ? stk[3] : stk[4];
+                        double v = l;
+                        if (hl && hr) v = __dadd_rn(l, r);
+                        else if (hr) { v = r; has |= 1u << (sp - 1); }
+                        if (sp == 1) stk[0] = v; else if (sp == 2) stk[1] = v; else if (sp == 3) stk[2] = v;
+                        else if (sp == 4) stk[3] = v; else stk[4] = v;
+                    }
+                }
+                acc = stk[0];
+            }
+            emit_match_lanes(p, lane, alive, qi, acc, d, (uint32_t)__popc(pm), false);
+            __syncwarp();
+            continue;
+        }
+        if (done) break;
+        /* ---- next work item ---- */
+        if (db >= it_b1) {
+            if (total_acc || it_b1) { /* close the previous item: its owned documents are matches */
+                const uint32_t t = __reduce_add_sync(FULL, total_acc);
+                if (lane == 0 && t && p.pass == 0) atomicAdd(&p.qstate[it_query].total, t);
+                total_acc = 0; it_b1 = 0; db = 0;
+            }
+            uint32_t item = 0;
+            if (lane == 0) item = atomicAdd(p.work_counter + 10 + p.pass, 1u);
+            item = __shfl_sync(FULL, item, 0);
+            if (item >= p.nitems_or) { done = true; continue; }
+            const XgmWorkItem wi = p.items_or[item];
+            if (p.pass != 0 && p.qstate[wi.query].rerun == 0) continue;
+            q = &p.queries[wi.query];
+            if (q->or_fast == 0) continue; /* this query's items belong to xgm_or_kernel */
+            nterms = q->nterms;
+            it_drv = wi.pad;
+            can_prune = (q->sort_by == 0) && (q->topk != 0);
+            /* MaxScore at work-item granularity (see xgm_or_kernel): nothing this item owns can reach the top-k */
+            if (can_prune) {
+                const XgmQState* st = &p.qstate[wi.query];
+                const uint32_t bstar = *reinterpret_cast<const volatile uint32_t*>(&st->bstar);
+                if (bstar != 0 && *reinterpret_cast<const volatile uint32_t*>(&st->total) >= q->check_at_least) {
+                    double ub = 0.0;
+                    for (uint32_t i = it_drv; i < nterms; ++i) ub += q->terms[i].maxpart;
+                    ub *= 1.0 + 1e-12;
+                    if (match_bucket(q, ub, 0) < bstar) {
+                        if (lane == 0) p.qstate[wi.query].skipped = 1u;
+                        continue;
+                    }
+                }
+            }
+            it_query = wi.query; it_b1 = wi.b1; db = wi.b0;
+            drv_begin = q->terms[it_drv].blk_begin;
+#pragma unroll
+            for (int j = 0; j < OR3_MAX_LEAVES; ++j) bmp[j] = p.bitmaps + ((uint32_t)j < nterms ? q->terms[j].bm_off : 0ull);
+            /* lane m holds the pruning bucket of presence mask m: the bound of a document is the sum of the
+             * get_maxpart bounds of the leaves it contains (the bound and the tree-order sum round differently) */
+            {
+                double ub = 0.0;
+                for (uint32_t i = 0; i < nterms; ++i)
+                    if (lane >> i & 1u) ub += q->terms[i].maxpart;
+                ubbkt = match_bucket(q, ub * (1.0 + 1e-12), 0);
+            }
+            for (uint32_t b = db; b < it_b1 && b < db + 3; ++b) issue(b);
+            continue;
+        }
+        /* ---- one block of the owner leaf ---- */
+        {
+            if (db + 3 < it_b1) issue(db + 3);
+            const uint4 h = __ldg(reinterpret_cast<const uint4*>(hdr + drv_begin + db));
+            const uint32_t bits = XGM_HDR_DOC_BITS(h.w), cnt = XGM_HDR_COUNT(h.w), cur = db & 3u;
+            if (bits) { mbar_wait_a(bar_base + cur * 8u, (phases >> cur) & 1u); phases ^= 1u << cur; }
+            uint32_t c[4];
+            decode_docids(ws.dstage[cur], bits, h.x, lane, c);
+            const int nv = min(4, max(0, (int)cnt - 4 * (int)lane));
+            const uint32_t valid = (1u << nv) - 1u;
+            uint32_t pm[4] = {0, 0, 0, 0};
+            /* membership of the 128 docids in every other leaf: all probes issued before any is used */
+#pragma unroll
+            for (int j = 0; j < OR3_MAX_LEAVES; ++j) {
+                if ((uint32_t)j < nterms && (uint32_t)j != it_drv) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) w[k] = (valid >> k & 1u) ? __ldg(bmp[j] + (c[k] >> 5)) : 0u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) pm[k] |= (__funnelshift_r(w[k], 0u, c[k]) & 1u) << j;
+                }
+            }
+            const uint32_t rarer = (1u << it_drv) - 1u;
+            const uint32_t bstar = can_prune ? *reinterpret_cast<volatile uint32_t*>(&p.qstate[it_query].bstar) : 0u;
+            uint32_t cand = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t m = pm[k] | (1u << it_drv);
+                pm[k] = m;
+                const uint32_t bk = __shfl_sync(FULL, ubbkt, m & 31u);
+                bool own = (valid >> k & 1u) && (m & rarer) == 0u; /* a rarer leaf owns the document otherwise */
+                if (own && q->filter && !doc_passes_filter(p, q, c[k])) own = false;
+                total_acc += own ? 1u : 0u;
+                if (own && bk >= bstar) cand |= 1u << k;
+            }
+            const uint32_t B = __ballot_sync(FULL, cand != 0);
+            if (B) {
+                const uint32_t nm1 = (uint32_t)__popc(cand) - 1u;
+                const uint32_t B0 = __ballot_sync(FULL, cand != 0 && (nm1 & 1u));
+                const uint32_t B1 = __ballot_sync(FULL, cand != 0 && (nm1 & 2u));
+                if (cand) {
+                    const uint32_t lt = (1u << lane) - 1u;
+                    uint32_t slot = qn + __popc(B & lt) + __popc(B0 & lt) + 2u * __popc(B1 & lt);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (cand >> k & 1u) {
+                            ws.qdid[slot] = c[k];
+                            ws.qsrc[slot] = drv_begin + db;
+                            ws.qqi[slot] = it_query | ((4 * lane + k) << 25);
+                            ws.qpm[slot] = pm[k] | (it_drv << 16);
+                            ++slot;
+                        }
+                }
+                qn += __popc(B) + __popc(B0) + 2u * __popc(B1);
+            }
+            ++db;
+        }
+    }
+    if (total_acc || it_b1) {
+        const uint32_t t = __reduce_add_sync(FULL, total_acc);
+        if (lane == 0 && t && p.pass == 0) atomicAdd(&p.qstate[it_query].total, t);
+    }
+}
+
+typedef void (*or3_fn)(const XgmKernelParams);
+static or3_fn or3_kernel() { return xgm_or3_kernel<3>; }
+
+cudaError_t xgm_launch_or3(const XgmKernelParams& p, int grid, cudaStream_t s) {
+    or3_kernel()<<<grid, OR3_WARPS * 32, sizeof(Or3Scratch) * OR3_WARPS, s>>>(p);
+    return cudaGetLastError();
+}
+
+/* also opts in to the dynamic shared memory on the current device (call once per searcher) */
+int xgm_or3_occupancy_blocks_per_sm() {
+    int n = 0;
+    const size_t smem = sizeof(Or3Scratch) * OR3_WARPS;
+    cudaFuncSetAttribute(or3_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, or3_kernel(), OR3_WARPS * 32, smem);
+    return n;
 }
 
 /* ------------------------------------------------------------------ top-k / ProtoMSet */
