@@ -462,7 +462,7 @@ def ours(args):
         def exchange_stats(bi: int):
             return None
 
-    NSEARCH = 3  # batches in flight in the end-to-end loop (host planning / GPU / result scatter overlap)
+    NSEARCH = int(os.environ.get("XGM_BENCH_NSEARCH", 3))  # batches in flight in the end-to-end loop (host planning / GPU / result scatter overlap)
     searchers = [xgm.Searcher(ix, max_batch=BATCH, max_topk=TOPK) for _ in range(NSEARCH)]
     streams = [torch.cuda.ExternalStream(s.stream(), device=torch.device("cuda", local_rank)) for s in searchers]
 

@@ -212,11 +212,11 @@ def test_process_exits_after_a_large_batch():
     at exit() once blocked every Python process that had submitted a large batch)."""
     import subprocess
     import sys
-    code = ("import sys; sys.path.insert(0, %r)\n"
+    code = ("import sys; sys.path.insert(0, {root!r})\n"
             "from xapiand_b200 import xgm\n"
             "ix = xgm.Index.synthetic(20000, 3000)\n"
             "s = xgm.Searcher(ix, max_batch=640, max_topk=16)\n"
             "r = s.search([xgm.Query(xgm.OP_AND, [i % 50, 50 + i % 40], maxitems=10) for i in range(600)])\n"
-            "print(sum(m.status == 0 for m in r))\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+            "print(sum(m.status == 0 for m in r))\n").format(root=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=180)
     assert p.returncode == 0 and p.stdout.strip() == "600", p.stderr[-500:]

@@ -32,6 +32,7 @@ struct XgmKernelParams {
     const uint32_t* bitmaps;
     const uint32_t* ranks;
     uint32_t lastdocid;
+    uint32_t doclen_lb;           /* Database::get_doclength_lower_bound: block-level weight bounds */
     XgmDevSlot slots[XGM_MAX_SLOTS];
     /* batch */
     const XgmDevQuery* queries;

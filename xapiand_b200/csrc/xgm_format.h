@@ -32,12 +32,13 @@ struct XgmBlockHdr {
     uint32_t first;    /* docid of the block's first posting */
     uint32_t doc_off;  /* offset of the packed docid deltas, in 16-byte units into docs[] */
     uint32_t tf_off;   /* offset of the packed wdfs, in 16-byte units into tfs[] */
-    uint32_t meta;     /* doc_bits | tf_bits << 8 | (count-1) << 16 */
+    uint32_t meta;     /* doc_bits | tf_bits << 8 | (count-1) << 16 | min(255, largest wdf in the block) << 24 */
 };
 
 #define XGM_HDR_DOC_BITS(m) ((m) & 0xffu)
 #define XGM_HDR_TF_BITS(m) (((m) >> 8) & 0xffu)
 #define XGM_HDR_COUNT(m) ((((m) >> 16) & 0xffu) + 1u)
+#define XGM_HDR_MAXWDF(m) ((m) >> 24) /* 255 = "255 or more": use the term's own bound */
 
 #define XGM_NO_BITMAP 0xFFFFFFFFFFFFFFFFull
 #define XGM_NO_SRC 0xFFFFFFFFu

@@ -205,7 +205,7 @@ static void compress_term(Chunk& c, const uint32_t* docids, const uint32_t* wdfs
         h.first = docids[off];
         h.doc_off = (uint32_t)(c.docs.size() / 4);
         h.tf_off = (uint32_t)(c.tfs.size() / 4);
-        h.meta = db | (tb << 8) | ((cnt - 1) << 16);
+        h.meta = db | (tb << 8) | ((cnt - 1) << 16) | (std::min<uint32_t>(maxw, 255u) << 24);
         c.hdr.push_back(h);
         pack_bits(c.docs, delta, cnt, db);
         pack_bits(c.tfs, wdfs + off, cnt, tb);
@@ -780,7 +780,7 @@ extern "C" xgm_status xgm_term_stats_many(const xgm_index* ix, uint32_t n, const
 static void fill_index_params(const xgm_index* ix, XgmKernelParams& p) {
     memset(&p, 0, sizeof(p));
     p.hdr = ix->d_hdr; p.docs = ix->d_docs; p.tfs = ix->d_tfs; p.doclen = ix->d_doclen; p.lastdocid = ix->lastdocid;
-    p.bitmaps = ix->d_bitmaps; p.ranks = ix->d_ranks;
+    p.bitmaps = ix->d_bitmaps; p.ranks = ix->d_ranks; p.doclen_lb = ix->doclen_lb;
     for (int s = 0; s < XGM_MAX_SLOTS; ++s) { p.slots[s].voff = ix->d_voff[s]; p.slots[s].vals = ix->d_vals[s]; }
 }
 
@@ -1913,7 +1913,8 @@ static void finish_info(const PlannedQuery& pq, const XgmDevResult* dr, const do
          * or is never reached.  In between, the reference's min_weight only starts rising at the first
          * replacement after known_matching_docs reached check_at_least (protomset.h:377-398), so it counts
          * more: our count is then a lower bound — flag the bounds. */
-        if (pq.check_at_least > pq.topk + 1 && known < dr->exact && !pq.count_only) o->flags |= XGM_MSET_BOUNDS_APPROX;
+        if (pq.check_at_least > pq.topk + 1 && known < dr->exact && !pq.count_only && pq.sort_by == XGM_SORT_REL_VAL)
+            o->flags |= XGM_MSET_BOUNDS_APPROX; /* relevance-then-value still uses the simple counting rule */
         if (dr->flags & 5u) o->status = XGM_E_UNIMPLEMENTED; /* candidates lost: pathological tie mass */
         if (dr->flags & 2u) o->flags |= XGM_MSET_BOUNDS_APPROX;
         if (dr->flags & 8u) o->flags |= XGM_MSET_BOUNDS_APPROX | XGM_MSET_COUNT_LOWER_BOUND;

@@ -1905,7 +1905,8 @@ __global__ void __launch_bounds__(OR3_WARPS * 32, MINB) xgm_or3_kernel(const __g
     uint32_t qn = 0; /* warp-uniform queue length */
     bool done = false;
     /* current work item: blocks [db, it_b1) of leaf it_drv of query it_query are left */
-    uint32_t it_query = 0, it_b1 = 0, db = 0, it_drv = 0, drv_begin = 0, nterms = 0, ubbkt = 0;
+    uint32_t it_query = 0, it_b1 = 0, db = 0, it_drv = 0, drv_begin = 0, nterms = 0;
+    double others = 0.0, drv_tw = 0.0, drv_maxpart = 0.0;
     uint32_t total_acc = 0; /* documents this lane owns in the current item (exact match count) */
     bool can_prune = false;
     const XgmDevQuery* q = p.queries;
@@ -1937,7 +1938,22 @@ __global__ void __launch_bounds__(OR3_WARPS * 32, MINB) xgm_or3_kernel(const __g
             const uint32_t pmd = alive ? ws.qpm[qn + lane] : 0u;
             const uint32_t qi = qp & 0x1ffffffu, pos = qp >> 25, pm = pmd & 0xffffu, drv = pmd >> 16;
             double acc = 0.0;
+            bool score = alive;
             if (alive) {
+                /* before the other leaves are looked up: the owner's exact weight plus the bounds of the others
+                 * already decides most documents (MaxScore at its finest grain) */
+                const XgmDevQuery* mq = &p.queries[qi];
+                const uint32_t bstar = (mq->sort_by == 0 && mq->topk != 0) ? *reinterpret_cast<volatile uint32_t*>(&p.qstate[qi].bstar) : 0u;
+                if (bstar != 0) {
+                    const XgmBlockHdr hh = hdr[src];
+                    const uint32_t tf = unpack_gl(p.tfs, hh.tf_off, pos, XGM_HDR_TF_BITS(hh.meta));
+                    double ub = bm25_sumpart(mq->terms[drv].termweight, mq, tf, __ldg(&p.doclen[d]));
+                    for (uint32_t i = 0; i < mq->nterms; ++i)
+                        if ((pm >> i & 1u) && i != drv) ub += mq->terms[i].maxpart;
+                    if (match_bucket(mq, ub * (1.0 + 1e-12), 0) < bstar) score = false;
+                }
+            }
+            if (score) {
                 const XgmDevQuery* mq = &p.queries[qi];
                 const uint32_t dlen = __ldg(&p.doclen[d]);
                 /* weight = fold of the tree over the leaves present (OrPostList::get_weight, orpostlist.cc:93-103) */
@@ -1981,7 +1997,7 @@ __global__ void __launch_bounds__(OR3_WARPS * 32, MINB) xgm_or3_kernel(const __g
                 }
                 acc = stk[0];
             }
-            emit_match_lanes(p, lane, alive, qi, acc, d, (uint32_t)__popc(pm), false);
+            emit_match_lanes(p, lane, score, qi, acc, d, (uint32_t)__popc(pm), false);
             __syncwarp();
             continue;
         }
@@ -2022,13 +2038,15 @@ __global__ void __launch_bounds__(OR3_WARPS * 32, MINB) xgm_or3_kernel(const __g
             drv_begin = q->terms[it_drv].blk_begin;
 #pragma unroll
             for (int j = 0; j < OR3_MAX_LEAVES; ++j) bmp[j] = p.bitmaps + ((uint32_t)j < nterms ? q->terms[j].bm_off : 0ull);
-            /* lane m holds the pruning bucket of presence mask m: the bound of a document is the sum of the
-             * get_maxpart bounds of the leaves it contains (the bound and the tree-order sum round differently) */
+            /* lane m holds, for presence mask m, the sum of the get_maxpart bounds of the leaves other than the
+             * owner; the owner's own bound is per block (its largest wdf is in the header) */
             {
                 double ub = 0.0;
                 for (uint32_t i = 0; i < nterms; ++i)
-                    if (lane >> i & 1u) ub += q->terms[i].maxpart;
-                ubbkt = match_bucket(q, ub * (1.0 + 1e-12), 0);
+                    if ((lane >> i & 1u) && i != it_drv) ub += q->terms[i].maxpart;
+                others = ub;
+                drv_tw = q->terms[it_drv].termweight;
+                drv_maxpart = q->terms[it_drv].maxpart;
             }
             for (uint32_t b = db; b < it_b1 && b < db + 3; ++b) issue(b);
             continue;
@@ -2057,6 +2075,14 @@ __global__ void __launch_bounds__(OR3_WARPS * 32, MINB) xgm_or3_kernel(const __g
             }
             const uint32_t rarer = (1u << it_drv) - 1u;
             const uint32_t bstar = can_prune ? *reinterpret_cast<volatile uint32_t*>(&p.qstate[it_query].bstar) : 0u;
+            /* pruning bucket of every presence mask for THIS block: the owner contributes at most its weight at
+             * the block's largest wdf and the shortest document (increasing in wdf, decreasing in length) */
+            uint32_t ubbkt = XGM_NBINS;
+            if (bstar != 0) {
+                const uint32_t mw = XGM_HDR_MAXWDF(h.w);
+                const double own = mw == 255u ? drv_maxpart : bm25_sumpart(drv_tw, q, mw, p.doclen_lb);
+                ubbkt = match_bucket(q, (own + others) * (1.0 + 1e-12), 0);
+            }
             uint32_t cand = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {

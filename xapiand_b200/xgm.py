@@ -511,9 +511,12 @@ class Searcher:
         return out
 
     def search(self, queries: Union[QueryBatch, Sequence[Query]]) -> List[MSet]:
+        if not isinstance(queries, QueryBatch) and len(queries) > self.max_batch:
+            out: List[MSet] = []  # split into max_batch chunks
+            for a in range(0, len(queries), self.max_batch):
+                out += self.search(queries[a:a + self.max_batch])
+            return out
         batch = queries if isinstance(queries, QueryBatch) else QueryBatch(queries)
-        out: List[MSet] = []
-        # split into max_batch chunks
         if batch.n <= self.max_batch:
             self.submit(batch)
             return self.wait()
