@@ -96,6 +96,17 @@ void xgm_builder_free(xgm_builder*);
 xgm_status xgm_index_build_synthetic(uint32_t ndocs, uint32_t vocab, uint64_t seed, uint32_t nshards,
                                      uint32_t shard, int with_values, int device, int host_threads,
                                      xgm_index** out);
+/* A glass database directory, read directly: `iamglass` + the B-tree of `postlist.glass` (posting lists,
+ * document lengths, value streams and statistics all live there) are parsed by the library itself — no Xapian
+ * code, no cursors (src/xapian/backends/glass/glass_table.h:66-300, glass_postlist.cc:677-695,
+ * glass_values.cc:69-91, glass_version.cc:97-234).  The index carries the
+ * database's revision; value slots go in as stored (xgm_builder_add_value_slot_serialised). */
+xgm_status xgm_index_open(const char* glass_path, int device, xgm_index** out);
+/* Host-only helpers of the same reader: the revision and document counts of the version file (to decide
+ * whether an index is stale), and a dump in the XGMFLAT1 format of `oracle/ref_runner export`, which is how
+ * the reader is pinned against the reference's own iterators without a GPU. */
+xgm_status xgm_glass_revision(const char* glass_path, uint64_t* revision, uint32_t* doccount, uint32_t* lastdocid);
+xgm_status xgm_glass_export_flat(const char* glass_path, const char* out_path);
 /* XGMFLAT1 file (oracle/ref_runner `export`: a glass DB dumped through the public iterators). */
 xgm_status xgm_index_load_flat(const char* path, int device, xgm_index** out);
 void xgm_index_close(xgm_index*);

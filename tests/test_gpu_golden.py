@@ -262,24 +262,12 @@ def test_cuda_matches_reference_more_regimes(tag):
 
 
 
-def test_cuda_matches_xapiand_multivalue_classes():
-    """SURVEY.md §8 rows a15 / a16 against Xapiand's REAL classes (multivalue_5k fixture: src/multivalue/range.cc,
-    keymaker.cc, serialise_list.h, sortable_serialise.cc compiled from the reference).  The index is built from the
-    slot bytes exactly as Xapiand stores them (xgm_builder_add_value_slot_serialised); range bounds and the
-    missing-value keys go in as value keys of the reference's serialised bytes; MSetIterator::get_sort_key bytes are
-    rebuilt from the device's keys (xgm_sort_key_bytes) and must equal Multi_MultiValueKeyMaker's."""
+def _check_multivalue(ix, fx, revision):
     from oracle import oracle as O
-    fx = load("multivalue_5k")
-    orc = O.Index.synthetic(fx["ndocs"], fx["vocab"], fx["seed"])  # the corpus' postings only
-    terms = [(orc.name(t),) + tuple(orc.postings(t)) for t in range(orc.nterms)]
-    last = orc.lastdocid
-    slots = {int(s): [bytes.fromhex(fx["slots"][s].get(str(d), "")) for d in range(last + 1)] for s in fx["slots"]}
-    ix = xgm.Index.from_postings(orc.doclen(), terms, serialised_slots=slots, revision=7)
-    assert ix.info().revision == 7
     key = lambda v: xgm.value_key(bytes.fromhex(fx["serialised"][str(v)]))[0]
     qs = []
     for q in fx["queries"]:
-        kw = dict(first=q["first"], maxitems=q["maxitems"], check_at_least=q["check_at_least"], revision=7)
+        kw = dict(first=q["first"], maxitems=q["maxitems"], check_at_least=q["check_at_least"], revision=revision)
         if "mvr" in q:
             kw.update(filter=xgm.FILTER_MULTI_RANGE, filter_slot=q["mvr"][0], range_lo=key(q["mvr"][1]),
                       range_hi=key(q["mvr"][2]), filter_weighted=bool(q["mvr"][3]))
@@ -300,6 +288,47 @@ def test_cuda_matches_xapiand_multivalue_classes():
         mine = [O.convert_to_percent(w, m.percent_scale_factor) for w in m.weights]
         assert mine == q["percents"], ctx
     assert exact_bounds >= len(qs) * 3 // 4
+
+
+def test_cuda_matches_xapiand_multivalue_classes():
+    """SURVEY.md §8 rows a15 / a16 against Xapiand's REAL classes (multivalue_5k fixture: src/multivalue/range.cc,
+    keymaker.cc, serialise_list.h, sortable_serialise.cc compiled from the reference).  The index is built from the
+    slot bytes exactly as Xapiand stores them (xgm_builder_add_value_slot_serialised); range bounds and the
+    missing-value keys go in as value keys of the reference's serialised bytes; MSetIterator::get_sort_key bytes are
+    rebuilt from the device's keys (xgm_sort_key_bytes) and must equal Multi_MultiValueKeyMaker's."""
+    from oracle import oracle as O
+    fx = load("multivalue_5k")
+    orc = O.Index.synthetic(fx["ndocs"], fx["vocab"], fx["seed"])  # the corpus' postings only
+    terms = [(orc.name(t),) + tuple(orc.postings(t)) for t in range(orc.nterms)]
+    last = orc.lastdocid
+    slots = {int(s): [bytes.fromhex(fx["slots"][s].get(str(d), "")) for d in range(last + 1)] for s in fx["slots"]}
+    ix = xgm.Index.from_postings(orc.doclen(), terms, serialised_slots=slots, revision=7)
+    assert ix.info().revision == 7
+    _check_multivalue(ix, fx, 7)
     # a query that names another revision is refused with XGM_E_STALE (→ Xapian::DatabaseModifiedError)
     stale = xgm.Searcher(ix, max_batch=1, max_topk=16).search([xgm.Query(xgm.OP_AND, ["T000001"], revision=8)])
     assert stale[0].status == xgm.E_STALE
+
+
+def test_direct_glass_reader_index_matches_xapiand_multivalue_classes():
+    """xgm_index_open reads the glass directory itself (iamglass + the postlist B-tree:
+    posting chunks, document lengths, value streams) — the same fixture as above must come out of an index built that
+    way from the database the reference wrote, carrying the database's own revision."""
+    import ctypes
+    import shutil
+    import tempfile
+    from oracle import oracle as O
+    if not O.have_reference():
+        pytest.skip("compiled reference (oracle/_ref) not shipped")
+    fx = load("multivalue_5k")
+    tmp = tempfile.mkdtemp(prefix="xgm_glass_")
+    try:
+        db = tmp + "/db"
+        O.ref_build(db, fx["ndocs"], fx["vocab"], seed=fx["seed"], mvalues=True, sparse=fx["sparse"])
+        rev = ctypes.c_uint64()
+        assert xgm.lib().xgm_glass_revision(db.encode(), ctypes.byref(rev), None, None) == 0
+        ix = xgm.Index.open_glass(db)
+        assert ix.info().revision == rev.value and ix.info().doccount == fx["ndocs"]
+        _check_multivalue(ix, fx, rev.value)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)

@@ -44,6 +44,15 @@ static xgm_status fail(xgm_status st, const char* fmt, ...) {
             return fail(XGM_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
+/* for the other translation units of the library (xgm_glass.cu) */
+xgm_status xgm_fail(xgm_status st, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return st;
+}
+
 extern "C" const char* xgm_last_error(void) { return g_err; }
 extern "C" uint32_t xgm_abi_version(void) { return XGM_ABI_VERSION; }
 
@@ -371,6 +380,14 @@ extern "C" xgm_status xgm_builder_add_term(xgm_builder* b, const char* term, uin
     b->names.emplace_back(term, term_len);
     b->first_wdf.push_back(n ? wdfs[0] : 0);
     b->ub_given.push_back(wdf_ub != 0);
+    return XGM_OK;
+}
+
+/* internal: a reference-provided wdf bound of 0 is authoritative (0 otherwise means "derive it") */
+xgm_status xgm_builder_force_wdf_ub(xgm_builder* b, uint32_t term_id, uint32_t wdf_ub) {
+    if (!b || term_id >= b->terms.size()) return fail(XGM_E_INVALID, "bad term id");
+    b->terms[term_id].wdf_ub = wdf_ub;
+    b->ub_given[term_id] = true;
     return XGM_OK;
 }
 

@@ -4,9 +4,10 @@
  * What it does for one Matcher::get_mset call:
  *   1. decides whether libxgm covers the request (single local shard, BM25, no decider / spies / collapse /
  *      cut-offs, one of the query shapes of include/xgm.h); anything else is left to the reference matcher;
- *   2. finds — or builds, once per (database uuid, revision) — the HBM index, walking the database through its
- *      public iterators (Database::allterms_begin / postlist_begin / get_doclength / valuestream_begin), the
- *      read side of GlassPostList (backends/glass/glass_postlist.cc:722-991);
+ *   2. finds — or builds, once per (database uuid, revision) — the HBM index: a glass directory is handed to
+ *      xgm_index_open (libxgm parses iamglass + the postlist B-tree itself); any other backend, or a directory
+ *      that has moved on to a newer revision, is walked through the public iterators (Database::allterms_begin /
+ *      postlist_begin / get_doclength / valuestream_begin);
  *   3. translates the Query tree (api/queryinternal.h) and the collated statistics (weight/weightinternal.h)
  *      into an xgm_query, calls xgm_search, and builds the MSet::Internal (api/msetinternal.h:89-99) from the
  *      result exactly as ProtoMSet::finalise does (matcher/protomset.h:672-682).
@@ -30,6 +31,8 @@
 
 #include "xapian.h"
 #include "xapian/api/msetinternal.h"
+#include "xapian/backends/backends.h"
+#include "xapian/backends/databaseinternal.h"
 #include "xapian/api/queryinternal.h"
 #include "xapian/api/result.h"
 #include "xapian/common/pack.h"
@@ -49,7 +52,7 @@ struct Lib {
     XGM_FN(xgm_builder_add_value_slot_serialised) XGM_FN(xgm_builder_set_revision) XGM_FN(xgm_builder_finish)
     XGM_FN(xgm_builder_free) XGM_FN(xgm_index_close) XGM_FN(xgm_searcher_new) XGM_FN(xgm_searcher_free)
     XGM_FN(xgm_search) XGM_FN(xgm_value_key) XGM_FN(xgm_value_key_bytes) XGM_FN(xgm_sort_key_bytes)
-    XGM_FN(xgm_abi_version)
+    XGM_FN(xgm_abi_version) XGM_FN(xgm_index_open) XGM_FN(xgm_index_info_get)
 #undef XGM_FN
 };
 
@@ -77,7 +80,7 @@ Lib& lib() {
         XGM_LOAD(xgm_builder_add_value_slot_serialised) XGM_LOAD(xgm_builder_set_revision) XGM_LOAD(xgm_builder_finish)
         XGM_LOAD(xgm_builder_free) XGM_LOAD(xgm_index_close) XGM_LOAD(xgm_searcher_new) XGM_LOAD(xgm_searcher_free)
         XGM_LOAD(xgm_search) XGM_LOAD(xgm_value_key) XGM_LOAD(xgm_value_key_bytes) XGM_LOAD(xgm_sort_key_bytes)
-        XGM_LOAD(xgm_abi_version)
+        XGM_LOAD(xgm_abi_version) XGM_LOAD(xgm_index_open) XGM_LOAD(xgm_index_info_get)
 #undef XGM_LOAD
         if (!all) { L.why = "libxgm.so lacks an entry point"; return; }
         if (L.xgm_abi_version() != XGM_ABI_VERSION) { L.why = "libxgm.so ABI version mismatch"; return; }
@@ -111,6 +114,23 @@ std::shared_ptr<IndexEntry> build_index(const Xapian::Database& db, Xapian::rev 
     Lib& L = lib();
     auto e = std::make_shared<IndexEntry>();
     e->revision = revision;
+    int device = 0;
+    if (const char* d = getenv("XGM_DEVICE")) device = atoi(d);
+    /* a glass directory is read directly by libxgm (no cursors); only if what is on disk is the very revision
+     * this Database object sees — otherwise (a writer committed meanwhile) walk the snapshot we were given */
+    {
+        std::string path;
+        const char* direct = getenv("XGM_SHIM_DIRECT_GLASS");
+        if (!(direct && *direct == '0') && db.size() == 1 &&
+            db.internal->get_backend_info(&path) == BACKEND_GLASS && !path.empty()) {
+            xgm_index* ix = nullptr;
+            if (L.xgm_index_open(path.c_str(), device, &ix) == XGM_OK) {
+                xgm_index_info info;
+                if (L.xgm_index_info_get(ix, &info) == XGM_OK && info.revision == revision) { e->ix = ix; return e; }
+                L.xgm_index_close(ix);
+            }
+        }
+    }
     xgm_builder* b = nullptr;
     if (L.xgm_builder_new(&b) != XGM_OK) { e->failed = L.xgm_last_error(); return e; }
     const Xapian::docid last = db.get_lastdocid();
@@ -143,8 +163,6 @@ std::shared_ptr<IndexEntry> build_index(const Xapian::Database& db, Xapian::rev 
     }
     if (st == XGM_OK) st = L.xgm_builder_set_revision(b, revision);
     if (st != XGM_OK) { e->failed = L.xgm_last_error(); L.xgm_builder_free(b); return e; }
-    int device = 0;
-    if (const char* d = getenv("XGM_DEVICE")) device = atoi(d);
     st = L.xgm_builder_finish(b, device, &e->ix); /* consumes the builder */
     if (st != XGM_OK) { e->failed = L.xgm_last_error(); e->ix = nullptr; }
     return e;

@@ -35,6 +35,7 @@ EXPORTS = [
     "xgm_merge_topk_device_slab",
     "xgm_builder_add_value_slot_serialised", "xgm_builder_set_revision", "xgm_index_value_freq",
     "xgm_value_key", "xgm_value_key_bytes", "xgm_sort_key_bytes", "xgm_term_stats_many",
+    "xgm_index_open", "xgm_glass_revision", "xgm_glass_export_flat",
 ]
 
 
@@ -130,6 +131,9 @@ def lib():
     L.xgm_index_build_synthetic.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int,
                                             C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.xgm_index_load_flat.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.xgm_index_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.xgm_glass_revision.argtypes = [C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.xgm_glass_export_flat.argtypes = [C.c_char_p, C.c_char_p]
     L.xgm_index_close.argtypes = [C.c_void_p]
     L.xgm_index_close.restype = None
     L.xgm_index_info_get.argtypes = [C.c_void_p, C.POINTER(IndexInfo)]
@@ -356,6 +360,13 @@ class Index:
     def load_flat(cls, path: str, device: int = 0) -> "Index":
         h = C.c_void_p()
         _check(lib().xgm_index_load_flat(path.encode(), device, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def open_glass(cls, path: str, device: int = 0) -> "Index":
+        """A glass database directory read directly by the library (xgm_index_open)."""
+        h = C.c_void_p()
+        _check(lib().xgm_index_open(path.encode(), device, C.byref(h)))
         return cls(h)
 
     @classmethod
