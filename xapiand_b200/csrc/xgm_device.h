@@ -42,7 +42,7 @@ struct XgmKernelParams {
     uint32_t nitems, nitems_or, nitems_bm;
     const uint32_t* nitems_bm_dev; /* non-null: item count of the bitmap AND list lives on the device (range-major expansion) */
     uint32_t nq;
-    uint32_t* work_counter;       /* [10],[11] OR items of xgm_or3_kernel (first / second pass); [8..9] 64-bit pool reservation; [0] AND items, [1] OR items, [2],[3] same for the second pass, [4] #queries to re-run, [5] overflow-pool entries reserved, [6],[7] bitmap-AND items (first / second pass) */
+    uint32_t* work_counter;       /* [10],[11] OR items of xgm_or3_kernel (first / second pass); [12],[13] tiles of xgm_or_tile_kernel; [14],[15] items of xgm_or3_kernel<PHASE 1>; [8..9] 64-bit pool reservation; [0] AND items, [1] OR items, [2],[3] same for the second pass, [4] #queries to re-run, [5] overflow-pool entries reserved, [6],[7] bitmap-AND items (first / second pass) */
     uint32_t pass;                /* 0 = first pass, 1 = re-run of overflowed queries with their exact b* */
     XgmQState* qstate;            /* [nq] */
     uint32_t* hist;               /* [nq][XGM_NBINS] */
@@ -64,6 +64,8 @@ struct XgmKernelParams {
     uint64_t* out_k;
     XgmDevResult* out_info;
     XgmRaise* raise_log;          /* [nq][XGM_RAISE_LOG] */
+    const uint32_t* tileq;        /* queries answered by xgm_or_tile_kernel + xgm_or3_kernel<PHASE 1> */
+    uint32_t ntileq;
 };
 
 cudaError_t xgm_launch_and(const XgmKernelParams& p, int grid, cudaStream_t s);
@@ -78,7 +80,9 @@ cudaError_t xgm_launch_expand_ranges(const XgmWorkItem* seg, uint32_t nseg, cons
                                      uint32_t* off, uint32_t* total, XgmWorkItem* out, cudaStream_t s);
 cudaError_t xgm_launch_or(const XgmKernelParams& p, int grid, cudaStream_t s);
 int xgm_or_occupancy_blocks_per_sm();
-cudaError_t xgm_launch_or3(const XgmKernelParams& p, int grid, cudaStream_t s);
+cudaError_t xgm_launch_or3(const XgmKernelParams& p, int grid, int phase, cudaStream_t s);
+cudaError_t xgm_launch_or_tile(const XgmKernelParams& p, int grid, cudaStream_t s);
+int xgm_or_tile_occupancy_blocks_per_sm();
 int xgm_or3_occupancy_blocks_per_sm();
 cudaError_t xgm_launch_topk(const XgmKernelParams& p, uint32_t nq, cudaStream_t s);
 cudaError_t xgm_launch_decode(const XgmKernelParams& p, uint32_t blk_begin, uint32_t nblocks, uint32_t* out_d,

@@ -976,8 +976,12 @@ struct xgm_searcher {
     uint32_t nq = 0, nitems = 0, nitems_or = 0, nitems_bm = 0;
     bool pending = false, any_sort = false;
     xgm_batch_stats stats{};
-    int grid = 0, grid_or = 0, grid_or3 = 0, grid_and2 = 0, grid_bm = 0;
+    int grid = 0, grid_or = 0, grid_or3 = 0, grid_tile = 0, grid_and2 = 0, grid_bm = 0;
     bool any_or_fast = false, any_or_slow = false;
+    uint32_t* h_tileq = nullptr;  /* pinned: queries of the batch answered by the bitmap-union kernel */
+    uint32_t* d_tileq = nullptr;
+    uint32_t ntileq = 0;
+    bool or_tile = true;          /* XGM_OR_TILE=0: keep every fast OR query in the one-launch kernel */
     int and_version = 1; /* 1 = warp-autonomous kernel, 2 = chunked CTA kernel (XGM_AND_KERNEL env) */
     XgmKernelParams params;
     /* xgm_search_submit_async: a worker thread plans and enqueues the batch while the caller scatters the
@@ -1021,7 +1025,7 @@ extern "C" void xgm_searcher_free(xgm_searcher* s) {
     cudaSetDevice(s->ix->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFreeHost(s->h_queries); cudaFreeHost(s->h_items); cudaFreeHost(s->h_items_or); cudaFreeHost(s->h_items_bm); cudaFreeHost(s->h_out_w); cudaFreeHost(s->h_out_d);
-    cudaFreeHost(s->h_out_k); cudaFreeHost(s->h_info); cudaFreeHost(s->h_raise); cudaFree(s->d_raise); cudaFreeHost(s->h_qstate);
+    cudaFreeHost(s->h_out_k); cudaFreeHost(s->h_info); cudaFreeHost(s->h_raise); cudaFree(s->d_raise); cudaFreeHost(s->h_qstate); cudaFreeHost(s->h_tileq); cudaFree(s->d_tileq);
     cudaFree(s->d_queries); cudaFree(s->d_items); cudaFree(s->d_items_or); cudaFree(s->d_items_bm); cudaFree(s->d_exp[0]); cudaFree(s->d_exp[1]); cudaFree(s->d_exp[2]);
     for (int w = 0; w < 3; ++w) { if (s->h_levels[w]) cudaFreeHost(s->h_levels[w]); cudaFree(s->d_levels[w]); } cudaFree(s->d_ctrl); cudaFree(s->d_match_w); cudaFree(s->d_match_d);
     cudaFree(s->d_match_k); cudaFree(s->d_pool_w); cudaFree(s->d_pool_d); cudaFree(s->d_pool_k); cudaFree(s->d_slab); cudaFree(s->d_out_k);
@@ -1112,6 +1116,9 @@ extern "C" xgm_status xgm_searcher_new(const xgm_index* ix, uint32_t max_batch, 
     CUDA_TRY(cudaMalloc(&s->d_queries, nq * sizeof(XgmDevQuery)));
     CUDA_TRY(cudaMallocHost(&s->h_raise, nq * XGM_RAISE_LOG * sizeof(XgmRaise)));
     CUDA_TRY(cudaMallocHost(&s->h_qstate, nq * sizeof(XgmQState)));
+    CUDA_TRY(cudaMallocHost(&s->h_tileq, nq * 4));
+    CUDA_TRY(cudaMalloc(&s->d_tileq, nq * 4));
+    if (const char* e = getenv("XGM_OR_TILE")) s->or_tile = atoi(e) != 0;
     CUDA_TRY(cudaMalloc(&s->d_raise, nq * XGM_RAISE_LOG * sizeof(XgmRaise)));
     s->ctrl_bytes = 64 + nq * sizeof(XgmQState) + nq * XGM_NBINS * 4;
     CUDA_TRY(cudaMalloc(&s->d_ctrl, s->ctrl_bytes));
@@ -1147,6 +1154,9 @@ extern "C" xgm_status xgm_searcher_new(const xgm_index* ix, uint32_t max_batch, 
     occ = xgm_or3_occupancy_blocks_per_sm();
     if (occ < 1) occ = 1;
     s->grid_or3 = ix->sm_count * occ;
+    occ = xgm_or_tile_occupancy_blocks_per_sm();
+    if (occ < 1) occ = 1;
+    s->grid_tile = ix->sm_count * occ;
     occ = xgm_and_bm_occupancy_blocks_per_sm();
     if (occ < 1) occ = 1;
     s->grid_bm = ix->sm_count * occ;
@@ -1623,7 +1633,8 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
     } else {
         bool fastor = n <= 5 && !(getenv("XGM_OR_KERNEL") && atoi(getenv("XGM_OR_KERNEL")) == 1);
         for (uint32_t leaf = 0; leaf < n; ++leaf) fastor = fastor && dq.terms[leaf].bm_off != XGM_NO_BITMAP;
-        dq.or_fast = fastor ? 1u : 0u;
+        /* relevance order, no predicate, results wanted: multi-leaf documents by bitmap union first (or_fast 2) */
+        dq.or_fast = !fastor ? 0u : (s->or_tile && q.filter == XGM_FILTER_NONE && q.sort_by == XGM_SORT_REL && dq.topk != 0) ? 2u : 1u;
         for (uint32_t leaf = 0; leaf < n; ++leaf) {
             XgmWorkItem wi;
             wi.query = qi; wi.b0 = dq.terms[leaf].nblocks; wi.b1 = 0; wi.pad = leaf;
@@ -1677,8 +1688,13 @@ static xgm_status launch_batch(xgm_searcher* s) {
     };
     if (s->nitems_bm) { CUDA_TRY(xgm_launch_and_bm(p, s->grid_bm, cs)); s->stats.kernel_launches++; }
     if (s->nitems) { CUDA_TRY(launch_and(p)); s->stats.kernel_launches++; }
-    if (s->nitems_or && s->any_or_fast) { CUDA_TRY(xgm_launch_or3(p, s->grid_or3, cs)); s->stats.kernel_launches++; }
+    if (s->nitems_or && s->any_or_fast) { CUDA_TRY(xgm_launch_or3(p, s->grid_or3, 0, cs)); s->stats.kernel_launches++; }
     if (s->nitems_or && s->any_or_slow) { CUDA_TRY(xgm_launch_or(p, s->grid_or, cs)); s->stats.kernel_launches++; }
+    if (s->ntileq) { /* documents with >= 2 leaves by bitmap union, then the single-leaf ones against the threshold */
+        CUDA_TRY(xgm_launch_or_tile(p, s->grid_tile, cs));
+        CUDA_TRY(xgm_launch_or3(p, s->grid_or3, 1, cs));
+        s->stats.kernel_launches += 2;
+    }
     CUDA_TRY(cudaEventRecord(s->ev1, cs));
     CUDA_TRY(xgm_launch_topk(p, s->nq, cs));
     s->stats.kernel_launches++;
@@ -1687,8 +1703,13 @@ static xgm_status launch_batch(xgm_searcher* s) {
     p2.pass = 1;
     if (s->nitems_bm) { CUDA_TRY(xgm_launch_and_bm(p2, s->grid_bm, cs)); s->stats.kernel_launches++; }
     if (s->nitems) { CUDA_TRY(launch_and(p2)); s->stats.kernel_launches++; }
-    if (s->nitems_or && s->any_or_fast) { CUDA_TRY(xgm_launch_or3(p2, s->grid_or3, cs)); s->stats.kernel_launches++; }
+    if (s->nitems_or && s->any_or_fast) { CUDA_TRY(xgm_launch_or3(p2, s->grid_or3, 0, cs)); s->stats.kernel_launches++; }
     if (s->nitems_or && s->any_or_slow) { CUDA_TRY(xgm_launch_or(p2, s->grid_or, cs)); s->stats.kernel_launches++; }
+    if (s->ntileq) {
+        CUDA_TRY(xgm_launch_or_tile(p2, s->grid_tile, cs));
+        CUDA_TRY(xgm_launch_or3(p2, s->grid_or3, 1, cs));
+        s->stats.kernel_launches += 2;
+    }
     CUDA_TRY(xgm_launch_topk(p2, s->nq, cs));
     s->stats.kernel_launches++;
     CUDA_TRY(cudaEventRecord(s->ev2, cs));
@@ -1871,8 +1892,15 @@ static xgm_status submit_impl(xgm_searcher* s, const xgm_query* queries, uint32_
     s->any_raise = false;
     for (uint32_t i = 0; i < nq; ++i) s->any_raise |= s->plan[i].log_raises;
     s->any_or_fast = s->any_or_slow = false;
+    s->ntileq = 0;
     for (uint32_t i = 0; i < nq; ++i)
-        if (s->h_queries[i].route == 1 && s->plan[i].on_device) { if (s->h_queries[i].or_fast) s->any_or_fast = true; else s->any_or_slow = true; }
+        if (s->h_queries[i].route == 1 && s->plan[i].on_device) {
+            if (s->h_queries[i].or_fast == 2) s->h_tileq[s->ntileq++] = i;
+            else if (s->h_queries[i].or_fast) s->any_or_fast = true;
+            else s->any_or_slow = true;
+        }
+    p.tileq = s->d_tileq; p.ntileq = s->ntileq;
+    if (s->ntileq) CUDA_TRY(cudaMemcpyAsync(s->d_tileq, s->h_tileq, (size_t)s->ntileq * 4, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaMemcpyAsync(s->d_queries, s->h_queries, (size_t)nq * sizeof(XgmDevQuery), cudaMemcpyHostToDevice, s->stream));
     if (s->nseg[0])
         CUDA_TRY(cudaMemcpyAsync(s->d_items, s->h_items, (size_t)s->nseg[0] * sizeof(XgmWorkItem), cudaMemcpyHostToDevice, s->stream));

@@ -1087,7 +1087,9 @@ __device__ __forceinline__ void emit_match_lanes(const XgmKernelParams& p, uint3
                     p.match_w[o] = w; p.match_d[o] = d; p.match_k[o] = kv;
                 }
                 const uint32_t after = idx + 1;
-                crossed = (idx >> 8) != (after >> 8) && after >= q->topk && after >= p.keep_cap / 2;
+                /* (AND: not before half of what the top-k kernel can rank is in use, so that small match sets stay
+                 * unpruned and their known_matching_docs is exact; an OR's union is far larger than that anyway) */
+                crossed = (idx >> 8) != (after >> 8) && after >= q->topk && (q->route == 1 || after >= p.keep_cap / 2);
             } else if (idx < st->pool_cap) {
                 const size_t o = (size_t)st->pool_off + idx;
                 p.pool_w[o] = w; p.pool_d[o] = d; p.pool_k[o] = kv;
@@ -1864,6 +1866,56 @@ __global__ void __launch_bounds__(OR_WARPS * 32) xgm_or_kernel(XgmKernelParams p
     }
 }
 
+/* Weight of document d of an OR query = fold of the reference's OrPostList tree over the leaves present
+ * (OrPostList::get_weight, orpostlist.cc:93-103; presence mask pm over leaf positions).  The wdf of leaf `drv`
+ * (the owner, if any: drv < nterms) comes from position pos of the block whose header is hdr[src]; every other
+ * leaf is looked up through its rank directory.  At most OR3_MAX_LEAVES leaves: the stack stays in registers. */
+#define OR3_MAX_LEAVES 5
+__device__ __forceinline__ double or_score_doc(const XgmKernelParams& p, const XgmDevQuery* mq, uint32_t d, uint32_t pm,
+                                               uint32_t drv, uint32_t src, uint32_t pos) {
+    const XgmBlockHdr* __restrict__ hdr = p.hdr;
+    const uint32_t dlen = __ldg(&p.doclen[d]);
+    double stk[OR3_MAX_LEAVES + 1];
+    uint32_t has = 0;
+    int sp = 0;
+    const uint32_t plen = mq->prog_len;
+    for (uint32_t i = 0; i < plen; ++i) {
+        const int op = mq->prog[i];
+        if (op >= 0) {
+            if (pm >> op & 1u) {
+                uint32_t tf;
+                if ((uint32_t)op == drv) {
+                    const XgmBlockHdr hh = hdr[src];
+                    tf = unpack_gl(p.tfs, hh.tf_off, pos, XGM_HDR_TF_BITS(hh.meta));
+                } else {
+                    const uint32_t r = bitmap_rank(p, mq->terms[op], d);
+                    const XgmBlockHdr bh = hdr[mq->terms[op].blk_begin + (r >> 7)];
+                    tf = unpack_gl(p.tfs, bh.tf_off, r & 127u, XGM_HDR_TF_BITS(bh.meta));
+                }
+                const double v = bm25_sumpart(mq->terms[op].termweight, mq, tf, dlen);
+                /* static indexing keeps the stack in registers */
+                if (sp == 0) stk[0] = v; else if (sp == 1) stk[1] = v; else if (sp == 2) stk[2] = v;
+                else if (sp == 3) stk[3] = v; else if (sp == 4) stk[4] = v; else stk[5] = v;
+                has |= 1u << sp;
+            } else {
+                has &= ~(1u << sp);
+            }
+            ++sp;
+        } else {
+            --sp;
+            const bool hl = has >> (sp - 1) & 1u, hr = has >> sp & 1u;
+            const double r = sp == 1 ? stk[1] : sp == 2 ? stk[2] : sp == 3 ? stk[3] : sp == 4 ? stk[4] : stk[5];
+            const double l = sp == 1 ? stk[0] : sp == 2 ? stk[1] : sp == 3 ? stk[2] : sp == 4 ? stk[3] : stk[4];
+            double v = l;
+            if (hl && hr) v = __dadd_rn(l, r);
+            else if (hr) { v = r; has |= 1u << (sp - 1); }
+            if (sp == 1) stk[0] = v; else if (sp == 2) stk[1] = v; else if (sp == 3) stk[2] = v;
+            else if (sp == 4) stk[3] = v; else stk[4] = v;
+        }
+    }
+    return stk[0];
+}
+
 /* ------------------------------------------------------------------ OR kernel, bitmap leaves + queued scoring */
 
 /* Same contract as xgm_or_kernel for queries whose leaves ALL have membership bitmaps and number at most five
@@ -1877,7 +1929,6 @@ __global__ void __launch_bounds__(OR_WARPS * 32) xgm_or_kernel(XgmKernelParams p
  * program (orpostlist.cc:93-103).  The queue lives as long as the warp, so scoring always runs on full warps. */
 #define OR3_WARPS 8
 #define OR3_QCAP 160 /* < 32 left over + up to 128 new candidates per iteration */
-#define OR3_MAX_LEAVES 5
 
 struct __align__(16) Or3Scratch {
     uint32_t dstage[4][STAGE_WORDS];
@@ -1888,7 +1939,10 @@ struct __align__(16) Or3Scratch {
     uint64_t dbar[4];
 };
 
-template <int MINB>
+/* PHASE 0: the whole union in one launch (queries with or_fast == 1).  PHASE 1: the documents holding exactly ONE
+ * leaf of the queries whose documents with two or more leaves were already produced by xgm_or_tile_kernel
+ * (or_fast == 2) — see there. */
+template <int MINB, int PHASE>
 __global__ void __launch_bounds__(OR3_WARPS * 32, MINB) xgm_or3_kernel(const __grid_constant__ XgmKernelParams p) {
     extern __shared__ __align__(16) unsigned char or3_raw[];
     Or3Scratch* scratch = reinterpret_cast<Or3Scratch*>(or3_raw);
@@ -1953,50 +2007,7 @@ __global__ void __launch_bounds__(OR3_WARPS * 32, MINB) xgm_or3_kernel(const __g
                     if (match_bucket(mq, ub * (1.0 + 1e-12), 0) < bstar) score = false;
                 }
             }
-            if (score) {
-                const XgmDevQuery* mq = &p.queries[qi];
-                const uint32_t dlen = __ldg(&p.doclen[d]);
-                /* weight = fold of the tree over the leaves present (OrPostList::get_weight, orpostlist.cc:93-103) */
-                double stk[OR3_MAX_LEAVES + 1];
-                uint32_t has = 0;
-                int sp = 0;
-                const uint32_t plen = mq->prog_len;
-                for (uint32_t i = 0; i < plen; ++i) {
-                    const int op = mq->prog[i];
-                    if (op >= 0) {
-                        if (pm >> op & 1u) {
-                            uint32_t tf;
-                            if ((uint32_t)op == drv) {
-                                const XgmBlockHdr hh = hdr[src];
-                                tf = unpack_gl(p.tfs, hh.tf_off, pos, XGM_HDR_TF_BITS(hh.meta));
-                            } else {
-                                const uint32_t r = bitmap_rank(p, mq->terms[op], d);
-                                const XgmBlockHdr bh = hdr[mq->terms[op].blk_begin + (r >> 7)];
-                                tf = unpack_gl(p.tfs, bh.tf_off, r & 127u, XGM_HDR_TF_BITS(bh.meta));
-                            }
-                            const double v = bm25_sumpart(mq->terms[op].termweight, mq, tf, dlen);
-                            /* static indexing keeps the stack in registers */
-                            if (sp == 0) stk[0] = v; else if (sp == 1) stk[1] = v; else if (sp == 2) stk[2] = v;
-                            else if (sp == 3) stk[3] = v; else if (sp == 4) stk[4] = v; else stk[5] = v;
-                            has |= 1u << sp;
-                        } else {
-                            has &= ~(1u << sp);
-                        }
-                        ++sp;
-                    } else {
-                        --sp;
-                        const bool hl = has >> (sp - 1) & 1u, hr = has >> sp & 1u;
-                        const double r = sp == 1 ? stk[1] : sp == 2 ? stk[2] : sp == 3 ? stk[3] : sp == 4 ? stk[4] : stk[5];
-                        const double l = sp == 1 ? stk[0] : sp == 2 ? stk[1] : sp == 3 ? stk[2] : sp == 4 ? stk[3] : stk[4];
-                        double v = l;
-                        if (hl && hr) v = __dadd_rn(l, r);
-                        else if (hr) { v = r; has |= 1u << (sp - 1); }
-                        if (sp == 1) stk[0] = v; else if (sp == 2) stk[1] = v; else if (sp == 3) stk[2] = v;
-                        else if (sp == 4) stk[3] = v; else stk[4] = v;
-                    }
-                }
-                acc = stk[0];
-            }
+            if (score) acc = or_score_doc(p, &p.queries[qi], d, pm, drv, src, pos);
             emit_match_lanes(p, lane, score, qi, acc, d, (uint32_t)__popc(pm), false);
             __syncwarp();
             continue;
@@ -2010,13 +2021,13 @@ __global__ void __launch_bounds__(OR3_WARPS * 32, MINB) xgm_or3_kernel(const __g
                 total_acc = 0; it_b1 = 0; db = 0;
             }
             uint32_t item = 0;
-            if (lane == 0) item = atomicAdd(p.work_counter + 10 + p.pass, 1u);
+            if (lane == 0) item = atomicAdd(p.work_counter + (PHASE ? 14 : 10) + p.pass, 1u);
             item = __shfl_sync(FULL, item, 0);
             if (item >= p.nitems_or) { done = true; continue; }
             const XgmWorkItem wi = p.items_or[item];
             if (p.pass != 0 && p.qstate[wi.query].rerun == 0) continue;
             q = &p.queries[wi.query];
-            if (q->or_fast == 0) continue; /* this query's items belong to xgm_or_kernel */
+            if (q->or_fast != (PHASE ? 2u : 1u)) continue; /* another kernel's query */
             nterms = q->nterms;
             it_drv = wi.pad;
             can_prune = (q->sort_by == 0) && (q->topk != 0);
@@ -2024,7 +2035,10 @@ __global__ void __launch_bounds__(OR3_WARPS * 32, MINB) xgm_or3_kernel(const __g
             if (can_prune) {
                 const XgmQState* st = &p.qstate[wi.query];
                 const uint32_t bstar = *reinterpret_cast<const volatile uint32_t*>(&st->bstar);
-                if (bstar != 0 && *reinterpret_cast<const volatile uint32_t*>(&st->total) >= q->check_at_least) {
+                if (PHASE) {
+                    /* only single-leaf documents are left: none of this leaf can reach the threshold */
+                    if (bstar != 0 && match_bucket(q, q->terms[it_drv].maxpart * (1.0 + 1e-12), 0) < bstar) continue;
+                } else if (bstar != 0 && *reinterpret_cast<const volatile uint32_t*>(&st->total) >= q->check_at_least) {
                     double ub = 0.0;
                     for (uint32_t i = it_drv; i < nterms; ++i) ub += q->terms[i].maxpart;
                     ub *= 1.0 + 1e-12;
@@ -2057,6 +2071,15 @@ __global__ void __launch_bounds__(OR3_WARPS * 32, MINB) xgm_or3_kernel(const __g
             const uint4 h = __ldg(reinterpret_cast<const uint4*>(hdr + drv_begin + db));
             const uint32_t bits = XGM_HDR_DOC_BITS(h.w), cnt = XGM_HDR_COUNT(h.w), cur = db & 3u;
             if (bits) { mbar_wait_a(bar_base + cur * 8u, (phases >> cur) & 1u); phases ^= 1u << cur; }
+            if (PHASE) {
+                /* a block whose best possible single-leaf document is below the threshold is skipped whole */
+                const uint32_t bs = *reinterpret_cast<volatile uint32_t*>(&p.qstate[it_query].bstar);
+                if (bs != 0) {
+                    const uint32_t mw = XGM_HDR_MAXWDF(h.w);
+                    const double own = mw == 255u ? drv_maxpart : bm25_sumpart(drv_tw, q, mw, p.doclen_lb);
+                    if (match_bucket(q, own * (1.0 + 1e-12), 0) < bs) { ++db; continue; }
+                }
+            }
             uint32_t c[4];
             decode_docids(ws.dstage[cur], bits, h.x, lane, c);
             const int nv = min(4, max(0, (int)cnt - 4 * (int)lane));
@@ -2089,9 +2112,14 @@ __global__ void __launch_bounds__(OR3_WARPS * 32, MINB) xgm_or3_kernel(const __g
                 const uint32_t m = pm[k] | (1u << it_drv);
                 pm[k] = m;
                 const uint32_t bk = __shfl_sync(FULL, ubbkt, m & 31u);
-                bool own = (valid >> k & 1u) && (m & rarer) == 0u; /* a rarer leaf owns the document otherwise */
-                if (own && q->filter && !doc_passes_filter(p, q, c[k])) own = false;
-                total_acc += own ? 1u : 0u;
+                bool own;
+                if (PHASE) {
+                    own = (valid >> k & 1u) && m == (1u << it_drv); /* no other leaf holds the document */
+                } else {
+                    own = (valid >> k & 1u) && (m & rarer) == 0u; /* a rarer leaf owns the document otherwise */
+                    if (own && q->filter && !doc_passes_filter(p, q, c[k])) own = false;
+                    total_acc += own ? 1u : 0u;
+                }
                 if (own && bk >= bstar) cand |= 1u << k;
             }
             const uint32_t B = __ballot_sync(FULL, cand != 0);
@@ -2123,11 +2151,9 @@ __global__ void __launch_bounds__(OR3_WARPS * 32, MINB) xgm_or3_kernel(const __g
     }
 }
 
-typedef void (*or3_fn)(const XgmKernelParams);
-static or3_fn or3_kernel() { return xgm_or3_kernel<3>; }
-
-cudaError_t xgm_launch_or3(const XgmKernelParams& p, int grid, cudaStream_t s) {
-    or3_kernel()<<<grid, OR3_WARPS * 32, sizeof(Or3Scratch) * OR3_WARPS, s>>>(p);
+cudaError_t xgm_launch_or3(const XgmKernelParams& p, int grid, int phase, cudaStream_t s) {
+    if (phase) xgm_or3_kernel<3, 1><<<grid, OR3_WARPS * 32, sizeof(Or3Scratch) * OR3_WARPS, s>>>(p);
+    else xgm_or3_kernel<3, 0><<<grid, OR3_WARPS * 32, sizeof(Or3Scratch) * OR3_WARPS, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -2135,8 +2161,130 @@ cudaError_t xgm_launch_or3(const XgmKernelParams& p, int grid, cudaStream_t s) {
 int xgm_or3_occupancy_blocks_per_sm() {
     int n = 0;
     const size_t smem = sizeof(Or3Scratch) * OR3_WARPS;
-    cudaFuncSetAttribute(or3_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, or3_kernel(), OR3_WARPS * 32, smem);
+    cudaFuncSetAttribute(xgm_or3_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(xgm_or3_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, xgm_or3_kernel<3, 0>, OR3_WARPS * 32, smem);
+    return n;
+}
+
+/* ------------------------------------------------------------------ OR by bitmap union (documents with >= 2 leaves) */
+
+/* For an OR whose leaves all have membership bitmaps the union needs no posting list at all: word w of the
+ * union is the OR of word w of every leaf's bitmap — coalesced 128-byte reads per leaf and warp, 6 MB per
+ * 5-leaf query over 10M documents — and its population count is the exact match count (no ownership logic).  The
+ * same words give "held by two or more leaves" (two |= one & x; one |= x): those documents, a few percent of the
+ * union, are the only ones scored here — presence mask from the bits, MaxScore bucket from a table held one entry
+ * per lane, wdf of every present leaf through its rank directory, the reference's tree order (or_score_doc).
+ * Their weights give the top-k threshold b* its level BEFORE the far more numerous single-leaf documents are
+ * looked at: those are left to xgm_or3_kernel<PHASE 1>, which walks the posting lists and, knowing b*, skips
+ * whole leaves and whole blocks (largest wdf of the block in its header) without decoding them.  A single-leaf
+ * document in the final top-k has a weight >= the final threshold >= b* after this kernel, so nothing is lost.
+ * Work item = 2048 words (65 536 docids) of one query, ordered range-major over the batch. */
+#define TILE_WARPS 8
+#define TILE_ITERS 64
+#define TILE_QCAP 64
+
+struct __align__(16) TileScratch {
+    uint32_t qdid[TILE_QCAP];
+    uint32_t qqi[TILE_QCAP];
+    uint32_t qpm[TILE_QCAP];
+};
+
+__global__ void __launch_bounds__(TILE_WARPS * 32, 4) xgm_or_tile_kernel(const __grid_constant__ XgmKernelParams p) {
+    __shared__ TileScratch scratch[TILE_WARPS];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    TileScratch& ws = scratch[warp];
+    if (p.pass != 0 && *reinterpret_cast<volatile uint32_t*>(p.work_counter + 4) == 0) return;
+    const uint32_t nwords = (p.lastdocid >> 5) + 1u;
+    const uint32_t items_per_q = (nwords + 32u * TILE_ITERS - 1u) / (32u * TILE_ITERS);
+    const uint32_t nitems = items_per_q * p.ntileq;
+    uint32_t qn = 0;
+    bool done = false;
+
+    auto flush = [&](uint32_t count) {
+        qn -= count;
+        const bool alive = lane < count;
+        const uint32_t d = alive ? ws.qdid[qn + lane] : 0u;
+        const uint32_t qi = alive ? ws.qqi[qn + lane] : 0u;
+        const uint32_t pm = alive ? ws.qpm[qn + lane] : 0u;
+        double acc = 0.0;
+        if (alive) acc = or_score_doc(p, &p.queries[qi], d, pm, 0xffu, 0u, 0u);
+        emit_match_lanes(p, lane, alive, qi, acc, d, (uint32_t)__popc(pm), false);
+        __syncwarp();
+    };
+
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(p.work_counter + 12 + p.pass, 1u);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= nitems) break;
+        const uint32_t tile = item / p.ntileq, qi = __ldg(p.tileq + (item - tile * p.ntileq));
+        if (p.pass != 0 && p.qstate[qi].rerun == 0) continue;
+        const XgmDevQuery* q = &p.queries[qi];
+        const uint32_t nterms = q->nterms;
+        const uint32_t* bmp[OR3_MAX_LEAVES];
+#pragma unroll
+        for (int j = 0; j < OR3_MAX_LEAVES; ++j) bmp[j] = p.bitmaps + ((uint32_t)j < nterms ? q->terms[j].bm_off : 0ull);
+        /* lane m: pruning bucket of presence mask m (sum of the get_maxpart bounds of its leaves) */
+        uint32_t ubbkt;
+        {
+            double ub = 0.0;
+            for (uint32_t i = 0; i < nterms; ++i)
+                if (lane >> i & 1u) ub += q->terms[i].maxpart;
+            ubbkt = match_bucket(q, ub * (1.0 + 1e-12), 0);
+        }
+        uint32_t total_acc = 0;
+        const uint32_t w0 = tile * (32u * TILE_ITERS);
+        for (uint32_t it = 0; it < TILE_ITERS; ++it) {
+            const uint32_t word = w0 + it * 32u + lane;
+            if (w0 + it * 32u >= nwords) break;
+            uint32_t w[OR3_MAX_LEAVES];
+#pragma unroll
+            for (int j = 0; j < OR3_MAX_LEAVES; ++j) w[j] = ((uint32_t)j < nterms && word < nwords) ? __ldg(bmp[j] + word) : 0u;
+            uint32_t one = 0, two = 0;
+#pragma unroll
+            for (int j = 0; j < OR3_MAX_LEAVES; ++j) { two |= one & w[j]; one |= w[j]; }
+            total_acc += (uint32_t)__popc(one);
+            const uint32_t bstar = *reinterpret_cast<volatile uint32_t*>(&p.qstate[qi].bstar);
+            uint32_t cand = two;
+            while (__any_sync(FULL, cand != 0)) { /* one document per lane and round */
+                const bool has = cand != 0;
+                const uint32_t bit = has ? (uint32_t)__ffs(cand) - 1u : 0u;
+                cand &= cand - 1u;
+                uint32_t pm = 0;
+#pragma unroll
+                for (int j = 0; j < OR3_MAX_LEAVES; ++j) pm |= (w[j] >> bit & 1u) << j;
+                const uint32_t bk = __shfl_sync(FULL, ubbkt, pm & 31u);
+                const bool ok = has && bk >= bstar;
+                const uint32_t B = __ballot_sync(FULL, ok);
+                if (B) {
+                    if (ok) {
+                        const uint32_t slot = qn + __popc(B & ((1u << lane) - 1u));
+                        ws.qdid[slot] = (word << 5) + bit;
+                        ws.qqi[slot] = qi;
+                        ws.qpm[slot] = pm;
+                    }
+                    qn += __popc(B);
+                    if (qn >= 32) { __syncwarp(); flush(32); }
+                }
+            }
+        }
+        const uint32_t t = __reduce_add_sync(FULL, total_acc);
+        if (lane == 0 && t && p.pass == 0) atomicAdd(&p.qstate[qi].total, t);
+    }
+    (void)done;
+    __syncwarp();
+    if (qn) flush(qn);
+}
+
+cudaError_t xgm_launch_or_tile(const XgmKernelParams& p, int grid, cudaStream_t s) {
+    xgm_or_tile_kernel<<<grid, TILE_WARPS * 32, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+int xgm_or_tile_occupancy_blocks_per_sm() {
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, xgm_or_tile_kernel, TILE_WARPS * 32, 0);
     return n;
 }
 
