@@ -2235,11 +2235,6 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 4) xgm_or_tile_kernel(const _
         }
         uint32_t total_acc = 0;
         const uint32_t w0 = tile * (32u * TILE_ITERS);
-        /* The presence masks whose bound reaches b* form an upward-closed family; `minset` holds its minimal
-         * members (bit m = mask m), recomputed when b* moves.  A document is worth scoring iff its mask contains
-         * one of them, which is bit-parallel work on the words: f = OR over minimal masks of the AND of their
-         * leaves' words — no per-document loop for the (many) documents of frequent, low-weight leaves. */
-        uint32_t last_bstar = 0xffffffffu, minset = 0;
         for (uint32_t it = 0; it < TILE_ITERS; ++it) {
             const uint32_t word = w0 + it * 32u + lane;
             if (w0 + it * 32u >= nwords) break;
@@ -2251,28 +2246,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 4) xgm_or_tile_kernel(const _
             for (int j = 0; j < OR3_MAX_LEAVES; ++j) { two |= one & w[j]; one |= w[j]; }
             total_acc += (uint32_t)__popc(one);
             const uint32_t bstar = *reinterpret_cast<volatile uint32_t*>(&p.qstate[qi].bstar);
-            if (bstar != last_bstar) {
-                last_bstar = bstar;
-                const uint32_t live = (lane != 0 && ubbkt >= bstar) ? 1u : 0u;
-                bool minimal = live != 0;
-#pragma unroll
-                for (int j = 0; j < OR3_MAX_LEAVES; ++j) {
-                    const uint32_t sub = lane & ~(1u << j);
-                    const uint32_t sl = __shfl_sync(FULL, live, sub);
-                    if ((lane >> j & 1u) && sl) minimal = false; /* a proper submask already reaches b* */
-                }
-                minset = __ballot_sync(FULL, minimal);
-            }
-            uint32_t f = 0;
-            for (uint32_t ms = minset; ms; ms &= ms - 1u) {
-                const uint32_t mu = (uint32_t)__ffs(ms) - 1u;
-                uint32_t t = 0xffffffffu;
-#pragma unroll
-                for (int j = 0; j < OR3_MAX_LEAVES; ++j)
-                    if (mu >> j & 1u) t &= w[j];
-                f |= t;
-            }
-            uint32_t cand = two & f;
+            uint32_t cand = two;
             while (__any_sync(FULL, cand != 0)) { /* one document per lane and round */
                 const bool has = cand != 0;
                 const uint32_t bit = has ? (uint32_t)__ffs(cand) - 1u : 0u;
@@ -2280,15 +2254,19 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 4) xgm_or_tile_kernel(const _
                 uint32_t pm = 0;
 #pragma unroll
                 for (int j = 0; j < OR3_MAX_LEAVES; ++j) pm |= (w[j] >> bit & 1u) << j;
-                const uint32_t B = __ballot_sync(FULL, has);
-                if (has) {
-                    const uint32_t slot = qn + __popc(B & ((1u << lane) - 1u));
-                    ws.qdid[slot] = (word << 5) + bit;
-                    ws.qqi[slot] = qi;
-                    ws.qpm[slot] = pm;
+                const uint32_t bk = __shfl_sync(FULL, ubbkt, pm & 31u);
+                const bool ok = has && bk >= bstar;
+                const uint32_t B = __ballot_sync(FULL, ok);
+                if (B) {
+                    if (ok) {
+                        const uint32_t slot = qn + __popc(B & ((1u << lane) - 1u));
+                        ws.qdid[slot] = (word << 5) + bit;
+                        ws.qqi[slot] = qi;
+                        ws.qpm[slot] = pm;
+                    }
+                    qn += __popc(B);
+                    if (qn >= 32) { __syncwarp(); flush(32); }
                 }
-                qn += __popc(B);
-                if (qn >= 32) { __syncwarp(); flush(32); }
             }
         }
         const uint32_t t = __reduce_add_sync(FULL, total_acc);
