@@ -438,26 +438,25 @@ def ours(args):
         # phase 1 of Xapiand's two-phase scheme (src/database/handler.cc:1532-1538, weightinternal.cc:54-72) per batch:
         # local termfreq of every distinct query term (one C call), ONE all-reduce of (termfreqs, doccount,
         # total_length), then the sums go into the batch's statistics blocks.  All of it is inside the e2e region.
-        names = [term_name(r) for r in range(TOPRANKS)]
-        name_arr = [n.encode() for n in names]
+        lookup = ix.term_freq_lookup([term_name(r) for r in range(TOPRANKS)])  # every term a query may draw
         term_idx = [np.array([q[0] for q in qs], np.int64) for qs in raw]
-        uniq = [np.unique(t) for t in term_idx]
         for b in batches:
             b.attach_global_stats()
         stat_buf = torch.zeros(TOPRANKS + 2, dtype=torch.int64, device="cuda")
         stat_host = torch.zeros(TOPRANKS + 2, dtype=torch.int64).pin_memory()
+        stat_np = stat_host.numpy()
+        stat_np[TOPRANKS] = int(info.doccount)
+        stat_np[TOPRANKS + 1] = int(info.total_length)
 
         def exchange_stats(bi: int):
-            u = uniq[bi]
-            tf = ix.term_freqs([name_arr[i] for i in u])
-            stat_host.zero_()
-            stat_host[:TOPRANKS][torch.from_numpy(u)] = torch.from_numpy(tf.astype(np.int64))
-            stat_host[TOPRANKS] = int(info.doccount)
-            stat_host[TOPRANKS + 1] = int(info.total_length)
+            stat_np[:TOPRANKS] = lookup()                 # local termfreqs: one C call
             stat_buf.copy_(stat_host, non_blocking=True)
-            dist.all_reduce(stat_buf)
-            g = stat_buf.cpu().numpy()
-            batches[bi].set_global_stats(int(g[TOPRANKS]), int(g[TOPRANKS + 1]), g[:TOPRANKS][term_idx[bi]].astype(np.uint32))
+            dist.all_reduce(stat_buf)                      # the one exchange of phase 1
+            stat_host.copy_(stat_buf)                      # (synchronises)
+            batches[bi].set_global_stats(int(stat_np[TOPRANKS]), int(stat_np[TOPRANKS + 1]),
+                                         stat_np[:TOPRANKS][term_idx[bi]].astype(np.uint32))
+            stat_np[TOPRANKS] = int(info.doccount)
+            stat_np[TOPRANKS + 1] = int(info.total_length)
     else:
         def exchange_stats(bi: int):
             return None
@@ -465,6 +464,9 @@ def ours(args):
     NSEARCH = int(os.environ.get("XGM_BENCH_NSEARCH", 3))  # batches in flight in the end-to-end loop (host planning / GPU / result scatter overlap)
     searchers = [xgm.Searcher(ix, max_batch=BATCH, max_topk=TOPK) for _ in range(NSEARCH)]
     streams = [torch.cuda.ExternalStream(s.stream(), device=torch.device("cuda", local_rank)) for s in searchers]
+    if world > 1:
+        for s in searchers:
+            s.results_on_device(True)  # the per-shard MSets are exchanged and merged on the device
 
     # ---- N > 1: the merge.  Rank r owns queries [r*BATCH/N, (r+1)*BATCH/N): one all-to-all moves every shard's
     # top-k of those queries to r (three regions of the result slab: weights | docids | records), r merges them
@@ -513,13 +515,18 @@ def ours(args):
             if world > 1:
                 srch.launched()
                 merge_step(si, True)
-            srch.wait_raw()
+                srch.wait_device()
+            else:
+                srch.wait_raw()
     exchange_stats(0)
     if world > 1:  # the device-resident loop alternates between two searchers holding the same resident plan
         searchers[1].submit(batches[0])
-        searchers[1].wait_raw()
+        searchers[1].wait_device()
+        searchers[0].results_on_device(False)
     searchers[0].submit(batches[0])
     _, _, _, inf0 = searchers[0].wait_raw()
+    if world > 1:
+        searchers[0].results_on_device(True)
     bad = sum(1 for i in range(BATCH) if inf0[i].status != 0)
     if bad:
         raise SystemExit(f"{bad} queries of the bench batch were not answered on the device")
@@ -590,7 +597,7 @@ def ours(args):
         si = k % NSEARCH
         bi = W + 1 + k
         if len(inflight) == NSEARCH:
-            searchers[inflight.pop(0)].wait_raw()
+            (searchers[inflight.pop(0)].wait_device if world > 1 else searchers[inflight.pop(0)].wait_raw)()
         ts = time.perf_counter()
         exchange_stats(bi)  # N > 1: phase-1 statistics of THIS batch (lookups + all-reduce + fill-in)
         stats_s += time.perf_counter() - ts
@@ -607,7 +614,7 @@ def ours(args):
         merge_step(prev, True)
     pending = inflight[-1]
     for si in inflight:
-        searchers[si].wait_raw()
+        (searchers[si].wait_device if world > 1 else searchers[si].wait_raw)()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     sampler.end()

@@ -296,6 +296,10 @@ xgm_status xgm_search_device_results(xgm_searcher*, void** weights, void** docid
  * handler.cc:1540-1556's per-shard prepared MSets). */
 xgm_status xgm_search_device_slab(xgm_searcher*, void** base, uint64_t* bytes, uint64_t* off_docids,
                                   uint64_t* off_counts, uint32_t* stride);
+/* Multi-GPU use: leave the batch's results in the device slab only — xgm_search_submit* then skips the
+ * device→host copies and xgm_search_wait only synchronises (its output arguments may be NULL).  The caller
+ * exchanges and merges the slabs on the device and copies the merged MSets itself. */
+xgm_status xgm_searcher_set_results_on_device(xgm_searcher*, int on);
 /* CUDA stream of the searcher (cudaStream_t as void*) and timing/roofline counters of the last batch. */
 void* xgm_searcher_stream(xgm_searcher*);
 typedef struct xgm_batch_stats {

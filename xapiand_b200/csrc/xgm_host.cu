@@ -981,6 +981,7 @@ struct xgm_searcher {
     uint32_t* h_tileq = nullptr;  /* pinned: queries of the batch answered by the bitmap-union kernel */
     uint32_t* d_tileq = nullptr;
     uint32_t ntileq = 0;
+    bool device_only = false;     /* results stay on the device (xgm_searcher_set_results_on_device) */
     bool or_tile = true;          /* XGM_OR_TILE=0: keep every fast OR query in the one-launch kernel */
     int and_version = 1; /* 1 = warp-autonomous kernel, 2 = chunked CTA kernel (XGM_AND_KERNEL env) */
     XgmKernelParams params;
@@ -1914,6 +1915,12 @@ static xgm_status submit_impl(xgm_searcher* s, const xgm_query* queries, uint32_
     st = launch_batch(s);
     if (st != XGM_OK) return st;
     size_t ns = (size_t)nq * s->max_topk;
+    if (s->device_only) { /* the caller reads the result slab on the device (multi-GPU exchange + merge) */
+        s->stats.d2h_bytes = 0;
+        s->pending = true;
+        s->stats.host_plan_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_submit0).count();
+        return XGM_OK;
+    }
     CUDA_TRY(cudaMemcpyAsync(s->h_info, s->d_info, (size_t)nq * sizeof(XgmDevResult), cudaMemcpyDeviceToHost, s->stream));
     if (s->range_mode) CUDA_TRY(cudaMemcpyAsync(s->h_rng_total, s->d_rng_total, 4, cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaMemcpyAsync(s->h_out_w, s->d_out_w, ns * 8, cudaMemcpyDeviceToHost, s->stream));
@@ -2053,9 +2060,16 @@ extern "C" xgm_status xgm_search_launched(xgm_searcher* s) {
     return join_async(s);
 }
 
+extern "C" xgm_status xgm_searcher_set_results_on_device(xgm_searcher* s, int on) {
+    if (!s) return fail(XGM_E_INVALID, "null argument");
+    if (s->pending) return fail(XGM_E_INVALID, "a batch is in flight");
+    s->device_only = on != 0;
+    return XGM_OK;
+}
+
 extern "C" xgm_status xgm_search_wait(xgm_searcher* s, uint32_t* docids, double* weights, uint64_t* sort_keys,
                                       uint32_t stride, xgm_mset_info* info) {
-    if (!s || !info) return fail(XGM_E_INVALID, "null argument");
+    if (!s || (!info && !s->device_only)) return fail(XGM_E_INVALID, "null argument");
     if (!s->pending) return fail(XGM_E_INVALID, "no batch submitted");
     {
         xgm_status jst = join_async(s);
@@ -2065,6 +2079,7 @@ extern "C" xgm_status xgm_search_wait(xgm_searcher* s, uint32_t* docids, double*
     cudaError_t e = cudaStreamSynchronize(s->stream);
     s->pending = false;
     if (e != cudaSuccess) return fail(XGM_E_CUDA, "batch failed: %s", cudaGetErrorString(e));
+    if (s->device_only) return XGM_OK; /* nothing was copied: the results are in the device slab */
     cudaEventElapsedTime(&s->stats.match_kernel_ms, s->ev0, s->ev1);
     cudaEventElapsedTime(&s->stats.topk_kernel_ms, s->ev1, s->ev2);
     const auto t_wait0 = std::chrono::steady_clock::now();

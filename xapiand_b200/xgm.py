@@ -35,7 +35,7 @@ EXPORTS = [
     "xgm_merge_topk_device_slab",
     "xgm_builder_add_value_slot_serialised", "xgm_builder_set_revision", "xgm_index_value_freq",
     "xgm_value_key", "xgm_value_key_bytes", "xgm_sort_key_bytes", "xgm_term_stats_many",
-    "xgm_index_open", "xgm_glass_revision", "xgm_glass_export_flat",
+    "xgm_index_open", "xgm_glass_revision", "xgm_glass_export_flat", "xgm_searcher_set_results_on_device",
 ]
 
 
@@ -154,6 +154,7 @@ def lib():
     L.xgm_search.argtypes = [C.c_void_p, C.POINTER(CQuery), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                              C.POINTER(MSetInfo)]
     L.xgm_search_replay.argtypes = [C.c_void_p]
+    L.xgm_searcher_set_results_on_device.argtypes = [C.c_void_p, C.c_int]
     L.xgm_search_device_results.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                             C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]
     L.xgm_search_device_slab.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
@@ -439,12 +440,20 @@ class Index:
 
     def term_freqs(self, names: Sequence[Union[str, bytes]]) -> np.ndarray:
         """Local termfreq of many terms in one C call (xgm_term_stats_many)."""
+        return self.term_freq_lookup(names)()
+
+    def term_freq_lookup(self, names: Sequence[Union[str, bytes]]):
+        """A callable that looks the same terms up again and again (the marshalling is done once)."""
         bs = [t.encode() if isinstance(t, str) else bytes(t) for t in names]
         arr = (C.c_char_p * len(bs))(*bs)
         lens = np.array([len(b) for b in bs], np.uint32)
         out = np.zeros(len(bs), np.uint32)
-        _check(lib().xgm_term_stats_many(self._h, len(bs), arr, _ptr(lens), _ptr(out)))
-        return out
+        L, h, n = lib(), self._h, len(bs)
+
+        def lookup(_keep=(bs, arr, lens)):
+            _check(L.xgm_term_stats_many(h, n, arr, _ptr(lens), _ptr(out)))
+            return out
+        return lookup
 
     def decode_term(self, term_id: int):
         n = C.c_uint32()
@@ -503,6 +512,13 @@ class Searcher:
 
     def launched(self):
         _check(lib().xgm_search_launched(self._h))
+
+    def results_on_device(self, on: bool = True):
+        """Leave results in the device slab (multi-GPU exchange + merge); wait_device() then only synchronises."""
+        _check(lib().xgm_searcher_set_results_on_device(self._h, int(on)))
+
+    def wait_device(self):
+        _check(lib().xgm_search_wait(self._h, None, None, None, self.max_topk, None))
 
     def wait_raw(self):
         """Results left in the searcher's flat host buffers (stride = max_topk)."""
