@@ -442,17 +442,18 @@ def ours(args):
         term_idx = [np.array([q[0] for q in qs], np.int64) for qs in raw]
         for b in batches:
             b.attach_global_stats()
-        stat_buf = torch.zeros(TOPRANKS + 2, dtype=torch.int64, device="cuda")
-        stat_host = torch.zeros(TOPRANKS + 2, dtype=torch.int64).pin_memory()
+        # the sums are host data on both sides (term dictionary in, planner out): a CPU (gloo) group carries this
+        # one small all-reduce, so that it is not queued behind the result exchanges of earlier batches on the NCCL
+        # communicator (which would tie the host to the GPU's progress)
+        stats_pg = dist.new_group(backend="gloo")
+        stat_host = torch.zeros(TOPRANKS + 2, dtype=torch.int64)
         stat_np = stat_host.numpy()
         stat_np[TOPRANKS] = int(info.doccount)
         stat_np[TOPRANKS + 1] = int(info.total_length)
 
         def exchange_stats(bi: int):
             stat_np[:TOPRANKS] = lookup()                 # local termfreqs: one C call
-            stat_buf.copy_(stat_host, non_blocking=True)
-            dist.all_reduce(stat_buf)                      # the one exchange of phase 1
-            stat_host.copy_(stat_buf)                      # (synchronises)
+            dist.all_reduce(stat_host, group=stats_pg)     # the one exchange of phase 1
             batches[bi].set_global_stats(int(stat_np[TOPRANKS]), int(stat_np[TOPRANKS + 1]),
                                          stat_np[:TOPRANKS][term_idx[bi]].astype(np.uint32))
             stat_np[TOPRANKS] = int(info.doccount)
@@ -626,8 +627,7 @@ def ours(args):
     bs = searchers[pending].last_stats()
     h2d, d2h = int(bs.h2d_bytes), int(bs.d2h_bytes)
     if world > 1:
-        h2d += (TOPRANKS + 2) * 8
-        d2h += QL * TOPK * 12 + QL * 4 + (TOPRANKS + 2) * 8
+        d2h += QL * TOPK * 12 + QL * 4
     clocks = sampler.stop()
     e2e_value = BATCH * args.steps / e2e_s
 
