@@ -591,31 +591,32 @@ def ours(args):
     barrier()
     sampler.begin()
     t0 = time.perf_counter()
-    inflight = []
-    prev = None
     stats_s = 0.0
+    wait = (lambda s: s.wait_device()) if world > 1 else (lambda s: s.wait_raw())
+    # Software pipeline over NSEARCH searchers.  Batch k is submitted in iteration k (its searcher's worker thread
+    # plans + enqueues it); N > 1: its exchange + merge is enqueued two iterations later, when that worker has long
+    # finished, so xgm_search_launched never blocks this thread; its results are collected NSEARCH iterations later.
+    LAG = 2 if NSEARCH >= 3 else 1
+    def finish(j):  # exchange + merge of batch j (N > 1)
+        searchers[j % NSEARCH].launched()
+        merge_step(j % NSEARCH, True)
     for k in range(args.steps):
         si = k % NSEARCH
         bi = W + 1 + k
-        if len(inflight) == NSEARCH:
-            (searchers[inflight.pop(0)].wait_device if world > 1 else searchers[inflight.pop(0)].wait_raw)()
+        if world > 1 and k >= LAG:
+            finish(k - LAG)
+        if k >= NSEARCH:
+            wait(searchers[si])  # batch k - NSEARCH: scatter (N = 1) / synchronise (N > 1)
         ts = time.perf_counter()
         exchange_stats(bi)  # N > 1: phase-1 statistics of THIS batch (lookups + all-reduce + fill-in)
         stats_s += time.perf_counter() - ts
-        # the searcher's worker thread plans + enqueues batch k while this thread scatters an earlier one
         searchers[si].submit(batches[bi], background=True)
-        if world > 1 and prev is not None:
-            # exchange + merge of the previous batch: its kernels were enqueued while we were busy above
-            searchers[prev].launched()
-            merge_step(prev, True)
-        prev = si
-        inflight.append(si)
     if world > 1:
-        searchers[prev].launched()
-        merge_step(prev, True)
-    pending = inflight[-1]
-    for si in inflight:
-        (searchers[si].wait_device if world > 1 else searchers[si].wait_raw)()
+        for j in range(max(0, args.steps - LAG), args.steps):
+            finish(j)
+    for j in range(max(0, args.steps - NSEARCH), args.steps):
+        wait(searchers[j % NSEARCH])
+    pending = (args.steps - 1) % NSEARCH
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     sampler.end()
