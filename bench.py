@@ -423,6 +423,9 @@ def ours(args):
         torch.cuda.synchronize()
 
     t_setup = time.time()
+    host_cpus = ref_cores()[0]
+    if world > 1:  # N ranks share the box's CPUs: size the library's planner pool accordingly
+        os.environ.setdefault("XGM_HOST_THREADS", str(max(1, min(8, host_cpus // world - 1))))
     threads = max(4, (os.cpu_count() or 8) // max(1, world))
     ix = xgm.Index.synthetic(cfg["docs"], VOCAB, seed=SEED, nshards=world, shard=rank, values=cfg["values"],
                              device=local_rank, host_threads=min(64, threads))
@@ -446,18 +449,29 @@ def ours(args):
         # one small all-reduce, so that it is not queued behind the result exchanges of earlier batches on the NCCL
         # communicator (which would tie the host to the GPU's progress)
         stats_pg = dist.new_group(backend="gloo")
-        stat_host = torch.zeros(TOPRANKS + 2, dtype=torch.int64)
-        stat_np = stat_host.numpy()
-        stat_np[TOPRANKS] = int(info.doccount)
-        stat_np[TOPRANKS + 1] = int(info.total_length)
+
+        pending_stats = {}
+
+        def start_stats(bi: int):
+            """Phase 1 of batch bi, first half: local termfreqs (one C call) and the all-reduce, left in flight."""
+            if bi in pending_stats or bi >= nbatches:
+                return
+            buf = torch.zeros(TOPRANKS + 2, dtype=torch.int64)
+            a = buf.numpy()
+            a[:TOPRANKS] = lookup()
+            a[TOPRANKS] = int(info.doccount)
+            a[TOPRANKS + 1] = int(info.total_length)
+            pending_stats[bi] = (buf, dist.all_reduce(buf, group=stats_pg, async_op=True))
 
         def exchange_stats(bi: int):
-            stat_np[:TOPRANKS] = lookup()                 # local termfreqs: one C call
-            dist.all_reduce(stat_host, group=stats_pg)     # the one exchange of phase 1
-            batches[bi].set_global_stats(int(stat_np[TOPRANKS]), int(stat_np[TOPRANKS + 1]),
-                                         stat_np[:TOPRANKS][term_idx[bi]].astype(np.uint32))
-            stat_np[TOPRANKS] = int(info.doccount)
-            stat_np[TOPRANKS + 1] = int(info.total_length)
+            """Second half: wait for the sums and write them into the batch's statistics blocks.  The exchange of
+            batch bi + 1 is started before returning, so that it overlaps the planning and matching of batch bi."""
+            start_stats(bi)
+            buf, work = pending_stats.pop(bi)
+            work.wait()
+            a = buf.numpy()
+            batches[bi].set_global_stats(int(a[TOPRANKS]), int(a[TOPRANKS + 1]), a[:TOPRANKS][term_idx[bi]].astype(np.uint32))
+            start_stats(bi + 1)
     else:
         def exchange_stats(bi: int):
             return None
@@ -690,7 +704,7 @@ def ours(args):
                          "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms_per_launch": kern_ms},
-            "step_breakdown_ms": step_parts, "step_bound_by": bound,
+            "step_breakdown_ms": step_parts, "step_bound_by": bound, "host_cpus": host_cpus,
             "bounds_approx_fraction": approx0 / BATCH,
             "clocks": clocks}
 
