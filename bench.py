@@ -49,7 +49,7 @@ CONFIGS = {
                kernel="xgm_and_bm3_kernel (decode driver + bitmap intersect + BM25)", ref_queries=1024, parity=1024),
     "C3": dict(metric="queries/sec, 10M-doc 5-term OR BM25 top-1000", op="OR", nterms=5, topk=1000, batch=512,
                workload="C3: 10M docs, V=1M Zipf(1) terms, 5-term OP_OR, BM25, get_mset(0,1000)",
-               kernel="xgm_or_kernel (owner-leaf union + tree-order BM25)", ref_queries=256, parity=200),
+               kernel="xgm_or_tile_kernel + xgm_or3_kernel<phase 1> (bitmap union count, MaxScore candidates, tree-order BM25)", ref_queries=256, parity=200),
     "C5": dict(metric="queries/sec, 10M-doc 2-term AND + multivalue range filter + sort by value, top-100", op="AND",
                nterms=2, topk=100, batch=4096, values=True,
                workload=("C5: 10M docs, OP_FILTER(2-term OP_AND, Xapiand MultipleValueRange(slot 0, [lo, lo+1e4])), "
