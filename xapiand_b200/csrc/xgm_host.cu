@@ -28,6 +28,9 @@
 /* ------------------------------------------------------------------ errors */
 
 static thread_local char g_err[512] = "";
+static const bool g_trace = getenv("XGM_TRACE") != nullptr && atoi(getenv("XGM_TRACE")) != 0;
+static cudaEvent_t g_tr_base = nullptr; /* XGM_TRACE: common origin of every searcher's timeline */
+static std::chrono::steady_clock::time_point g_tr_t0;
 
 static xgm_status fail(xgm_status st, const char* fmt, ...) {
     va_list ap;
@@ -919,6 +922,9 @@ struct xgm_searcher {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     cudaEvent_t ev_in = nullptr, ev_done = nullptr; /* hand-over between the copy stream and the shared compute stream */
+    /* XGM_TRACE=1: one stderr line per batch with its host and GPU timeline (see trace_line) */
+    cudaEvent_t tr_h2d = nullptr, tr_out = nullptr;
+    std::chrono::steady_clock::time_point tr_submit, tr_planned, tr_launched, tr_async;
     bool shared_compute = true;
     /* pinned host staging */
     XgmDevQuery* h_queries = nullptr;
@@ -1036,6 +1042,8 @@ extern "C" void xgm_searcher_free(xgm_searcher* s) {
     cudaFree(s->d_rng); cudaFree(s->d_rng_total);
     if (s->h_rng_total) cudaFreeHost(s->h_rng_total);
     if (s->ev_in) cudaEventDestroy(s->ev_in);
+    if (s->tr_h2d) cudaEventDestroy(s->tr_h2d);
+    if (s->tr_out) cudaEventDestroy(s->tr_out);
     if (s->ev_done) cudaEventDestroy(s->ev_done);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -1100,6 +1108,15 @@ extern "C" xgm_status xgm_searcher_new(const xgm_index* ix, uint32_t max_batch, 
     CUDA_TRY(cudaEventCreate(&s->ev0)); CUDA_TRY(cudaEventCreate(&s->ev1)); CUDA_TRY(cudaEventCreate(&s->ev2));
     CUDA_TRY(cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming));
+    if (g_trace) {
+        CUDA_TRY(cudaEventCreate(&s->tr_h2d)); CUDA_TRY(cudaEventCreate(&s->tr_out));
+        if (!g_tr_base) {
+            CUDA_TRY(cudaEventCreate(&g_tr_base));
+            CUDA_TRY(cudaEventRecord(g_tr_base, s->stream));
+            CUDA_TRY(cudaEventSynchronize(g_tr_base));
+            g_tr_t0 = std::chrono::steady_clock::now();
+        }
+    }
     if (const char* e = getenv("XGM_SHARED_COMPUTE")) s->shared_compute = atoi(e) != 0;
     if (const char* e = getenv("XGM_RANGE_BITS")) s->range_bits = (uint32_t)std::min(31, std::max(0, atoi(e)));
     CUDA_TRY(cudaMalloc(&s->d_rng_total, 64));
@@ -1912,6 +1929,7 @@ static xgm_status submit_impl(xgm_searcher* s, const xgm_query* queries, uint32_
     for (int w = 0; w < 3; ++w)
         if (s->nlevels[w])
             CUDA_TRY(cudaMemcpyAsync(s->d_levels[w], s->h_levels[w], ((size_t)s->nlevels[w] + 1) * 4, cudaMemcpyHostToDevice, s->stream));
+    if (g_trace) { s->tr_submit = t_submit0; s->tr_planned = t_interleaved; CUDA_TRY(cudaEventRecord(s->tr_h2d, s->stream)); }
     st = launch_batch(s);
     if (st != XGM_OK) return st;
     size_t ns = (size_t)nq * s->max_topk;
@@ -1932,6 +1950,7 @@ static xgm_status submit_impl(xgm_searcher* s, const xgm_query* queries, uint32_
     }
     s->pending = true;
     s->stats.host_plan_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_submit0).count();
+    if (g_trace) { CUDA_TRY(cudaEventRecord(s->tr_out, s->stream)); s->tr_launched = std::chrono::steady_clock::now(); }
     if (getenv("XGM_DEBUG_TIMING"))
         fprintf(stderr, "xgm submit: plan %.3f ms, interleave %.3f ms, enqueue %.3f ms (T=%d, items %zu)\n",
                 std::chrono::duration<float, std::milli>(t_planned - t_submit0).count(),
@@ -2049,6 +2068,7 @@ extern "C" xgm_status xgm_search_submit_async(xgm_searcher* s, const xgm_query* 
         s->job_status = XGM_OK;
         s->job = xgm_searcher::JOB_QUEUED;
         s->pending = true;
+        if (g_trace) s->tr_async = std::chrono::steady_clock::now();
     }
     s->cv.notify_all();
     return XGM_OK;
@@ -2067,14 +2087,33 @@ extern "C" xgm_status xgm_searcher_set_results_on_device(xgm_searcher* s, int on
     return XGM_OK;
 }
 
+/* XGM_TRACE=1: host times (ms since the searcher was created: async hand-over, worker start, planned, enqueued,
+ * wait entered, worker joined, stream drained, scattered) and GPU times on the same origin (plan on the device,
+ * match kernels begin / end, top-k end, results on the host).  A measurement aid; nothing reads it back. */
+static void trace_line(xgm_searcher* s, std::chrono::steady_clock::time_point wait_in,
+                       std::chrono::steady_clock::time_point joined, std::chrono::steady_clock::time_point synced) {
+    auto ms = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(t - g_tr_t0).count(); };
+    float g[5] = {0, 0, 0, 0, 0};
+    cudaEventElapsedTime(&g[0], g_tr_base, s->tr_h2d);
+    cudaEventElapsedTime(&g[1], g_tr_base, s->ev0);
+    cudaEventElapsedTime(&g[2], g_tr_base, s->ev1);
+    cudaEventElapsedTime(&g[3], g_tr_base, s->ev2);
+    cudaEventElapsedTime(&g[4], g_tr_base, s->tr_out);
+    fprintf(stderr, "XGMTRACE s=%p nq=%u host async=%.3f start=%.3f planned=%.3f enq=%.3f wait=%.3f joined=%.3f synced=%.3f done=%.3f "
+            "gpu h2d=%.3f k0=%.3f k1=%.3f k2=%.3f out=%.3f second_pass=%u\n", (void*)s, s->nq, ms(s->tr_async), ms(s->tr_submit), ms(s->tr_planned),
+            ms(s->tr_launched), ms(wait_in), ms(joined), ms(synced), ms(std::chrono::steady_clock::now()), g[0], g[1], g[2], g[3], g[4], s->stats.second_pass_queries);
+}
+
 extern "C" xgm_status xgm_search_wait(xgm_searcher* s, uint32_t* docids, double* weights, uint64_t* sort_keys,
                                       uint32_t stride, xgm_mset_info* info) {
     if (!s || (!info && !s->device_only)) return fail(XGM_E_INVALID, "null argument");
     if (!s->pending) return fail(XGM_E_INVALID, "no batch submitted");
+    const auto tr_wait_in = std::chrono::steady_clock::now();
     {
         xgm_status jst = join_async(s);
         if (jst != XGM_OK) return jst;
     }
+    const auto tr_joined = std::chrono::steady_clock::now();
     CUDA_TRY(cudaSetDevice(s->ix->device));
     cudaError_t e = cudaStreamSynchronize(s->stream);
     s->pending = false;
@@ -2102,6 +2141,7 @@ extern "C" xgm_status xgm_search_wait(xgm_searcher* s, uint32_t* docids, double*
         }
     }
     s->stats.host_wait_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_wait0).count();
+    if (g_trace) trace_line(s, tr_wait_in, tr_joined, t_wait0);
     return XGM_OK;
 }
 

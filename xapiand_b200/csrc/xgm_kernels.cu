@@ -1065,14 +1065,22 @@ __device__ __noinline__ void raise_bstar_warp(const XgmKernelParams& p, uint32_t
 __device__ __forceinline__ void emit_match_lanes(const XgmKernelParams& p, uint32_t lane, bool alive, uint32_t qi, double w,
                                                  uint32_t d, uint32_t aux, bool count = true) {
     bool crossed = false;
+    /* A query with 10^5..10^6 matches would otherwise send every one of them to the same two words (total, maxw):
+     * same-address atomics serialise in L2 and one such query doubled the launch time of a 4096-query batch.  The
+     * lanes of one query are counted by their lowest lane, and maxw — which only rises — is read first. */
+    if (p.pass == 0 && count) {
+        const uint32_t grp = __match_any_sync(FULL, alive ? qi : 0xffffffffu);
+        if (alive && lane == (uint32_t)__ffs(grp) - 1u) atomicAdd(&p.qstate[qi].total, (uint32_t)__popc(grp));
+    }
     if (alive) {
         const XgmDevQuery* q = &p.queries[qi];
         XgmQState* st = &p.qstate[qi];
         if (p.pass == 0) {
-            if (count) atomicAdd(&st->total, 1u); /* the OR kernel counts the documents it owns, scored or not */
             const unsigned long long wb = (unsigned long long)__double_as_longlong(w);
-            const unsigned long long oldmax = atomicMax(&st->maxw, wb);
-            if (q->log_raises && wb >= oldmax) log_raise(p, qi, wb, d, aux);
+            if (wb >= *reinterpret_cast<volatile unsigned long long*>(&st->maxw)) {
+                const unsigned long long oldmax = atomicMax(&st->maxw, wb);
+                if (q->log_raises && wb >= oldmax) log_raise(p, qi, wb, d, aux);
+            }
         }
         const uint64_t key = q->sort_by != 0 ? doc_sort_key(p, q, d) : 0ull;
         const uint32_t bkt = match_bucket(q, w, key);
