@@ -2207,7 +2207,6 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 4) xgm_or_tile_kernel(const _
     const uint32_t items_per_q = (nwords + 32u * TILE_ITERS - 1u) / (32u * TILE_ITERS);
     const uint32_t nitems = items_per_q * p.ntileq;
     uint32_t qn = 0;
-    bool done = false;
 
     auto flush = [&](uint32_t count) {
         qn -= count;
@@ -2230,9 +2229,14 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 4) xgm_or_tile_kernel(const _
         if (p.pass != 0 && p.qstate[qi].rerun == 0) continue;
         const XgmDevQuery* q = &p.queries[qi];
         const uint32_t nterms = q->nterms;
+        /* the loads carry no per-leaf predicate: a missing leaf re-reads leaf 0's word (an L1 hit) and is masked */
         const uint32_t* bmp[OR3_MAX_LEAVES];
+        uint32_t lm[OR3_MAX_LEAVES];
 #pragma unroll
-        for (int j = 0; j < OR3_MAX_LEAVES; ++j) bmp[j] = p.bitmaps + ((uint32_t)j < nterms ? q->terms[j].bm_off : 0ull);
+        for (int j = 0; j < OR3_MAX_LEAVES; ++j) {
+            bmp[j] = p.bitmaps + q->terms[(uint32_t)j < nterms ? j : 0].bm_off;
+            lm[j] = (uint32_t)j < nterms ? 0xffffffffu : 0u;
+        }
         /* lane m: pruning bucket of presence mask m (sum of the get_maxpart bounds of its leaves) */
         uint32_t ubbkt;
         {
@@ -2243,44 +2247,59 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 4) xgm_or_tile_kernel(const _
         }
         uint32_t total_acc = 0;
         const uint32_t w0 = tile * (32u * TILE_ITERS);
-        for (uint32_t it = 0; it < TILE_ITERS; ++it) {
-            const uint32_t word = w0 + it * 32u + lane;
-            if (w0 + it * 32u >= nwords) break;
-            uint32_t w[OR3_MAX_LEAVES];
+        const uint32_t iters = min((uint32_t)TILE_ITERS, (nwords - w0 + 31u) >> 5);
+        /* the words of iteration it + 1 are requested before the candidates of iteration it are looked at (the
+         * loads of one iteration used to be the only ones in flight); indices are clamped, not predicated */
+        uint32_t w[OR3_MAX_LEAVES], wn[OR3_MAX_LEAVES];
+        {
+            const uint32_t word = w0 + lane;
+            const uint32_t cw = min(word, nwords - 1u), vm = word < nwords ? 0xffffffffu : 0u;
 #pragma unroll
-            for (int j = 0; j < OR3_MAX_LEAVES; ++j) w[j] = ((uint32_t)j < nterms && word < nwords) ? __ldg(bmp[j] + word) : 0u;
+            for (int j = 0; j < OR3_MAX_LEAVES; ++j) w[j] = __ldg(bmp[j] + cw) & lm[j] & vm;
+        }
+        for (uint32_t it = 0; it < iters; ++it) {
+            const uint32_t word = w0 + it * 32u + lane;
+            {
+                const uint32_t nx = word + 32u;
+                const uint32_t cw = min(nx, nwords - 1u), vm = (it + 1u < iters && nx < nwords) ? 0xffffffffu : 0u;
+#pragma unroll
+                for (int j = 0; j < OR3_MAX_LEAVES; ++j) wn[j] = __ldg(bmp[j] + cw) & lm[j] & vm;
+            }
             uint32_t one = 0, two = 0;
 #pragma unroll
             for (int j = 0; j < OR3_MAX_LEAVES; ++j) { two |= one & w[j]; one |= w[j]; }
             total_acc += (uint32_t)__popc(one);
-            const uint32_t bstar = *reinterpret_cast<volatile uint32_t*>(&p.qstate[qi].bstar);
             uint32_t cand = two;
-            while (__any_sync(FULL, cand != 0)) { /* one document per lane and round */
-                const bool has = cand != 0;
-                const uint32_t bit = has ? (uint32_t)__ffs(cand) - 1u : 0u;
-                cand &= cand - 1u;
-                uint32_t pm = 0;
+            if (__any_sync(FULL, cand != 0)) {
+                const uint32_t bstar = *reinterpret_cast<volatile uint32_t*>(&p.qstate[qi].bstar);
+                do { /* one document per lane and round */
+                    const bool has = cand != 0;
+                    const uint32_t bit = has ? (uint32_t)__ffs(cand) - 1u : 0u;
+                    cand &= cand - 1u;
+                    uint32_t pm = 0;
 #pragma unroll
-                for (int j = 0; j < OR3_MAX_LEAVES; ++j) pm |= (w[j] >> bit & 1u) << j;
-                const uint32_t bk = __shfl_sync(FULL, ubbkt, pm & 31u);
-                const bool ok = has && bk >= bstar;
-                const uint32_t B = __ballot_sync(FULL, ok);
-                if (B) {
-                    if (ok) {
-                        const uint32_t slot = qn + __popc(B & ((1u << lane) - 1u));
-                        ws.qdid[slot] = (word << 5) + bit;
-                        ws.qqi[slot] = qi;
-                        ws.qpm[slot] = pm;
+                    for (int j = 0; j < OR3_MAX_LEAVES; ++j) pm |= (w[j] >> bit & 1u) << j;
+                    const uint32_t bk = __shfl_sync(FULL, ubbkt, pm & 31u);
+                    const bool ok = has && bk >= bstar;
+                    const uint32_t B = __ballot_sync(FULL, ok);
+                    if (B) {
+                        if (ok) {
+                            const uint32_t slot = qn + __popc(B & ((1u << lane) - 1u));
+                            ws.qdid[slot] = (word << 5) + bit;
+                            ws.qqi[slot] = qi;
+                            ws.qpm[slot] = pm;
+                        }
+                        qn += __popc(B);
+                        if (qn >= 32) { __syncwarp(); flush(32); }
                     }
-                    qn += __popc(B);
-                    if (qn >= 32) { __syncwarp(); flush(32); }
-                }
+                } while (__any_sync(FULL, cand != 0));
             }
+#pragma unroll
+            for (int j = 0; j < OR3_MAX_LEAVES; ++j) w[j] = wn[j];
         }
         const uint32_t t = __reduce_add_sync(FULL, total_acc);
         if (lane == 0 && t && p.pass == 0) atomicAdd(&p.qstate[qi].total, t);
     }
-    (void)done;
     __syncwarp();
     if (qn) flush(qn);
 }
