@@ -988,6 +988,7 @@ struct xgm_searcher {
     uint32_t* d_tileq = nullptr;
     uint32_t ntileq = 0;
     bool device_only = false;     /* results stay on the device (xgm_searcher_set_results_on_device) */
+    uint32_t bpi_override = 0;    /* XGM_BPI: driver blocks per work item for batches >= 256 (default 16) */
     bool or_tile = true;          /* XGM_OR_TILE=0: keep every fast OR query in the one-launch kernel */
     int and_version = 1; /* 1 = warp-autonomous kernel, 2 = chunked CTA kernel (XGM_AND_KERNEL env) */
     XgmKernelParams params;
@@ -1137,6 +1138,7 @@ extern "C" xgm_status xgm_searcher_new(const xgm_index* ix, uint32_t max_batch, 
     CUDA_TRY(cudaMallocHost(&s->h_tileq, nq * 4));
     CUDA_TRY(cudaMalloc(&s->d_tileq, nq * 4));
     if (const char* e = getenv("XGM_OR_TILE")) s->or_tile = atoi(e) != 0;
+    if (const char* e = getenv("XGM_BPI")) s->bpi_override = (uint32_t)std::min(32, std::max(0, atoi(e)));
     CUDA_TRY(cudaMalloc(&s->d_raise, nq * XGM_RAISE_LOG * sizeof(XgmRaise)));
     s->ctrl_bytes = 64 + nq * sizeof(XgmQState) + nq * XGM_NBINS * 4;
     CUDA_TRY(cudaMalloc(&s->d_ctrl, s->ctrl_bytes));
@@ -1750,8 +1752,9 @@ static xgm_status submit_impl(xgm_searcher* s, const xgm_query* queries, uint32_
     items.reserve(4096);
     /* first pass with a provisional granularity needs the driver block counts; plan twice is wasteful,
      * so use a fixed small granularity scaled by batch size */
-    uint32_t bpi = nq >= 256 ? 16 : (nq >= 16 ? 4 : 1);
+    uint32_t bpi = nq >= 256 ? 12 : (nq >= 16 ? 4 : 1); /* 12: scripts/sweep_bm.py, 8..32 x range widths 2^17..2^20 */
     if (s->and_version == 2) bpi = nq >= 64 ? 16 : (nq >= 8 ? 8 : 4);
+    if (s->bpi_override && nq >= 256) bpi = s->bpi_override; /* XGM_BPI: measurement aid */
     s->any_sort = false;
     uint64_t alg = 0, postings = 0;
     /* Planning (term lookup, Weight::init_, evaluation order, work items) is independent per query:

@@ -2610,7 +2610,42 @@ __global__ void __launch_bounds__(TOPK_THREADS) xgm_topk_kernel(XgmKernelParams 
          * ProtoMSet's count is only needed when the count is reported (unpruned set) and can differ from n
          * (more matches than the free_count that are counted unconditionally). */
         const bool need_counts = complete && !st.skipped && n > free_count;
-        if (need_counts) {
+        if (need_counts && n <= TOPK_THREADS) {
+            /* Few survivors (the common case of a 3-term AND: 100 < n <= 256): one element per thread and one
+             * pass over the others gives the rank, the docid-order position and both "earlier" counters — no
+             * sort, one barrier.  The merge sort below needs ~45 barrier-separated stages for the same n. */
+            const bool act = tid < n;
+            const uint64_t* bw = reinterpret_cast<const uint64_t*>(sw);
+            const uint64_t bi = act ? bw[tid] : 0ull;
+            const uint32_t di = act ? sd[tid] : 0u;
+            uint32_t rank = 0, posd = 0, gt = 0, ge = 0;
+            if (act)
+                for (uint32_t j = 0; j < n; ++j) {
+                    const uint64_t bj = bw[j];
+                    const uint32_t before = (uint32_t)(sd[j] < di), g = (uint32_t)(bj > bi), e = (uint32_t)(bj == bi);
+                    posd += before;
+                    gt += before & g;
+                    ge += before & (g | e);
+                    rank += g | (e & before);
+                }
+            const uint32_t cal = q->check_at_least;
+            if (tid == 0) s_prefix[0] = cal <= topk + 1 ? topk : 0xffffffffu;
+            __syncthreads();
+            if (cal > topk + 1) {
+                const uint32_t from = cal - 1 > topk ? cal - 1 : topk;
+                if (act && posd >= from && ge < topk) atomicMin(&s_prefix[0], posd);
+                __syncthreads();
+            }
+            const uint32_t r_raise = s_prefix[0];
+            if (act) {
+                if (rank < topk) {
+                    p.out_w[ooff + rank] = sw[tid];
+                    p.out_d[ooff + rank] = di;
+                    p.out_k[ooff + rank] = sk[tid] & 0xffull;
+                }
+                if (posd <= r_raise || gt < topk) ++known;
+            }
+        } else if (need_counts) {
             /* n <= XGM_EXACT_COUNT_MAX.  Sort the survivors by docid (bitonic, in shared memory): "earlier in
              * docid order" becomes "smaller index", so `before` is the index itself and each pair costs one
              * or two f64 compares instead of the three-counter test on unsorted data. */
