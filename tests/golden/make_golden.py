@@ -152,6 +152,22 @@ def ops_queries(rng, n, topranks, ndocs):
     return qs
 
 
+def orops_queries(rng, n, topranks, ndocs):
+    """The same groups around an OR base — a free-text OR restricted by boolean terms, the commonest filtered
+    search: OP_FILTER(OP_OR(...), terms), OP_AND_NOT, OP_AND_MAYBE (api/queryinternal.cc:2208-2283)."""
+    qs = []
+    for _ in range(n):
+        nb = rng.choice([2, 2, 3, 4, 5])
+        pool = rng.sample(range(topranks), nb + 9)
+        nf, nx, nm = rng.choice([0, 1, 1, 2]), rng.choice([0, 0, 1, 2, 3]), rng.choice([0, 0, 0, 1, 2])
+        if nf + nx + nm == 0:
+            nf = 1
+        qs.append(dict(op="OR", terms=pool[:nb], first=rng.choice([0, 0, 3]), maxitems=rng.choice([5, 10, 50, 200]),
+                       check_at_least=rng.choice([0, 0, ndocs]), filter_terms=pool[nb:nb + nf],
+                       not_terms=pool[nb + 3:nb + 3 + nx], maybe_terms=pool[nb + 6:nb + 6 + nm]))
+    return qs
+
+
 def scale_queries(rng, n, topranks, ndocs):
     """OP_SCALE_WEIGHT factors on the leaves of AND / OR queries (Xapiand's _boost); factor 0 = unweighted leaf."""
     qs = []
@@ -223,6 +239,9 @@ def main():
     if sys.argv[1:] == ["mv"]:
         run_mv_set("multivalue_5k", 5000, 2000, mv_queries(random.Random(20260930), 240, 60, 5000))
         return
+    if sys.argv[1:] == ["orops"]:
+        run_set("orops_6k", 6000, 900, orops_queries(random.Random(20260931), 240, 120, 6000), seed=11)
+        return
     if sys.argv[1:] == ["ops"]:  # only the fixtures added after round 1's first batch
         run_set("ops_6k", 6000, 900, ops_queries(random.Random(20260924), 240, 200, 6000), seed=11)
         run_set("scale_6k", 6000, 900, scale_queries(random.Random(20260925), 200, 200, 6000), seed=11)
@@ -263,6 +282,7 @@ def main():
     run_set("sortmodes_6k", 6000, 900, sortmode_queries(random.Random(20260928), 200, 100, 6000), seed=11, values=True)
     run_set("bm25_6k", 6000, 900, bm25_queries(random.Random(20260929), 200, 150, 6000), seed=11)
     run_mv_set("multivalue_5k", 5000, 2000, mv_queries(random.Random(20260930), 240, 60, 5000))
+    run_set("orops_6k", 6000, 900, orops_queries(random.Random(20260931), 240, 120, 6000), seed=11)
 
 
 if __name__ == "__main__":

@@ -61,6 +61,18 @@ def test_oracle_matches_reference_filter_andnot_andmaybe():
     assert len(shapes) >= 7  # every combination of the three groups is present
 
 
+def test_oracle_matches_reference_groups_around_or_base():
+    """The same three groups around an OR base (a free-text OR restricted by boolean terms): the MultiAndPostList
+    of [OrPostList tree, filter], AndNotPostList and AndMaybePostList above it — orops_6k fixture."""
+    fx = load("orops_6k")
+    ix = O.Index.synthetic(fx["ndocs"], fx["vocab"], fx["seed"])
+    shapes = set()
+    for i, q in enumerate(fx["queries"]):
+        check(ix.match(o_query(q)), q, f"orops[{i}] {q}")
+        shapes.add((bool(q["filter_terms"]), bool(q["not_terms"]), bool(q["maybe_terms"])))
+    assert len(shapes) >= 7
+
+
 def test_oracle_matches_reference_scale_weight():
     """OP_SCALE_WEIGHT factors on the leaves (QueryScaleWeight::postlist api/queryinternal.cc:1075-1080 →
     Weight::init_ factor), incl. factor 0 = unweighted leaf that is not a counted subquery."""

@@ -963,7 +963,8 @@ struct xgm_searcher {
     uint32_t range_bits = 18, nranges = 1;
     struct OrGroup { uint32_t seg_off, nseg, level_off, nlevels, out_off, total; };
     std::vector<OrGroup> or_groups; /* OR list: one level-ordered expansion per leaf position */
-    unsigned char* d_ctrl = nullptr; /* [16 B work counters][nq x XgmQState][nq x XGM_NBINS x u32] */
+    uint32_t* d_topk_list = nullptr; /* [max_batch] queries left to the CTA-per-query top-k kernel */
+    unsigned char* d_ctrl = nullptr; /* [XGM_CTRL_HDR B work counters][nq x XgmQState][nq x XGM_NBINS x u32] */
     double* d_match_w = nullptr;
     uint32_t* d_match_d = nullptr;
     uint64_t* d_match_k = nullptr;
@@ -1035,7 +1036,7 @@ extern "C" void xgm_searcher_free(xgm_searcher* s) {
     cudaFreeHost(s->h_queries); cudaFreeHost(s->h_items); cudaFreeHost(s->h_items_or); cudaFreeHost(s->h_items_bm); cudaFreeHost(s->h_out_w); cudaFreeHost(s->h_out_d);
     cudaFreeHost(s->h_out_k); cudaFreeHost(s->h_info); cudaFreeHost(s->h_raise); cudaFree(s->d_raise); cudaFreeHost(s->h_qstate); cudaFreeHost(s->h_tileq); cudaFree(s->d_tileq);
     cudaFree(s->d_queries); cudaFree(s->d_items); cudaFree(s->d_items_or); cudaFree(s->d_items_bm); cudaFree(s->d_exp[0]); cudaFree(s->d_exp[1]); cudaFree(s->d_exp[2]);
-    for (int w = 0; w < 3; ++w) { if (s->h_levels[w]) cudaFreeHost(s->h_levels[w]); cudaFree(s->d_levels[w]); } cudaFree(s->d_ctrl); cudaFree(s->d_match_w); cudaFree(s->d_match_d);
+    for (int w = 0; w < 3; ++w) { if (s->h_levels[w]) cudaFreeHost(s->h_levels[w]); cudaFree(s->d_levels[w]); } cudaFree(s->d_ctrl); cudaFree(s->d_topk_list); cudaFree(s->d_match_w); cudaFree(s->d_match_d);
     cudaFree(s->d_match_k); cudaFree(s->d_pool_w); cudaFree(s->d_pool_d); cudaFree(s->d_pool_k); cudaFree(s->d_slab); cudaFree(s->d_out_k);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -1140,8 +1141,9 @@ extern "C" xgm_status xgm_searcher_new(const xgm_index* ix, uint32_t max_batch, 
     if (const char* e = getenv("XGM_OR_TILE")) s->or_tile = atoi(e) != 0;
     if (const char* e = getenv("XGM_BPI")) s->bpi_override = (uint32_t)std::min(32, std::max(0, atoi(e)));
     CUDA_TRY(cudaMalloc(&s->d_raise, nq * XGM_RAISE_LOG * sizeof(XgmRaise)));
-    s->ctrl_bytes = 64 + nq * sizeof(XgmQState) + nq * XGM_NBINS * 4;
+    s->ctrl_bytes = XGM_CTRL_HDR + nq * sizeof(XgmQState) + nq * XGM_NBINS * 4;
     CUDA_TRY(cudaMalloc(&s->d_ctrl, s->ctrl_bytes));
+    CUDA_TRY(cudaMalloc(&s->d_topk_list, (size_t)nq * 4));
     CUDA_TRY(cudaMalloc(&s->d_match_w, nm * 8)); CUDA_TRY(cudaMalloc(&s->d_match_d, nm * 4)); CUDA_TRY(cudaMalloc(&s->d_match_k, nm * 8));
     {
         auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
@@ -1676,7 +1678,7 @@ static xgm_status launch_batch(xgm_searcher* s) {
         lk.lock(); /* one batch's launches stay contiguous in the shared stream */
         CUDA_TRY(cudaStreamWaitEvent(cs, s->ev_in, 0));
     }
-    CUDA_TRY(cudaMemsetAsync(s->d_ctrl, 0, 64 + (size_t)s->max_batch * sizeof(XgmQState), cs));
+    CUDA_TRY(cudaMemsetAsync(s->d_ctrl, 0, XGM_CTRL_HDR + (size_t)s->max_batch * sizeof(XgmQState), cs));
     CUDA_TRY(cudaMemsetAsync(p.hist, 0, (size_t)s->nq * XGM_NBINS * 4, cs));
     s->stats.kernel_launches = 0;
     p.pass = 0;
@@ -1903,8 +1905,9 @@ static xgm_status submit_impl(xgm_searcher* s, const xgm_query* queries, uint32_
     p.items_bm = s->d_exp[2]; p.nitems_bm = s->nitems_bm;
     p.nitems_bm_dev = s->range_mode ? s->d_rng_total : nullptr;
     p.work_counter = reinterpret_cast<uint32_t*>(s->d_ctrl);
-    p.qstate = reinterpret_cast<XgmQState*>(s->d_ctrl + 64);
-    p.hist = reinterpret_cast<uint32_t*>(s->d_ctrl + 64 + (size_t)s->max_batch * sizeof(XgmQState));
+    p.qstate = reinterpret_cast<XgmQState*>(s->d_ctrl + XGM_CTRL_HDR);
+    p.hist = reinterpret_cast<uint32_t*>(s->d_ctrl + XGM_CTRL_HDR + (size_t)s->max_batch * sizeof(XgmQState));
+    p.topk_list = s->d_topk_list;
     p.match_cap = s->match_cap; p.keep_cap = s->keep_cap;
     p.pool_total = s->pool_total; p.pool_w = s->d_pool_w; p.pool_d = s->d_pool_d; p.pool_k = s->d_pool_k;
     p.match_w = s->d_match_w; p.match_d = s->d_match_d; p.match_k = s->d_match_k;
@@ -1949,7 +1952,7 @@ static xgm_status submit_impl(xgm_searcher* s, const xgm_query* queries, uint32_
     if (s->any_sort) CUDA_TRY(cudaMemcpyAsync(s->h_out_k, s->d_out_k, ns * 8, cudaMemcpyDeviceToHost, s->stream));
     if (s->any_raise) {
         CUDA_TRY(cudaMemcpyAsync(s->h_raise, s->d_raise, (size_t)nq * XGM_RAISE_LOG * sizeof(XgmRaise), cudaMemcpyDeviceToHost, s->stream));
-        CUDA_TRY(cudaMemcpyAsync(s->h_qstate, s->d_ctrl + 64, (size_t)nq * sizeof(XgmQState), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(s->h_qstate, s->d_ctrl + XGM_CTRL_HDR, (size_t)nq * sizeof(XgmQState), cudaMemcpyDeviceToHost, s->stream));
     }
     s->pending = true;
     s->stats.host_plan_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_submit0).count();

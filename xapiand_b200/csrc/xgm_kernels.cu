@@ -2430,9 +2430,8 @@ __device__ __forceinline__ void threshold_bin(const uint32_t* lh, uint32_t want,
  * Second pass: the slice holds every match at or above b*.  If a single bucket holds a mass of ties the
  * slice can be far larger than shared memory: an MSB-first radix select over the composite sort key
  * (8 bits per round, in global memory) finds the exact topk-th key, and only the topk winners are sorted. */
-__global__ void __launch_bounds__(TOPK_THREADS) xgm_topk_kernel(XgmKernelParams p) {
+__device__ __forceinline__ void topk_one_query(const XgmKernelParams& p, const uint32_t qi) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint32_t qi = blockIdx.x;
     const XgmDevQuery* q = &p.queries[qi];
     const XgmQState st = p.qstate[qi];
     if (p.pass != 0 && st.rerun == 0) return;
@@ -2817,6 +2816,89 @@ __global__ void __launch_bounds__(TOPK_THREADS) xgm_topk_kernel(XgmKernelParams 
     }
 }
 
+/* Queries whose whole match set is a handful of documents — the majority of a batch of selective ANDs (70 % of
+ * BASELINE's C2 queries match <= 32 documents) — do not need a CTA, 45 KB of shared memory and a dozen barriers:
+ * one warp ranks up to 64 unpruned relevance-ordered matches (two per lane, pair test against a 768-byte
+ * staging area) and every one of them is counted (n <= max(check_at_least, topk + 1): protomset.h:340-376).
+ * Everything else is appended to topk_list for xgm_topk_kernel. */
+#define TOPK_SMALL_WARPS 8
+#define TOPK_SMALL_MAX 64u
+__global__ void __launch_bounds__(TOPK_SMALL_WARPS * 32) xgm_topk_small_kernel(const __grid_constant__ XgmKernelParams p) {
+    __shared__ unsigned long long s_w[TOPK_SMALL_WARPS][TOPK_SMALL_MAX];
+    __shared__ uint32_t s_d[TOPK_SMALL_WARPS][TOPK_SMALL_MAX];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t qi = blockIdx.x * TOPK_SMALL_WARPS + warp;
+    if (qi >= p.nq) return;
+    const XgmDevQuery* q = &p.queries[qi];
+    const XgmQState st = p.qstate[qi];
+    const uint32_t topk = q->topk, n = st.stored;
+    const uint32_t free_count = q->check_at_least > topk + 1 ? q->check_at_least : topk + 1;
+    const bool small = q->sort_by == 0 && topk != 0 && n == st.total && st.skipped == 0 && n <= TOPK_SMALL_MAX &&
+                       n <= free_count && n <= p.match_cap;
+    if (!small) {
+        if (lane == 0) p.topk_list[atomicAdd(p.work_counter + 16, 1u)] = qi;
+        return;
+    }
+    const size_t qoff = (size_t)qi * p.match_cap, ooff = (size_t)qi * p.out_stride;
+    unsigned long long bw[2] = {0ull, 0ull}, kk[2] = {0ull, 0ull};
+    uint32_t dd[2] = {0u, 0u};
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const uint32_t i = lane + 32u * u;
+        if (i < n) {
+            bw[u] = (unsigned long long)__double_as_longlong(__ldcs(p.match_w + qoff + i));
+            dd[u] = __ldcs(p.match_d + qoff + i);
+            kk[u] = __ldcs(p.match_k + qoff + i);
+            s_w[warp][i] = bw[u];
+            s_d[warp][i] = dd[u];
+        }
+    }
+    __syncwarp();
+    uint32_t rank[2] = {0u, 0u};
+    for (uint32_t j = 0; j < n; ++j) { /* weights are >= +0 and never NaN: their bit patterns order like the values */
+        const unsigned long long bj = s_w[warp][j];
+        const uint32_t dj = s_d[warp][j];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) rank[u] += (uint32_t)(bj > bw[u]) | ((uint32_t)(bj == bw[u]) & (uint32_t)(dj < dd[u]));
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const uint32_t i = lane + 32u * u;
+        if (i < n && rank[u] < topk) {
+            p.out_w[ooff + rank[u]] = __longlong_as_double((long long)bw[u]);
+            p.out_d[ooff + rank[u]] = dd[u];
+            p.out_k[ooff + rank[u]] = kk[u];
+        }
+    }
+    if (lane == 0) {
+        XgmDevResult r;
+        r.n = n < topk ? n : topk;
+        r.exact = st.total;
+        r.known = n;
+        r.flags = 0;
+        r.max_w = __longlong_as_double((long long)st.maxw);
+        r.max_subqs = q->nweighted;
+        r.pad = 0;
+        p.out_info[qi] = r;
+    }
+}
+
+/* CTA per query, persistent: the CTAs take the listed queries (first pass, after xgm_topk_small_kernel) or all
+ * queries of the batch (no list; second pass) from a counter. */
+__global__ void __launch_bounds__(TOPK_THREADS) xgm_topk_kernel(XgmKernelParams p) {
+    __shared__ uint32_t s_slot;
+    const bool listed = p.topk_list != nullptr && p.pass == 0;
+    const uint32_t count = listed ? *reinterpret_cast<volatile uint32_t*>(p.work_counter + 16) : p.nq;
+    for (;;) {
+        __syncthreads(); /* the previous query's shared state is no longer read */
+        if (threadIdx.x == 0) s_slot = atomicAdd(p.work_counter + 17 + p.pass, 1u);
+        __syncthreads();
+        const uint32_t slot = s_slot;
+        if (slot >= count) break;
+        topk_one_query(p, listed ? p.topk_list[slot] : slot);
+    }
+}
+
 /* ------------------------------------------------------------------ multi-shard merge */
 
 /* Matcher::merge_mset (matcher.cc:653-782) on the device, after an all-gather of the per-GPU top-k
@@ -3116,7 +3198,23 @@ cudaError_t xgm_launch_topk(const XgmKernelParams& p, uint32_t nq, cudaStream_t 
         cudaError_t e = optin_smem((const void*)xgm_topk_kernel, 1, smem);
         if (e != cudaSuccess) return e;
     }
-    xgm_topk_kernel<<<nq, TOPK_THREADS, smem, s>>>(p);
+    XgmKernelParams pp = p;
+    pp.nq = nq;
+    /* first pass of a real batch: the few-match queries are ranked a warp each, the rest listed for the CTAs */
+    if (p.pass == 0 && nq >= 64 && p.topk_list != nullptr)
+        xgm_topk_small_kernel<<<(nq + TOPK_SMALL_WARPS - 1) / TOPK_SMALL_WARPS, TOPK_SMALL_WARPS * 32, 0, s>>>(pp);
+    else
+        pp.topk_list = nullptr;
+    static int ctas = 0; /* resident CTAs of the persistent kernel on this device class */
+    if (ctas == 0) {
+        int dev = 0, sms = 0, occ = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, xgm_topk_kernel, TOPK_THREADS, smem);
+        ctas = sms * (occ > 0 ? occ : 1);
+    }
+    const uint32_t grid = nq < (uint32_t)ctas ? nq : (uint32_t)ctas;
+    xgm_topk_kernel<<<grid, TOPK_THREADS, smem, s>>>(pp);
     return cudaGetLastError();
 }
 
