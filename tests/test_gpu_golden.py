@@ -218,6 +218,34 @@ def test_cuda_matches_reference_filter_andnot_andmaybe():
     assert checked == len(qs)
 
 
+def test_cuda_matches_reference_groups_around_or_base():
+    """OP_FILTER with boolean terms and OP_AND_NOT around an OR base (a free-text OR restricted / thinned by
+    boolean terms) against the compiled reference's MSets (orops_6k); optional leaves on an OR base are declined."""
+    fx = load("orops_6k")
+    ix = xgm.Index.synthetic(fx["ndocs"], fx["vocab"], fx["seed"])
+    name = lambda t: f"T{t:06d}"
+    qs = [xgm.Query(xgm.OP_OR, [name(t) for t in q["terms"]], first=q["first"], maxitems=q["maxitems"],
+                    check_at_least=q["check_at_least"], filter_terms=[name(t) for t in q["filter_terms"]],
+                    not_terms=[name(t) for t in q["not_terms"]], maybe_terms=[name(t) for t in q["maybe_terms"]])
+          for q in fx["queries"]]
+    res = xgm.Searcher(ix, max_batch=len(qs), max_topk=256).search(qs)
+    served = 0
+    for i, (q, m) in enumerate(zip(fx["queries"], res)):
+        ctx = f"orops[{i}] {q['terms']} F{q['filter_terms']} N{q['not_terms']} M{q['maybe_terms']}"
+        if q["maybe_terms"]:
+            assert m.status == xgm.E_UNIMPLEMENTED, ctx
+            continue
+        assert m.status == 0, ctx
+        assert list(m.docids) == q["docids"], ctx
+        assert all(bits(a) == bits(b) for a, b in zip(m.weights, q["weights"])), ctx
+        assert bits(m.max_possible) == bits(q["max_possible"]) and bits(m.max_attained) == bits(q["max_attained"]), ctx
+        assert m.matches_upper_bound == q["ub"], ctx
+        if not (m.flags & 1):
+            assert (m.matches_lower_bound, m.get_matches_estimated()) == (q["lb"], q["est"]), ctx
+        served += 1
+    assert served >= 120
+
+
 @pytest.mark.parametrize("tag", ["wqf_6k", "bm25_6k", "regimes_6k", "sortmodes_6k", "scale_6k"])
 def test_cuda_matches_reference_more_regimes(tag):
     """The fixtures added late in round 1 (within-query frequencies, non-default BM25 parameters, intermediate

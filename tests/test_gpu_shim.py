@@ -18,7 +18,7 @@ pytestmark = [pytest.mark.gpu,
                                  reason="compiled reference + shim variant (oracle/_ref) not shipped")]
 
 #            fixture           min. share of queries libxgm must answer itself
-FIXTURES = [("c1_1k_100", 0.95), ("mid_20k", 0.95), ("ops_6k", 0.9), ("scale_6k", 0.7), ("regimes_6k", 0.9),
+FIXTURES = [("c1_1k_100", 0.95), ("mid_20k", 0.95), ("ops_6k", 0.9), ("orops_6k", 0.5), ("scale_6k", 0.7), ("regimes_6k", 0.9),
             ("wqf_6k", 0.95), ("sortmodes_6k", 0.9), ("bm25_6k", 0.8), ("values_5k", 0.95), ("multivalue_5k", 0.95),
             ("shard4_20k", 0.95)]
 

@@ -72,7 +72,7 @@ struct XgmDevQuery {
     uint32_t src_pos;                   /* ... before the weight of required list src_pos (MultiAndPostList order);
                                            nterms = after all; XGM_NO_SRC = the source only filters */
     uint32_t or_fast;                   /* OR: every leaf has a membership bitmap and there are at most 5 → xgm_or3_kernel */
-    uint32_t pad2;
+    uint32_t or_nreq;                   /* OR under OP_FILTER: terms[nterms .. nterms+or_nreq) must hold the document, then nnot excluded ones */
     uint32_t log_raises;                /* record the matches that attain the running maximum weight (XGM_RAISE_LOG) */
     XgmDevTerm terms[XGM_DEV_MAX_TERMS]; /* AND: ascending termfreq (MultiAndPostList order) */
 };

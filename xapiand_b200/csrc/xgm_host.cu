@@ -1305,9 +1305,11 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
     if (q.op != XGM_OP_AND && q.op != XGM_OP_OR) { pq.status = XGM_E_UNIMPLEMENTED; return XGM_OK; }
     const uint32_t nfilter = q.nfilter, nnot = q.nnot, nmaybe = q.nmaybe, ngroups = q.nfilter + q.nnot + q.nmaybe;
     if (ngroups) {
-        /* OP_FILTER with boolean terms / OP_AND_NOT / OP_AND_MAYBE around an AND (or single-term) base; an OR
-         * base, a value-range filter on top, or the chunked kernel variant are left to the reference */
-        if ((q.op != XGM_OP_AND && q.nterms != 1) || q.filter != XGM_FILTER_NONE || s->and_version != 1 ||
+        /* OP_FILTER with boolean terms / OP_AND_NOT / OP_AND_MAYBE around an AND (or single-term) base, the first
+         * two also around an OR base; optional leaves on an OR base, a value-range filter on top, or the chunked
+         * kernel variant are left to the reference */
+        const bool or_base = q.op == XGM_OP_OR && q.nterms != 1;
+        if ((or_base && q.nmaybe) || q.filter != XGM_FILTER_NONE || s->and_version != 1 ||
             (uint64_t)q.nterms + ngroups > XGM_MAX_TERMS) {
             pq.status = XGM_E_UNIMPLEMENTED;
             return XGM_OK;
@@ -1385,8 +1387,57 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
     dq.src_pos = XGM_NO_SRC; dq.src_weight = 0.0;
     double dbsize = ix->doccount;
     uint32_t order[XGM_MAX_TERMS];
-    bool any_absent = false;
+    bool any_absent = false, group_absent = false;
     for (uint32_t j = 0; j < n; ++j) any_absent |= (ltf[j] == 0);
+    /* bounds of the nested tree around the base: MultiAnd(base, filter) → AndNot(…, OR of excluded) */
+    auto group_bounds = [&](TfNode cur) {
+        if (nfilter) {
+            /* QueryFilter::postlist: MultiAndPostList of [base, Query(OP_AND, boolean terms)] */
+            const uint32_t* ftf = ltf + n;
+            TfNode f{ftf[0], ftf[0], ftf[0]};
+            if (nfilter > 1) {
+                TfIdx fin[XGM_MAX_TERMS], fo[XGM_MAX_TERMS];
+                for (uint32_t j = 0; j < nfilter; ++j) { fin[j].tf = ftf[j]; fin[j].idx = j; }
+                std::partial_sort_copy(fin, fin + nfilter, fo, fo + nfilter, [](const TfIdx& a, const TfIdx& c) { return a.tf < c.tf; });
+                uint32_t fs = fo[0].tf;
+                if (fs) for (uint32_t i = 1; i < nfilter; ++i) {
+                    uint32_t old = fs; fs += fo[i].tf;
+                    if (fs >= old && fs <= ix->doccount) { fs = 0; break; }
+                    fs -= ix->doccount;
+                }
+                f.mn = fs;
+                f.mx = fo[0].tf;
+                for (uint32_t i = 1; i < nfilter; ++i) f.mx = std::min(f.mx, fo[i].tf);
+                double fr = fo[0].tf;
+                for (uint32_t i = 1; i < nfilter; ++i) fr = (fr * fo[i].tf) / dbsize;
+                f.est = ix->doccount ? (uint32_t)(fr + 0.5) : 0;
+            }
+            TfNode c0 = cur, c1 = f; /* children in ascending-estimate order */
+            if (f.est < cur.est) { c0 = f; c1 = cur; }
+            uint32_t ms = c0.mn;
+            if (ms) {
+                uint32_t old = ms; ms += c1.mn;
+                if (ms >= old && ms <= ix->doccount) ms = 0; else ms -= ix->doccount;
+            }
+            cur.mn = ms;
+            cur.mx = std::min(c0.mx, c1.mx);
+            cur.est = ix->doccount ? (uint32_t)(((double)c0.est * (double)c1.est) / dbsize + 0.5) : 0;
+        }
+        if (nnot) {
+            /* AndNotPostList::get_termfreq_min/max/est, matcher/andnotpostlist.cc:30-62 */
+            const TfNode rr = or_group_node(ltf + n + nfilter, nnot, ix->doccount);
+            const TfNode a = cur;
+            cur.mn = a.mn <= rr.mx ? 0 : a.mn - rr.mx;
+            cur.mx = std::min(ix->doccount - rr.mn, a.mx);
+            if (ix->doccount == 0) cur.est = 0;
+            else {
+                double e = a.est;
+                e = (e * (double)(ix->doccount - rr.est)) / dbsize;
+                cur.est = (uint32_t)(e + 0.5);
+            }
+        }
+        return cur;
+    };
     if (q.op == XGM_OP_AND || n == 1) {
         /* children of the MultiAndPostList: the base terms and, for a Xapiand range, its source — sorted by
          * get_termfreq_est with the very call of multiandpostlist.h:126-131 */
@@ -1447,53 +1498,7 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
         if (ngroups == 0) {
             for (uint32_t i = 0; i < n; ++i) put_term(i, order[i], true);
         } else {
-            /* bounds of the nested tree: MultiAnd(base, filter) → AndNot(…, OR of excluded) */
-            TfNode cur{pq.tf_min, pq.tf_max, pq.tf_est};
-            if (nfilter) {
-                /* QueryFilter::postlist: MultiAndPostList of [base, Query(OP_AND, boolean terms)] */
-                const uint32_t* ftf = ltf + n;
-                TfNode f{ftf[0], ftf[0], ftf[0]};
-                if (nfilter > 1) {
-                    TfIdx fin[XGM_MAX_TERMS], fo[XGM_MAX_TERMS];
-                    for (uint32_t j = 0; j < nfilter; ++j) { fin[j].tf = ftf[j]; fin[j].idx = j; }
-                    std::partial_sort_copy(fin, fin + nfilter, fo, fo + nfilter, [](const TfIdx& a, const TfIdx& c) { return a.tf < c.tf; });
-                    uint32_t fs = fo[0].tf;
-                    if (fs) for (uint32_t i = 1; i < nfilter; ++i) {
-                        uint32_t old = fs; fs += fo[i].tf;
-                        if (fs >= old && fs <= ix->doccount) { fs = 0; break; }
-                        fs -= ix->doccount;
-                    }
-                    f.mn = fs;
-                    f.mx = fo[0].tf;
-                    for (uint32_t i = 1; i < nfilter; ++i) f.mx = std::min(f.mx, fo[i].tf);
-                    double fr = fo[0].tf;
-                    for (uint32_t i = 1; i < nfilter; ++i) fr = (fr * fo[i].tf) / dbsize;
-                    f.est = ix->doccount ? (uint32_t)(fr + 0.5) : 0;
-                }
-                TfNode c0 = cur, c1 = f; /* children in ascending-estimate order */
-                if (f.est < cur.est) { c0 = f; c1 = cur; }
-                uint32_t ms = c0.mn;
-                if (ms) {
-                    uint32_t old = ms; ms += c1.mn;
-                    if (ms >= old && ms <= ix->doccount) ms = 0; else ms -= ix->doccount;
-                }
-                cur.mn = ms;
-                cur.mx = std::min(c0.mx, c1.mx);
-                cur.est = ix->doccount ? (uint32_t)(((double)c0.est * (double)c1.est) / dbsize + 0.5) : 0;
-            }
-            if (nnot) {
-                /* AndNotPostList::get_termfreq_min/max/est, matcher/andnotpostlist.cc:30-62 */
-                const TfNode rr = or_group_node(ltf + n + nfilter, nnot, ix->doccount);
-                const TfNode a = cur;
-                cur.mn = a.mn <= rr.mx ? 0 : a.mn - rr.mx;
-                cur.mx = std::min(ix->doccount - rr.mn, a.mx);
-                if (ix->doccount == 0) cur.est = 0;
-                else {
-                    double e = a.est;
-                    e = (e * (double)(ix->doccount - rr.est)) / dbsize;
-                    cur.est = (uint32_t)(e + 0.5);
-                }
-            }
+            const TfNode cur = group_bounds(TfNode{pq.tf_min, pq.tf_max, pq.tf_est});
             pq.tf_min = cur.mn; pq.tf_max = cur.mx; pq.tf_est = cur.est;
             /* device lists: required = base (its own MultiAndPostList order, which fixes the order of the
              * weight sum) merged with the boolean filter terms by ascending termfreq; then the excluded lists
@@ -1604,17 +1609,37 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
         pq.max_possible = sm[0]; pq.tf_min = smin[0]; pq.tf_max = smax[0]; pq.tf_est = (uint32_t)se[0];
         pq.bucket_max = pq.max_possible;
         dq.route = 1;
-        for (uint32_t i = 0; i < n; ++i) {
-            uint32_t j = order[i];
-            dq.terms[i].termweight = tw[j];
-            dq.terms[i].maxpart = maxpart[j];
-            dq.terms[i].bm_off = XGM_NO_BITMAP; dq.terms[i].rk_off = 0;
-            dq.terms[i].blk_begin = 0; dq.terms[i].nblocks = 0;
+        auto put_leaf = [&](uint32_t slot, uint32_t j, bool weighted) {
+            dq.terms[slot].termweight = weighted ? tw[j] : 0.0;
+            dq.terms[slot].maxpart = weighted ? maxpart[j] : 0.0;
+            dq.terms[slot].bm_off = XGM_NO_BITMAP; dq.terms[slot].rk_off = 0;
+            dq.terms[slot].blk_begin = 0; dq.terms[slot].nblocks = 0;
             if (ids[j] != 0xffffffffu) {
                 const TermInfo& tinf = ix->terms[ids[j]];
-                dq.terms[i].blk_begin = tinf.blk_begin; dq.terms[i].nblocks = tinf.nblocks;
-                dq.terms[i].bm_off = tinf.bm_off; dq.terms[i].rk_off = tinf.rk_off;
+                dq.terms[slot].blk_begin = tinf.blk_begin; dq.terms[slot].nblocks = tinf.nblocks;
+                dq.terms[slot].bm_off = tinf.bm_off; dq.terms[slot].rk_off = tinf.rk_off;
             }
+        };
+        for (uint32_t i = 0; i < n; ++i) put_leaf(i, order[i], true);
+        if (ngroups) {
+            /* QueryFilter / QueryAndNot above the OrPostList tree: the filter's boolean terms and the excluded
+             * terms weigh nothing (MultiAndPostList::get_weight adds +0.0, AndNotPostList returns the left's
+             * weight), so a match keeps the tree's weight; the counts follow the same bound arithmetic as around
+             * an AND base.  The device keeps them behind the leaves: terms[n .. n + or_nreq) must hold the
+             * document, terms[n + or_nreq .. + nnot) must not. */
+            const TfNode cur = group_bounds(TfNode{pq.tf_min, pq.tf_max, pq.tf_est});
+            pq.tf_min = cur.mn; pq.tf_max = cur.mx; pq.tf_est = cur.est;
+            dq.nterms = n;
+            uint32_t slot = n;
+            for (uint32_t j = 0; j < nfilter; ++j) { put_leaf(slot++, n + j, false); group_absent |= (ltf[n + j] == 0); }
+            dq.or_nreq = nfilter;
+            uint32_t kept = 0;
+            for (uint32_t j = 0; j < nnot; ++j) {
+                if (ltf[n + nfilter + j] == 0) continue; /* nothing to exclude */
+                put_leaf(slot++, n + nfilter + j, false);
+                ++kept;
+            }
+            dq.nnot = kept;
         }
     }
     /* algorithmic bytes, SURVEY.md §8(d): compressed columns + 16 B per block header of every query
@@ -1641,6 +1666,7 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
     pq.log_raises = dq.log_raises != 0;
     if (cal == 0) { pq.on_device = false; return XGM_OK; } /* bounds only, matcher.cc:437-461 */
     if (dq.route == 0 && any_absent) { pq.on_device = false; return XGM_OK; } /* AND with an absent term: empty */
+    if (dq.route == 1 && group_absent) { pq.on_device = false; return XGM_OK; } /* OR filtered by an absent term: empty */
     pq.on_device = true;
     /* one segment per (query[, leaf]); the device expands segments into work items (xgm_expand_items_kernel) */
     (void)blocks_per_item;
@@ -1653,7 +1679,7 @@ static xgm_status plan_query(xgm_searcher* s, const xgm_query& q, uint32_t qi, P
         wi.query = qi; wi.b0 = dq.terms[0].nblocks; wi.b1 = 0; wi.pad = 0;
         if (wi.b0) dst.push_back(wi);
     } else {
-        bool fastor = n <= 5 && !(getenv("XGM_OR_KERNEL") && atoi(getenv("XGM_OR_KERNEL")) == 1);
+        bool fastor = n <= 5 && ngroups == 0 && !(getenv("XGM_OR_KERNEL") && atoi(getenv("XGM_OR_KERNEL")) == 1);
         for (uint32_t leaf = 0; leaf < n; ++leaf) fastor = fastor && dq.terms[leaf].bm_off != XGM_NO_BITMAP;
         /* relevance order, no predicate, results wanted: multi-leaf documents by bitmap union first (or_fast 2) */
         dq.or_fast = !fastor ? 0u : (s->or_tile && q.filter == XGM_FILTER_NONE && q.sort_by == XGM_SORT_REL && dq.topk != 0) ? 2u : 1u;

@@ -1809,6 +1809,20 @@ __global__ void __launch_bounds__(OR_WARPS * 32) xgm_or_kernel(XgmKernelParams p
                 for (int k = 0; k < 4; ++k)
                     if ((owned >> k & 1u) && !doc_passes_filter(p, q, c[k])) owned &= ~(1u << k);
             }
+            if (q->or_nreq | q->nnot) {
+                /* OP_FILTER's boolean terms / OP_AND_NOT's excluded terms above the OR: a document of the union
+                 * that fails them is not a match at all (neither counted nor scored) */
+                const uint32_t nreq = q->or_nreq, nnot = q->nnot;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (!(owned >> k & 1u)) continue;
+                    bool keep = true;
+                    uint32_t wdf_unused;
+                    for (uint32_t i = 0; i < nreq && keep; ++i) keep = lookup_posting(p, q->terms[nterms + i], c[k], &wdf_unused);
+                    for (uint32_t i = 0; i < nnot && keep; ++i) keep = !lookup_posting(p, q->terms[nterms + nreq + i], c[k], &wdf_unused);
+                    if (!keep) owned &= ~(1u << k);
+                }
+            }
             /* MaxScore: can the leaves present reach the current threshold at all? */
             uint32_t skip = 0;
             if (can_prune) {
@@ -2645,23 +2659,83 @@ __device__ __forceinline__ void topk_one_query(const XgmKernelParams& p, const u
                 if (posd <= r_raise || gt < topk) ++known;
             }
         } else if (need_counts) {
-            /* n <= XGM_EXACT_COUNT_MAX.  Sort the survivors by docid (bitonic, in shared memory): "earlier in
-             * docid order" becomes "smaller index", so `before` is the index itself and each pair costs one
-             * or two f64 compares instead of the three-counter test on unsorted data. */
-            uint32_t P = 32;
+            /* 256 < n <= XGM_EXACT_COUNT_MAX.  Put the survivors in docid order first: "earlier in docid order"
+             * becomes "smaller index".  Only 8-byte keys (docid << 10 | index) are sorted — 32 at a time in
+             * registers (one warp, shuffles, no barrier), then log2(P / 32) merge passes in shared memory, each
+             * element finding its place by one binary search in the other run — and the records are gathered
+             * once.  (A bitonic sort of the 20-byte records took 55 barrier-separated passes for P = 1024 and
+             * two thirds of this path's time.) */
+            uint32_t P = 512;
             while (P < n) P <<= 1;
-            for (uint32_t t = n + tid; t < P; t += TOPK_THREADS) { sd[t] = 0xffffffffu; sw[t] = 0.0; sk[t] = 0; }
-            __syncthreads();
-            bitonic_sort_candidates<true>(sw, sk, sd, P, tid);
+            {
+                uint64_t* ksrc = reinterpret_cast<uint64_t*>(sw + P); /* the upper halves are free: 2P <= keep_cap */
+                uint64_t* kdst = sk + P;
+                const uint32_t lane = tid & 31u, warp = tid >> 5;
+                for (uint32_t c = warp; c < P / 32u; c += TOPK_THREADS / 32u) {
+                    const uint32_t i = c * 32u + lane;
+                    uint64_t key = i < n ? ((uint64_t)sd[i] << 10) | i : ~0ull;
+#pragma unroll
+                    for (uint32_t k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+                        for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
+                            const uint64_t other = __shfl_xor_sync(FULL, key, j);
+                            const bool keep_min = ((lane & j) == 0) == ((lane & k2) == 0);
+                            key = keep_min ? (key < other ? key : other) : (key < other ? other : key);
+                        }
+                    }
+                    ksrc[i] = key;
+                }
+                __syncthreads();
+                for (uint32_t L = 32; L < P; L <<= 1) {
+                    for (uint32_t t = tid; t < P; t += TOPK_THREADS) {
+                        const uint32_t base = t & ~(2u * L - 1u), off = t - base;
+                        const uint64_t key = ksrc[t];
+                        uint32_t lo = 0, hi = L, pos;
+                        if (off < L) { /* run A: the b's strictly smaller go first */
+                            const uint64_t* o = ksrc + base + L;
+                            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (o[mid] < key) lo = mid + 1; else hi = mid; }
+                            pos = base + off + lo;
+                        } else {       /* run B: the a's not larger go first (only the padding keys are equal) */
+                            const uint64_t* o = ksrc + base;
+                            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (o[mid] <= key) lo = mid + 1; else hi = mid; }
+                            pos = base + (off - L) + lo;
+                        }
+                        kdst[pos] = key;
+                    }
+                    __syncthreads();
+                    uint64_t* tk_ = ksrc; ksrc = kdst; kdst = tk_;
+                }
+                /* gather: P / 256 <= 4 records per thread travel through registers into docid order; the
+                 * per-element state of the merge below goes into the aux word: aux (8 bits) | docid-order position
+                 * (11) | greater-before (11) | not-less-before (11) */
+                double gw[4];
+                uint64_t ga[4];
+                uint32_t gd[4];
+#pragma unroll
+                for (uint32_t x = 0; x < 4; ++x) {
+                    const uint32_t t = tid + x * TOPK_THREADS;
+                    gw[x] = 0.0; ga[x] = 0; gd[x] = 0xffffffffu;
+                    if (t < P) {
+                        const uint64_t key = ksrc[t];
+                        if (key != ~0ull) {
+                            const uint32_t i = (uint32_t)key & 1023u;
+                            gw[x] = sw[i]; ga[x] = sk[i] & 0xffull; gd[x] = (uint32_t)(key >> 10);
+                        }
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (uint32_t x = 0; x < 4; ++x) {
+                    const uint32_t t = tid + x * TOPK_THREADS;
+                    if (t < P) { sw[t] = gw[x]; sk[t] = ga[x] | ((uint64_t)t << 8); sd[t] = gd[x]; }
+                }
+                __syncthreads();
+            }
             /* Bottom-up merge sort by (weight desc, docid asc) of the docid-ordered survivors.  While run A
              * (earlier docids) is merged with run B, every b in B learns how many a in A are strictly greater
              * ("earlier and greater", ProtoMSet's min_weight test) and how many are not smaller; the merged
              * position of an element is its index in its run plus one binary search in the other run.  After
-             * log2(P) passes the array is the ranked MSet.  O(n log^2 n) instead of the n^2 pair test.
-             * The per-element state travels in the aux word: aux (8 bits) | docid-order position (11) |
-             * greater-before (11) | not-less-before (11). */
-            for (uint32_t t = tid; t < P; t += TOPK_THREADS) sk[t] = (sk[t] & 0xffull) | ((uint64_t)t << 8);
-            __syncthreads();
+             * log2(P) passes the array is the ranked MSet.  O(n log^2 n) instead of the n^2 pair test. */
             double* w_src = sw; double* w_dst = sw + P;
             uint64_t* k_src = sk; uint64_t* k_dst = sk + P;
             uint32_t* d_src = sd; uint32_t* d_dst = sd + P;
@@ -2691,7 +2765,8 @@ __device__ __forceinline__ void topk_one_query(const XgmKernelParams& p, const u
                     d_dst[pos] = d_src[t];
                     k_dst[pos] = st8;
                 }
-                __syncthreads();
+                /* a warp owns whole 32-element groups (t = tid + 256 x), so the passes inside a group need no CTA barrier */
+                if (L < 16) __syncwarp(); else __syncthreads();
                 double* tw_ = w_src; w_src = w_dst; w_dst = tw_;
                 uint64_t* tk_ = k_src; k_src = k_dst; k_dst = tk_;
                 uint32_t* td_ = d_src; d_src = d_dst; d_dst = td_;
