@@ -66,8 +66,9 @@ struct XgmKernelParams {
     XgmRaise* raise_log;          /* [nq][XGM_RAISE_LOG] */
     const uint32_t* tileq;        /* queries answered by xgm_or_tile_kernel + xgm_or3_kernel<PHASE 1> */
     uint32_t ntileq;
-    /* top-k: queries xgm_topk_small_kernel left to xgm_topk_kernel (count in work_counter[16]); null = every
-     * query of the batch.  work_counter[17 + pass] hands the entries out. */
+    /* top-k: queries xgm_topk_small_kernel left to xgm_topk_kernel (work_counter[16] expensive ones from the front
+     * of the list, [19] others from its back); null = every query of the batch.  work_counter[17 + pass] hands the
+     * entries out. */
     uint32_t* topk_list;
 };
 #define XGM_CTRL_HDR 128 /* bytes of work counters in front of the per-query state */

@@ -2686,21 +2686,36 @@ __device__ __forceinline__ void topk_one_query(const XgmKernelParams& p, const u
                     ksrc[i] = key;
                 }
                 __syncthreads();
+                const uint32_t nx = P / TOPK_THREADS; /* 2 or 4 elements per thread */
                 for (uint32_t L = 32; L < P; L <<= 1) {
-                    for (uint32_t t = tid; t < P; t += TOPK_THREADS) {
-                        const uint32_t base = t & ~(2u * L - 1u), off = t - base;
-                        const uint64_t key = ksrc[t];
-                        uint32_t lo = 0, hi = L, pos;
-                        if (off < L) { /* run A: the b's strictly smaller go first */
-                            const uint64_t* o = ksrc + base + L;
-                            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (o[mid] < key) lo = mid + 1; else hi = mid; }
-                            pos = base + off + lo;
-                        } else {       /* run B: the a's not larger go first (only the padding keys are equal) */
-                            const uint64_t* o = ksrc + base;
-                            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (o[mid] <= key) lo = mid + 1; else hi = mid; }
-                            pos = base + (off - L) + lo;
+                    /* the searches of a thread's elements run in lockstep — fixed trip count, no branches — so
+                     * that their dependent shared-memory probes overlap instead of queueing one behind the other */
+                    uint64_t key[4];
+                    const uint64_t* o[4];
+                    uint32_t dstb[4], cnt[4];
+                    bool isb[4];
+#pragma unroll
+                    for (uint32_t x = 0; x < 4; ++x) {
+                        const uint32_t t = tid + x * TOPK_THREADS, tt = x < nx ? t : tid;
+                        const uint32_t base = tt & ~(2u * L - 1u), off = tt - base;
+                        key[x] = ksrc[tt];
+                        isb[x] = off >= L;
+                        o[x] = ksrc + base + (isb[x] ? 0u : L);
+                        dstb[x] = base + (isb[x] ? off - L : off);
+                        cnt[x] = 0;
+                    }
+                    for (uint32_t step = L >> 1; step > 0; step >>= 1) {
+#pragma unroll
+                        for (uint32_t x = 0; x < 4; ++x) {
+                            const uint64_t e = o[x][cnt[x] + step - 1u];
+                            if (isb[x] ? e <= key[x] : e < key[x]) cnt[x] += step; /* A: b's strictly smaller; B: a's not larger */
                         }
-                        kdst[pos] = key;
+                    }
+#pragma unroll
+                    for (uint32_t x = 0; x < 4; ++x) {
+                        const uint64_t e = o[x][cnt[x]];
+                        if (isb[x] ? e <= key[x] : e < key[x]) ++cnt[x];
+                        if (x < nx) kdst[dstb[x] + cnt[x]] = key[x];
                     }
                     __syncthreads();
                     uint64_t* tk_ = ksrc; ksrc = kdst; kdst = tk_;
@@ -2739,31 +2754,45 @@ __device__ __forceinline__ void topk_one_query(const XgmKernelParams& p, const u
             double* w_src = sw; double* w_dst = sw + P;
             uint64_t* k_src = sk; uint64_t* k_dst = sk + P;
             uint32_t* d_src = sd; uint32_t* d_dst = sd + P;
+            const uint32_t nx = P / TOPK_THREADS;
             for (uint32_t L = 1; L < P; L <<= 1) {
-                for (uint32_t t = tid; t < P; t += TOPK_THREADS) {
-                    const uint32_t base = t & ~(2u * L - 1u), off = t - base;
-                    const uint64_t bi = wbits(w_src[t]);
-                    uint64_t st8 = k_src[t];
-                    uint32_t pos;
-                    if (off < L) { /* element of run A: the b's strictly greater go first */
-                        const uint64_t* o = reinterpret_cast<const uint64_t*>(w_src) + base + L;
-                        uint32_t lo = 0, hi = L;
-                        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (o[mid] > bi) lo = mid + 1; else hi = mid; }
-                        pos = base + off + lo;
-                    } else {       /* element of run B: the a's that are not smaller go first */
-                        const uint64_t* o = reinterpret_cast<const uint64_t*>(w_src) + base;
-                        uint32_t lo = 0, hi = L;
-                        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (o[mid] > bi) lo = mid + 1; else hi = mid; }
-                        const uint32_t greater = lo;
-                        hi = L;
-                        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (o[mid] >= bi) lo = mid + 1; else hi = mid; }
-                        const uint32_t notless = lo;
-                        pos = base + (off - L) + notless;
-                        st8 += ((uint64_t)greater << 19) + ((uint64_t)notless << 30);
+                /* as above: the elements of a thread search in lockstep.  Run A counts the b's strictly greater; run
+                 * B counts the a's strictly greater (its "greater before") and the a's not smaller (its place) */
+                uint64_t bi[4], st8[4];
+                const uint64_t* o[4];
+                uint32_t dstb[4], cgt[4], cge[4], dd[4];
+                bool isb[4];
+#pragma unroll
+                for (uint32_t x = 0; x < 4; ++x) {
+                    const uint32_t t = tid + x * TOPK_THREADS, tt = x < nx ? t : tid;
+                    const uint32_t base = tt & ~(2u * L - 1u), off = tt - base;
+                    bi[x] = wbits(w_src[tt]);
+                    st8[x] = k_src[tt];
+                    dd[x] = d_src[tt];
+                    isb[x] = off >= L;
+                    o[x] = reinterpret_cast<const uint64_t*>(w_src) + base + (isb[x] ? 0u : L);
+                    dstb[x] = base + (isb[x] ? off - L : off);
+                    cgt[x] = 0; cge[x] = 0;
+                }
+                for (uint32_t step = L >> 1; step > 0; step >>= 1) {
+#pragma unroll
+                    for (uint32_t x = 0; x < 4; ++x) {
+                        const uint64_t e1 = o[x][cgt[x] + step - 1u], e2 = o[x][cge[x] + step - 1u];
+                        if (e1 > bi[x]) cgt[x] += step;
+                        if (e2 >= bi[x]) cge[x] += step;
                     }
-                    w_dst[pos] = w_src[t];
-                    d_dst[pos] = d_src[t];
-                    k_dst[pos] = st8;
+                }
+#pragma unroll
+                for (uint32_t x = 0; x < 4; ++x) {
+                    if (o[x][cgt[x]] > bi[x]) ++cgt[x];
+                    if (o[x][cge[x]] >= bi[x]) ++cge[x];
+                    if (x < nx) {
+                        const uint32_t pos = dstb[x] + (isb[x] ? cge[x] : cgt[x]);
+                        if (isb[x]) st8[x] += ((uint64_t)cgt[x] << 19) + ((uint64_t)cge[x] << 30);
+                        reinterpret_cast<uint64_t*>(w_dst)[pos] = bi[x];
+                        d_dst[pos] = dd[x];
+                        k_dst[pos] = st8[x];
+                    }
                 }
                 /* a warp owns whole 32-element groups (t = tid + 256 x), so the passes inside a group need no CTA barrier */
                 if (L < 16) __syncwarp(); else __syncthreads();
@@ -2895,7 +2924,7 @@ __device__ __forceinline__ void topk_one_query(const XgmKernelParams& p, const u
  * BASELINE's C2 queries match <= 32 documents) — do not need a CTA, 45 KB of shared memory and a dozen barriers:
  * one warp ranks up to 64 unpruned relevance-ordered matches (two per lane, pair test against a 768-byte
  * staging area) and every one of them is counted (n <= max(check_at_least, topk + 1): protomset.h:340-376).
- * Everything else is appended to topk_list for xgm_topk_kernel. */
+ * Everything else is put on topk_list for xgm_topk_kernel (work_counter[16] entries from the front, [19] from the back). */
 #define TOPK_SMALL_WARPS 8
 #define TOPK_SMALL_MAX 64u
 __global__ void __launch_bounds__(TOPK_SMALL_WARPS * 32) xgm_topk_small_kernel(const __grid_constant__ XgmKernelParams p) {
@@ -2911,7 +2940,12 @@ __global__ void __launch_bounds__(TOPK_SMALL_WARPS * 32) xgm_topk_small_kernel(c
     const bool small = q->sort_by == 0 && topk != 0 && n == st.total && st.skipped == 0 && n <= TOPK_SMALL_MAX &&
                        n <= free_count && n <= p.match_cap;
     if (!small) {
-        if (lane == 0) p.topk_list[atomicAdd(p.work_counter + 16, 1u)] = qi;
+        /* longest first: the queries whose exact count needs the sorts (more than 256 stored matches) fill the
+         * list from the front, the others from the back, and the CTAs take the front first */
+        if (lane == 0) {
+            if (n > TOPK_THREADS) p.topk_list[atomicAdd(p.work_counter + 16, 1u)] = qi;
+            else p.topk_list[p.nq - 1u - atomicAdd(p.work_counter + 19, 1u)] = qi;
+        }
         return;
     }
     const size_t qoff = (size_t)qi * p.match_cap, ooff = (size_t)qi * p.out_stride;
@@ -2963,14 +2997,15 @@ __global__ void __launch_bounds__(TOPK_SMALL_WARPS * 32) xgm_topk_small_kernel(c
 __global__ void __launch_bounds__(TOPK_THREADS) xgm_topk_kernel(XgmKernelParams p) {
     __shared__ uint32_t s_slot;
     const bool listed = p.topk_list != nullptr && p.pass == 0;
-    const uint32_t count = listed ? *reinterpret_cast<volatile uint32_t*>(p.work_counter + 16) : p.nq;
+    const uint32_t nfront = listed ? *reinterpret_cast<volatile uint32_t*>(p.work_counter + 16) : p.nq;
+    const uint32_t count = nfront + (listed ? *reinterpret_cast<volatile uint32_t*>(p.work_counter + 19) : 0u);
     for (;;) {
         __syncthreads(); /* the previous query's shared state is no longer read */
         if (threadIdx.x == 0) s_slot = atomicAdd(p.work_counter + 17 + p.pass, 1u);
         __syncthreads();
         const uint32_t slot = s_slot;
         if (slot >= count) break;
-        topk_one_query(p, listed ? p.topk_list[slot] : slot);
+        topk_one_query(p, !listed ? slot : slot < nfront ? p.topk_list[slot] : p.topk_list[p.nq - 1u - (slot - nfront)]);
     }
 }
 
