@@ -2996,6 +2996,7 @@ __global__ void __launch_bounds__(TOPK_SMALL_WARPS * 32) xgm_topk_small_kernel(c
  * queries of the batch (no list; second pass) from a counter. */
 __global__ void __launch_bounds__(TOPK_THREADS) xgm_topk_kernel(XgmKernelParams p) {
     __shared__ uint32_t s_slot;
+    if (p.pass != 0 && *reinterpret_cast<volatile uint32_t*>(p.work_counter + 4) == 0) return; /* nothing to re-run */
     const bool listed = p.topk_list != nullptr && p.pass == 0;
     const uint32_t nfront = listed ? *reinterpret_cast<volatile uint32_t*>(p.work_counter + 16) : p.nq;
     const uint32_t count = nfront + (listed ? *reinterpret_cast<volatile uint32_t*>(p.work_counter + 19) : 0u);
