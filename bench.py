@@ -445,34 +445,62 @@ def ours(args):
         term_idx = [np.array([q[0] for q in qs], np.int64) for qs in raw]
         for b in batches:
             b.attach_global_stats()
-        # the sums are host data on both sides (term dictionary in, planner out): a CPU (gloo) group carries this
-        # one small all-reduce, so that it is not queued behind the result exchanges of earlier batches on the NCCL
-        # communicator (which would tie the host to the GPU's progress)
-        stats_pg = dist.new_group(backend="gloo")
+        # the sums are host data on both sides (term dictionary in, planner out) and 8 KB per batch.  On the NCCL
+        # communicator the exchange queued behind the result exchanges of earlier batches (0.8 ms); a gloo all-reduce
+        # between 8 local processes took 2.4 ms.  The ranks of one node exchange through shared memory instead
+        # (xapiand_b200/shm_exchange.py, ~20 us); ranks on several nodes (or XGM_BENCH_STATS=gloo) keep the gloo group.
+        one_node = int(os.environ.get("LOCAL_WORLD_SIZE", world)) == world
+        use_shm = one_node and os.environ.get("XGM_BENCH_STATS", "shm") == "shm"
+        stats_pg = None if use_shm else dist.new_group(backend="gloo")
+        shm = None
+        if use_shm:
+            from xapiand_b200.shm_exchange import ShmExchange
+            shm_name = f"xgm_p1_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}"
+            if rank == 0:
+                shm = ShmExchange(shm_name, 0, world, TOPRANKS + 2, create=True)
+            dist.barrier()
+            if rank != 0:
+                shm = ShmExchange(shm_name, rank, world, TOPRANKS + 2)
+            dist.barrier()
 
         pending_stats = {}
+        next_xid = [0]
 
-        def start_stats(bi: int):
-            """Phase 1 of batch bi, first half: local termfreqs (one C call) and the all-reduce, left in flight."""
-            if bi in pending_stats or bi >= nbatches:
-                return
-            buf = torch.zeros(TOPRANKS + 2, dtype=torch.int64)
-            a = buf.numpy()
+        def local_stats():
+            a = np.empty(TOPRANKS + 2, np.int64)
             a[:TOPRANKS] = lookup()
             a[TOPRANKS] = int(info.doccount)
             a[TOPRANKS + 1] = int(info.total_length)
-            pending_stats[bi] = (buf, dist.all_reduce(buf, group=stats_pg, async_op=True))
+            return a
+
+        def start_stats(bi: int):
+            """Phase 1 of batch bi, first half: local termfreqs (one C call) posted / the all-reduce left in flight."""
+            if bi in pending_stats or bi >= nbatches:
+                return
+            if use_shm:
+                xid = next_xid[0]
+                next_xid[0] += 1
+                shm.post(xid, local_stats())
+                pending_stats[bi] = xid
+            else:
+                buf = torch.from_numpy(local_stats())
+                pending_stats[bi] = (buf, dist.all_reduce(buf, group=stats_pg, async_op=True))
 
         def exchange_stats(bi: int):
             """Second half: wait for the sums and write them into the batch's statistics blocks.  The exchange of
             batch bi + 1 is started before returning, so that it overlaps the planning and matching of batch bi."""
             start_stats(bi)
-            buf, work = pending_stats.pop(bi)
-            work.wait()
-            a = buf.numpy()
+            if use_shm:
+                a = shm.collect(pending_stats.pop(bi))
+            else:
+                buf, work = pending_stats.pop(bi)
+                work.wait()
+                a = buf.numpy()
             batches[bi].set_global_stats(int(a[TOPRANKS]), int(a[TOPRANKS + 1]), a[:TOPRANKS][term_idx[bi]].astype(np.uint32))
             start_stats(bi + 1)
     else:
+        shm = None
+
         def exchange_stats(bi: int):
             return None
 
@@ -705,6 +733,7 @@ def ours(args):
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms_per_launch": kern_ms},
             "step_breakdown_ms": step_parts, "step_bound_by": bound, "host_cpus": host_cpus,
+            "stats_exchange_via": None if world == 1 else ("shared memory (one node)" if use_shm else "gloo all-reduce"),
             "bounds_approx_fraction": approx0 / BATCH,
             "clocks": clocks}
 
@@ -728,6 +757,9 @@ def ours(args):
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        if shm is not None:
+            dist.barrier()
+            shm.close()  # rank 0 removes the /dev/shm file
         dist.destroy_process_group()
     return 0
 
