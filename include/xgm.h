@@ -196,7 +196,8 @@ typedef struct xgm_query {
     uint32_t filter, filter_slot;
     uint64_t range_lo, range_hi;
     uint32_t sort_by, sort_slot, sort_reverse, sort_use_max; /* sort_use_max: key = largest value of the slot */
-    /* Term groups around an XGM_OP_AND (or single-term) base, innermost first.  Their
+    /* Term groups around the base, innermost first: all three around an XGM_OP_AND or
+     * single-term base, nfilter and nnot also around an XGM_OP_OR base (nmaybe there: XGM_E_UNIMPLEMENTED).  Their
      * terms follow the nterms base terms in terms / term_lens / term_ids (and stats->termfreq):
      *   nfilter  OP_FILTER(base, AND of boolean terms)   QueryFilter::postlist   api/queryinternal.cc:2270-2283
      *   nnot     OP_AND_NOT(…, OR of terms)              QueryAndNot::postlist   api/queryinternal.cc:2208-2225,
