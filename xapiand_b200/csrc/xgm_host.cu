@@ -1745,7 +1745,7 @@ static xgm_status launch_batch(xgm_searcher* s) {
     }
     CUDA_TRY(cudaEventRecord(s->ev1, cs));
     CUDA_TRY(xgm_launch_topk(p, s->nq, cs));
-    s->stats.kernel_launches++;
+    s->stats.kernel_launches += (s->nq >= 64 && p.topk_list) ? 2 : 1; /* xgm_topk_small_kernel + xgm_topk_kernel */
     /* second pass: only queries whose candidate buffer overflowed do any work (device-side flag) */
     XgmKernelParams p2 = p;
     p2.pass = 1;

@@ -7,7 +7,8 @@
            merger.merge_mset(...)                                          → one all-gather + merge
 
 Works with any backend (NCCL on GPUs, gloo in the CPU tests); the device-resident variant used for the
-throughput numbers lives in bench.py (all_gather_into_tensor + xgm_merge_topk_device).
+throughput numbers lives in bench.py (statistics through xapiand_b200/shm_exchange.py on one node, one all-to-all of
+per-query-slice top-k + xgm_merge_topk_device).
 """
 from __future__ import annotations
 
